@@ -1,0 +1,164 @@
+"""CPU tests: pin the oracle against the reference's golden vectors and live outputs."""
+
+import numpy as np
+import pytest
+
+from oracle import sknnr_oracle as orc
+from tests.conftest import FLOAT_CASES, load_golden, state_from_golden, yaimpute_weights
+
+# The reference forms d^2 from the float64 expansion |x|^2 - 2x.y + |y|^2.  On the raw,
+# uncentred Moscow features (values ~1e6) that expansion cancels ~9 digits, so the
+# reference's own distances carry ~1e-7 relative noise that depends on the BLAS summation
+# order; the restatement can only agree to that level there (1e-12 on the scaled spaces).
+DIST_RTOL = 1e-6
+
+
+@pytest.mark.parametrize(("name", "comp"), FLOAT_CASES)
+def test_oracle_matches_live_reference_kneighbors(name, comp):
+    g = load_golden(f"moscow_{name}_{comp}.npz")
+    sp = load_golden("moscow_split.npz")
+    st = state_from_golden(g)
+    # projection (a1-a4): transformed training plots must equal the reference's _fit_X
+    np.testing.assert_allclose(orc.transform(st, sp["X_train"]), g["state_fit_Z"], rtol=1e-9, atol=1e-11)
+    # X given
+    d, i = orc.kneighbors(st, sp["X_test"], k=5)
+    np.testing.assert_array_equal(i, g["live_tgt_nn"])
+    np.testing.assert_allclose(d, g["live_tgt_dist"], rtol=DIST_RTOL, atol=1e-12)
+    # X=None: k+1, self excluded (a9)
+    d, i = orc.kneighbors(st, None, k=5)
+    np.testing.assert_array_equal(i, g["live_ref_nn"])
+    np.testing.assert_allclose(d, g["live_ref_dist"], rtol=DIST_RTOL, atol=1e-12)
+    # dataframe-index crosswalk (ref:src/sknnr/_base.py:177-180)
+    np.testing.assert_array_equal(sp["index_train"][i], g["live_ref_ids"])
+
+
+@pytest.mark.parametrize(("name", "comp"), FLOAT_CASES)
+def test_oracle_matches_reference_golden_files(name, comp):
+    """ref:tests/test_regressions/*.npz (goldens use algorithm='auto': kd_tree for <=15
+    dims, so distances agree to rounding and index order inside exact ties may differ)."""
+    g = load_golden(f"moscow_{name}_{comp}.npz")
+    sp = load_golden("moscow_split.npz")
+    st = state_from_golden(g)
+    d, i = orc.kneighbors(st, sp["X_test"], k=5)
+    np.testing.assert_array_equal(i, g["refgold_tgt_index_nn"])
+    np.testing.assert_allclose(d, g["refgold_tgt_index_dist"], rtol=DIST_RTOL, atol=1e-11)
+    np.testing.assert_array_equal(sp["index_train"][i], g["refgold_tgt_ids_nn"])
+    d, i = orc.kneighbors(st, None, k=5)
+    np.testing.assert_array_equal(i, g["refgold_ref_index_nn"])
+    np.testing.assert_allclose(d, g["refgold_ref_index_dist"], rtol=DIST_RTOL, atol=1e-11)
+    # predictions: unweighted and the yaImpute callable
+    p = orc.predict(st, sp["X_test"], k=5)
+    np.testing.assert_allclose(p, g["refgold_tgt_unweighted_pred"], rtol=1e-9, atol=1e-12)
+    p = orc.predict(st, sp["X_test"], k=5, weights=yaimpute_weights)
+    np.testing.assert_allclose(p, g["refgold_tgt_weighted_pred"], rtol=DIST_RTOL, atol=1e-12)
+    p = orc.predict(st, None, k=5)
+    np.testing.assert_allclose(p, g["refgold_ref_unweighted_pred"], rtol=1e-9, atol=1e-12)
+    assert orc.r2_score_uniform(sp["y_train"], p) == pytest.approx(float(g["refgold_ref_unweighted_score"]), abs=1e-12)
+    p = orc.predict(st, None, k=5, weights=yaimpute_weights)
+    np.testing.assert_allclose(p, g["refgold_ref_weighted_pred"], rtol=DIST_RTOL, atol=1e-12)
+    assert orc.r2_score_uniform(sp["y_train"], p) == pytest.approx(float(g["refgold_ref_weighted_score"]), abs=1e-7)
+
+
+@pytest.mark.parametrize(("name", "comp"), FLOAT_CASES)
+def test_oracle_distance_weights(name, comp):
+    g = load_golden(f"moscow_{name}_{comp}.npz")
+    sp = load_golden("moscow_split.npz")
+    st = state_from_golden(g)
+    p = orc.predict(st, sp["X_test"], k=5, weights="distance")
+    np.testing.assert_allclose(p, g["live_tgt_pred_distance"], rtol=DIST_RTOL, atol=1e-12)
+    p = orc.predict(st, None, k=5, weights="distance")
+    np.testing.assert_allclose(p, g["live_ref_pred_distance"], rtol=DIST_RTOL, atol=1e-12)
+
+
+def test_oracle_config1_swo_msn():
+    g = load_golden("c1_swo_msn_k5.npz")
+    st = state_from_golden(g)
+    d, i = orc.kneighbors(st, None, k=5)
+    n_bad = orc.assert_tie_aware_equal(d, i, g["live_ref_dist"], g["live_ref_nn"], rtol=1e-7, atol=1e-9)
+    assert n_bad <= 2
+    p = orc.weighted_average(st.y, i)
+    assert orc.r2_score_uniform(g["y_targets"], p) == pytest.approx(float(g["live_ref_score"]), abs=1e-6)
+    d, i = orc.kneighbors(st, g["X"], k=5)
+    # self-distance: the reference's expansion gives ~1e-7 instead of 0 -> absolute floor
+    np.testing.assert_allclose(d, g["live_self_dist"], rtol=1e-6, atol=1e-6)
+
+
+def test_oracle_config2_moscow_gnn_independent_score():
+    g = load_golden("c2_moscow_gnn_k5.npz")
+    st = state_from_golden(g)
+    d, i = orc.kneighbors(st, None, k=5)
+    np.testing.assert_array_equal(i, g["live_ref_nn"])
+    np.testing.assert_allclose(d, g["live_ref_dist"], rtol=1e-9, atol=1e-12)
+    p = orc.weighted_average(st.y, i)
+    np.testing.assert_allclose(p, g["live_ref_pred"], rtol=1e-9, atol=1e-12)
+    assert orc.r2_score_uniform(g["y_targets"], p) == pytest.approx(float(g["live_ref_score"]), abs=1e-12)
+
+
+# ---- ordering known-answer tests (ref:tests/test_estimators.py:306-378) -------------
+def _raw_state(X, y):
+    return orc.FittedState(kind="euclidean", fit_Z=np.asarray(X, float), y=np.asarray(y, float))
+
+
+@pytest.mark.parametrize(("det", "expected"), [(False, [1, 0]), (True, [0, 1])])
+def test_oracle_deterministic_ordering(det, expected):
+    st = _raw_state(np.array([1e-11, 1e-12, 1.0]).reshape(-1, 1), [0, 1, 2])
+    _, idx = orc.kneighbors(st, np.array([[0.0]]), k=2, deterministic=det)
+    assert idx[0].tolist() == expected
+
+
+def test_oracle_uses_index_difference():
+    st = _raw_state(np.array([1e-11, 1e-12, 1.0]).reshape(-1, 1), [0, 1, 2])
+    _, idx = orc.kneighbors(st, np.array([[0.0], [0.0]]), k=2)
+    assert idx.tolist() == [[0, 1], [1, 0]]
+    # a sharded caller reproduces row 1 by passing its global offset
+    _, idx = orc.kneighbors(st, np.array([[0.0]]), k=2, row_offset=1)
+    assert idx.tolist() == [[1, 0]]
+
+
+@pytest.mark.parametrize(("dec", "expected"), [(8, [2, 1, 0]), (5, [1, 2, 0]), (2, [0, 1, 2])])
+def test_oracle_precision_decimals(dec, expected):
+    st = _raw_state(np.array([1e-3, 1e-6, 1e-9, 1.0]).reshape(-1, 1), [0, 1, 2, 3])
+    _, idx = orc.kneighbors(st, np.array([[0.0]]), k=3, decimals=dec)
+    assert idx[0].tolist() == expected
+
+
+def test_oracle_exclude_self_with_duplicates():
+    # >= k+1 exact duplicates: no column equals the row -> column 0 is dropped
+    X = np.zeros((6, 2))
+    st = _raw_state(X, np.arange(6))
+    d, i = orc.kneighbors(st, None, k=2, deterministic=False)
+    assert i[5].tolist() == [1, 2]
+    assert i[0].tolist() == [1, 2]
+    assert np.all(d == 0)
+
+
+# ---- Hamming ------------------------------------------------------------------------
+def test_hamming_c_oracle_is_bit_equal_to_scipy():
+    from scipy.spatial.distance import cdist
+
+    rng = np.random.default_rng(0)
+    Q = rng.integers(0, 6, size=(37, 53))
+    R = rng.integers(0, 6, size=(29, 53))
+    for w in (np.full(53, 1.0 / 53), rng.random(53) + 0.1):
+        ref = cdist(Q.astype(float), R.astype(float), metric="hamming", w=w)
+        assert np.array_equal(orc.hamming_cdist(Q, R, w, use_c=True), ref)
+        assert np.array_equal(orc.hamming_cdist(Q, R, w, use_c=False), ref)
+    w = np.full(53, 0.1 / 53)
+    lut = orc.hamming_lut(w)
+    ref = cdist(Q.astype(float), R.astype(float), metric="hamming", w=w)
+    m = (Q[:, None, :] != R[None, :, :]).sum(-1)
+    assert np.array_equal(lut[m], ref)
+    assert np.all(np.diff(lut) > 0)
+
+
+def test_hamming_oracle_matches_live_rfnn():
+    g = load_golden("moscow_rfnn.npz")
+    st = orc.FittedState(kind="hamming", fit_Z=g["ids_train"].astype(np.int64), y=g["y"], hamming_w=g["hamming_w"])
+    for X, key in ((g["ids_test"].astype(np.int64), "tgt"), (None, "ref")):
+        d, i = orc.kneighbors(st, X, k=5)
+        # distances are bit-equal; indices may differ only inside boundary ties
+        assert np.array_equal(d, g[f"live_{key}_dist"])
+        orc.assert_tie_aware_equal(d, i, g[f"live_{key}_dist"], g[f"live_{key}_nn"], rtol=0, atol=0, gap_rtol=0)
+    st2 = orc.FittedState(kind="hamming", fit_Z=st.fit_Z, y=st.y, hamming_w=g["hamming_w_nonuniform"])
+    d, i = orc.kneighbors(st2, g["ids_test"].astype(np.int64), k=5)
+    assert np.array_equal(d, g["live_tgt_dist_nonuniform"])
