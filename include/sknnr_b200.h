@@ -1,0 +1,180 @@
+/* sknnr_b200 - C ABI of the B200-native query-time hot path of lemma-osu/sknnr.
+ *
+ * The reference (pure Python) has no FFI layer; its narrowest seams for this path are
+ *
+ *   S1  super().kneighbors(X=..., n_neighbors=..., return_distance=True)
+ *       ref:src/sknnr/_base.py:162-164   (Z f64 [n_q,d'] | None, k) -> (dist f64, idx i64)
+ *       followed by the re-ordering at :166-175
+ *   S2  TransformedKNeighborsRegressor._transform_X       ref:src/sknnr/_base.py:236-239
+ *   S3  regressor_.predict / regressor_.score             ref:src/sknnr/_base.py:346-352
+ *
+ * Each entry point below names the seam it replaces.  Plain pointers and sizes only, no
+ * torch types; every function returns 0 on success or a negative SKNNR_E* code, never
+ * throws, and leaves a thread-local message for sknnr_last_error().  There is no CPU
+ * fallback anywhere behind this ABI: without a CUDA device every compute call fails.
+ *
+ * Ownership: the caller owns every input/output buffer; an index handle owns only device
+ * copies of the fitted state plus its scratch and is a rebuildable cache.  A handle is
+ * internally locked, so concurrent calls on one handle serialise; distinct handles are
+ * independent.
+ */
+#ifndef SKNNR_B200_H
+#define SKNNR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKNNR_ABI_VERSION 1
+
+/* error codes */
+#define SKNNR_OK 0
+#define SKNNR_EINVAL (-1)   /* bad argument (the Python layer validates first)        */
+#define SKNNR_ECUDA (-2)    /* CUDA runtime / launch failure                           */
+#define SKNNR_ENODEV (-3)   /* no CUDA device                                          */
+#define SKNNR_ENOMEM (-4)   /* device or pinned-host allocation failed                 */
+#define SKNNR_EUNSUP (-5)   /* shape outside what the kernels cover (k > 32, ...)      */
+
+/* dtype of a query matrix */
+#define SKNNR_F64 0
+#define SKNNR_F32 1
+
+/* flags for the query calls */
+#define SKNNR_EXCLUDE_SELF 1u   /* X=None semantics: search k+1, drop the query itself
+                                   ($SP/sklearn/neighbors/_base.py:821-826,929-958), used by
+                                   IndependentPredictorMixin (ref:src/sknnr/_base.py:37-40)  */
+#define SKNNR_DETERMINISTIC 2u  /* use_deterministic_ordering (ref:src/sknnr/_base.py:166-175) */
+#define SKNNR_TRANSFORMED 4u    /* X is already in the estimator's space (seam S1 alone,
+                                   RawKNNRegressor); otherwise S2 is fused in front         */
+#define SKNNR_DEVICE_PTRS 8u    /* X and all outputs are device pointers on the handle's
+                                   device; work is enqueued on `stream` and NOT synchronised */
+
+/* prediction weights (seam S3, $SP/sklearn/neighbors/_base.py:74-117) */
+#define SKNNR_W_NONE 0      /* no prediction requested                                    */
+#define SKNNR_W_UNIFORM 1   /* mean of the k targets                                       */
+#define SKNNR_W_DISTANCE 2  /* 1/d, rows containing d==0 use the (d==0) indicator          */
+
+/* search engines (diagnostics / benchmarking; 0 lets the library choose) */
+#define SKNNR_ENGINE_AUTO 0
+#define SKNNR_ENGINE_SIMT 1     /* FP32 FFMA2 register-tiled kernel                        */
+#define SKNNR_ENGINE_TENSOR 2   /* tcgen05 TF32 filter kernel                              */
+#define SKNNR_ENGINE_EXACT 3    /* FP64 exhaustive kernel (the certificate's fallback)     */
+
+typedef struct sknnr_index sknnr_index;           /* Euclidean-space estimators */
+typedef struct sknnr_hamming_index sknnr_hamming_index; /* RFNN node-ID estimators    */
+
+/* counters of the last query call on a handle (all int64) */
+typedef struct sknnr_stats {
+    int64_t n_queries;       /* rows processed                                           */
+    int64_t n_fallback;      /* rows whose certificate failed and were re-searched exactly */
+    int64_t kernel_launches; /* kernels of this library launched by the call              */
+    int64_t h2d_bytes;       /* bytes copied host->device by the call                     */
+    int64_t d2h_bytes;       /* bytes copied device->host by the call                     */
+    int64_t engine;          /* SKNNR_ENGINE_* actually used                              */
+    double search_ms;        /* device time of the dominant (search) kernels, CUDA events;
+                                only filled when sknnr_set_option("timing", 1)            */
+} sknnr_stats;
+
+const char *sknnr_last_error(void);
+int sknnr_abi_version(void);
+int sknnr_device_count(int *count);
+
+/* Global knobs (environment-style; never estimator constructor arguments):
+ *   "engine"      SKNNR_ENGINE_*           (default AUTO)
+ *   "chunk_rows"  rows per internal chunk  (default 1<<20)
+ *   "timing"      0/1 record search_ms     (default 0)                               */
+int sknnr_set_option(const char *name, int64_t value);
+
+/* ---- Euclidean-space index: Raw / Euclidean / Mahalanobis / MSN / GNN ------------------
+ * Fitted state of one estimator.  The four float transformers are one affine map
+ *     Z = ((X - center) / scale) @ proj
+ * (StandardScalerWithDOF: $SP/sklearn/preprocessing/_data.py:1131-1134 with scale_ from
+ *  ref:src/sknnr/transformers/_base.py:66; MahalanobisTransformer
+ *  ref:src/sknnr/transformers/_mahalanobis_transformer.py:55; CCorATransformer
+ *  ref:src/sknnr/transformers/_ccora_transformer.py:70; CCATransformer
+ *  ref:src/sknnr/transformers/_cca_transformer.py:87).
+ *
+ *   fit_z   [n_ref, d_out] f64 C-order  - regressor_._fit_X (transformed reference plots)
+ *   center  [d_in] or NULL (no centring); scale [d_in] or NULL (no scaling)
+ *   proj    [d_in, d_out] f64 C-order or NULL (identity, d_in == d_out)
+ *   y       [n_ref, n_out] f64 C-order or NULL (kneighbors only); regressor_._y
+ * All pointers are HOST pointers; the data is copied.                                    */
+int sknnr_index_create(const double *fit_z, int64_t n_ref, int32_t d_out,
+                       const double *center, const double *scale, const double *proj,
+                       int32_t d_in, const double *y, int32_t n_out, int32_t device,
+                       sknnr_index **out);
+int sknnr_index_destroy(sknnr_index *index);
+
+/* kneighbors (+ optional predict) for n_q query rows.  Replaces S2+S1(+S3) in one call.
+ *
+ *   X          [n_q, d_in] (or [n_q, d_out] with SKNNR_TRANSFORMED), dtype x_dtype,
+ *              row stride ldx elements.  With SKNNR_EXCLUDE_SELF X must be NULL: the query
+ *              set is the reference set itself and n_q is ignored (= n_ref).
+ *   row_offset global row number of X[0] - the |idx - query_row| tie-break key
+ *              (ref:src/sknnr/_base.py:171) of a sharded caller.
+ *   k          neighbours returned per row (1 <= k; k + exclude_self <= min(n_ref, 32)).
+ *   decimals   RawKNNRegressor.DISTANCE_PRECISION_DECIMALS (ref:src/sknnr/_base.py:102).
+ *   out_dist   [n_q, k] f64 or NULL;  out_idx [n_q, k] i64 or NULL
+ *   weights    SKNNR_W_*; out_pred [n_q, n_out] f64 (required unless SKNNR_W_NONE)
+ *   stream     cudaStream_t as void* (only with SKNNR_DEVICE_PTRS; else ignored)          */
+int sknnr_kneighbors(sknnr_index *index, const void *X, int32_t x_dtype, int64_t n_q,
+                     int64_t ldx, int64_t row_offset, int32_t k, uint32_t flags,
+                     int32_t decimals, double *out_dist, int64_t *out_idx, int32_t weights,
+                     double *out_pred, void *stream);
+
+/* S2 alone: Z = ((X - center) / scale) @ proj, out_z [n_q, d_out] f64 (host pointers).    */
+int sknnr_transform(sknnr_index *index, const void *X, int32_t x_dtype, int64_t n_q,
+                    int64_t ldx, double *out_z);
+
+/* S3 with caller-supplied weights (callable `weights=` evaluated by Python on the
+ * distances): out_pred[i, :] = sum_c w[i,c] * y[idx[i,c], :] / sum_c w[i,c]
+ * ($SP/sklearn/neighbors/_regression.py:262-267).  Host pointers.                         */
+int sknnr_weighted_average(sknnr_index *index, const int64_t *idx, const double *w,
+                           int64_t n_q, int32_t k, double *out_pred);
+
+int sknnr_index_stats(sknnr_index *index, sknnr_stats *out);
+
+/* ---- Hamming index: RFNNRegressor (metric="hamming" over terminal-node IDs) -------------
+ * Replaces sklearn's brute Hamming branch + scipy cdist_hamming
+ * ($SP/sklearn/neighbors/_base.py:879-908,715-754; $SP/scipy/spatial/distance.py:1718-1723)
+ * reached with w = hamming_weights_ (ref:src/sknnr/_weighted_trees.py:65-98,139-140).
+ *
+ *   ref_codes [n_ref, n_trees] u16 C-order: per-tree node codes.  Only equality matters, so
+ *             the host maps each tree's node IDs (int64 from
+ *             ref:src/sknnr/transformers/_tree_node_transformer.py:177-201) to dense codes
+ *             in [0, 31743]; 31743 is reserved for "matches nothing".
+ *   w         [n_trees] f64 hamming weights.  Equal weights use the integer kernel and a
+ *             host-built table of the float64 distances reachable (bit-exact with SciPy's
+ *             left-to-right sums); unequal weights use the exact float64 kernel.
+ *   y         [n_ref, n_out] f64 or NULL.                                                  */
+int sknnr_hamming_index_create(const uint16_t *ref_codes, int64_t n_ref, int32_t n_trees,
+                               const double *w, const double *y, int32_t n_out,
+                               int32_t device, sknnr_hamming_index **out);
+int sknnr_hamming_index_destroy(sknnr_hamming_index *index);
+
+/* Same contract as sknnr_kneighbors; q_codes [n_q, n_trees] u16, row stride ldq elements.
+ * Neighbours are the k smallest by (distance, index): the lowest index wins every tie.     */
+int sknnr_hamming_kneighbors(sknnr_hamming_index *index, const uint16_t *q_codes,
+                             int64_t n_q, int64_t ldq, int64_t row_offset, int32_t k,
+                             uint32_t flags, int32_t decimals, double *out_dist,
+                             int64_t *out_idx, int32_t weights, double *out_pred,
+                             void *stream);
+int sknnr_hamming_weighted_average(sknnr_hamming_index *index, const int64_t *idx,
+                                   const double *w, int64_t n_q, int32_t k,
+                                   double *out_pred);
+int sknnr_hamming_index_stats(sknnr_hamming_index *index, sknnr_stats *out);
+
+/* Pinned host memory for callers that stream large rasters (cudaHostAlloc / cudaFreeHost). */
+int sknnr_host_alloc(void **ptr, int64_t bytes);
+int sknnr_host_free(void *ptr);
+
+/* FP32 FMA-pipe peak probe: runs a register-resident FFMA2 loop on every SM and returns
+ * the achieved TFLOP/s (the denominator of the SIMT roofline, measured not assumed).      */
+int sknnr_measure_fp32_peak(int32_t device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKNNR_B200_H */

@@ -1,0 +1,238 @@
+"""Device-resident fitted state: thin Python owners of the C-ABI index handles.
+
+``KNNIndex`` serves the Euclidean-space estimators (Raw / Euclidean / Mahalanobis / MSN /
+GNN), ``HammingIndex`` serves RFNN.  Handles are caches: they are rebuilt from the NumPy
+fitted attributes on demand and never pickled.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+
+def default_device() -> int:
+    """Device ordinal for new indexes: SKNNR_B200_DEVICE, else LOCAL_RANK, else 0."""
+    for var in ("SKNNR_B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(var)
+        if v not in (None, ""):
+            return int(v)
+    return 0
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, ndim=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if ndim == 2 and a.ndim == 1:
+        a = a.reshape(-1, 1)
+    return a
+
+
+def _weights_mode(weights, with_pred):
+    if not with_pred:
+        return L.W_NONE
+    if weights in (None, "uniform"):
+        return L.W_UNIFORM
+    if isinstance(weights, str) and weights == "distance":
+        return L.W_DISTANCE
+    raise ValueError(f"unsupported device weights mode {weights!r}")
+
+
+class _IndexBase:
+    _destroy = None
+    _stats = None
+
+    def __init__(self):
+        self._h = C.c_void_p(None)
+        self._lib = L.load()
+
+    def close(self):
+        h, self._h = self._h, C.c_void_p(None)
+        if h and h.value:
+            getattr(self._lib, self._destroy)(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self) -> dict:
+        st = L.Stats()
+        L.check(getattr(self._lib, self._stats)(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def _flags(self, exclude_self, deterministic, transformed=False):
+        f = 0
+        if exclude_self:
+            f |= L.EXCLUDE_SELF
+        if deterministic:
+            f |= L.DETERMINISTIC
+        if transformed:
+            f |= L.TRANSFORMED
+        return f
+
+
+class KNNIndex(_IndexBase):
+    """Fitted state of one Euclidean-space estimator on the device.
+
+    ``fit_z``: transformed reference plots (``regressor_._fit_X``); ``center/scale/proj``:
+    the affine projection ``Z = ((X - center) / scale) @ proj`` (any may be None);
+    ``y``: targets (``regressor_._y``).
+    """
+
+    _destroy = "sknnr_index_destroy"
+    _stats = "sknnr_index_stats"
+
+    def __init__(self, fit_z, center=None, scale=None, proj=None, y=None, device=None):
+        super().__init__()
+        fit_z = _f64(fit_z)
+        if fit_z.ndim != 2:
+            raise ValueError("fit_z must be 2-D")
+        self.n_ref, self.d_out = fit_z.shape
+        center, scale, proj, y = _f64(center), _f64(scale), _f64(proj), _f64(y, 2)
+        if proj is not None:
+            self.d_in = proj.shape[0]
+            if proj.shape[1] != self.d_out:
+                raise ValueError("proj has the wrong number of columns")
+        elif center is not None:
+            self.d_in = center.shape[0]
+        elif scale is not None:
+            self.d_in = scale.shape[0]
+        else:
+            self.d_in = self.d_out
+        self.n_out = 0 if y is None else y.shape[1]
+        self.device = default_device() if device is None else int(device)
+        L.check(self._lib.sknnr_index_create(
+            _ptr(fit_z), self.n_ref, self.d_out, _ptr(center), _ptr(scale), _ptr(proj),
+            self.d_in, _ptr(y), self.n_out, self.device, C.byref(self._h)))
+
+    # -- host-buffer query (the drop-in call) ------------------------------------------
+    def query(self, X, k, *, exclude_self=False, deterministic=True, decimals=10,
+              row_offset=0, transformed=False, weights=None, with_pred=False,
+              return_distance=True, return_index=True):
+        """kneighbors (+ optional predict) on host arrays.  ``X=None`` with
+        ``exclude_self`` searches the reference set against itself."""
+        if exclude_self:
+            n_q, Xp, dt, ldx = self.n_ref, None, L.F64, 0
+        else:
+            X = np.asarray(X)
+            if X.dtype != np.float32:
+                X = np.asarray(X, dtype=np.float64)
+            if X.ndim != 2:
+                raise ValueError("X must be 2-D")
+            if X.strides[1] != X.itemsize or X.strides[0] % X.itemsize or X.strides[0] < X.shape[1] * X.itemsize:
+                X = np.ascontiguousarray(X)
+            n_q, dt = X.shape[0], (L.F32 if X.dtype == np.float32 else L.F64)
+            ldx = X.strides[0] // X.itemsize if n_q > 1 else X.shape[1]
+            want = self.d_out if transformed else self.d_in
+            if X.shape[1] != want:
+                raise ValueError(f"X has {X.shape[1]} features, but {want} are expected")
+            Xp = _ptr(X)
+        mode = _weights_mode(weights, with_pred)
+        dist = np.empty((n_q, k), dtype=np.float64) if return_distance else None
+        idx = np.empty((n_q, k), dtype=np.int64) if return_index else None
+        pred = np.empty((n_q, self.n_out), dtype=np.float64) if mode != L.W_NONE else None
+        L.check(self._lib.sknnr_kneighbors(
+            self._h, Xp, dt, n_q, ldx, int(row_offset), int(k),
+            self._flags(exclude_self, deterministic, transformed), int(decimals),
+            _ptr(dist), _ptr(idx), mode, _ptr(pred), None))
+        return dist, idx, pred
+
+    # -- device-pointer query (benchmarks, multi-GPU pipelines) -------------------------
+    def query_device(self, x_ptr, x_is_f32, n_q, ldx, k, *, dist_ptr=0, idx_ptr=0, pred_ptr=0,
+                     weights=None, deterministic=True, decimals=10, row_offset=0,
+                     transformed=False, stream=0):
+        mode = _weights_mode(weights, bool(pred_ptr))
+        flags = self._flags(False, deterministic, transformed) | L.DEVICE_PTRS
+        L.check(self._lib.sknnr_kneighbors(
+            self._h, C.c_void_p(x_ptr), L.F32 if x_is_f32 else L.F64, int(n_q), int(ldx),
+            int(row_offset), int(k), flags, int(decimals), C.c_void_p(dist_ptr or None),
+            C.c_void_p(idx_ptr or None), mode, C.c_void_p(pred_ptr or None),
+            C.c_void_p(stream or None)))
+
+    def transform(self, X):
+        X = np.asarray(X)
+        if X.dtype != np.float32:
+            X = np.ascontiguousarray(X, dtype=np.float64)
+        else:
+            X = np.ascontiguousarray(X)
+        out = np.empty((X.shape[0], self.d_out), dtype=np.float64)
+        L.check(self._lib.sknnr_transform(
+            self._h, _ptr(X), L.F32 if X.dtype == np.float32 else L.F64, X.shape[0], X.shape[1],
+            _ptr(out)))
+        return out
+
+    def weighted_average(self, idx, w):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        out = np.empty((idx.shape[0], self.n_out), dtype=np.float64)
+        L.check(self._lib.sknnr_weighted_average(self._h, _ptr(idx), _ptr(w), idx.shape[0],
+                                                 idx.shape[1], _ptr(out)))
+        return out
+
+
+class HammingIndex(_IndexBase):
+    """Fitted state of an RFNN-style estimator: 16-bit node codes + Hamming weights."""
+
+    _destroy = "sknnr_hamming_index_destroy"
+    _stats = "sknnr_hamming_index_stats"
+
+    def __init__(self, ref_codes, w, y=None, device=None):
+        super().__init__()
+        ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint16)
+        self.n_ref, self.n_trees = ref_codes.shape
+        w = _f64(w)
+        y = _f64(y, 2)
+        self.n_out = 0 if y is None else y.shape[1]
+        self.device = default_device() if device is None else int(device)
+        L.check(self._lib.sknnr_hamming_index_create(
+            _ptr(ref_codes), self.n_ref, self.n_trees, _ptr(w), _ptr(y), self.n_out, self.device,
+            C.byref(self._h)))
+
+    def query(self, codes, k, *, exclude_self=False, deterministic=True, decimals=10,
+              row_offset=0, weights=None, with_pred=False, return_distance=True,
+              return_index=True):
+        if exclude_self:
+            n_q, cp, ldq = self.n_ref, None, 0
+        else:
+            codes = np.ascontiguousarray(codes, dtype=np.uint16)
+            n_q, ldq = codes.shape[0], codes.shape[1]
+            if ldq != self.n_trees:
+                raise ValueError(f"X has {ldq} features, but {self.n_trees} are expected")
+            cp = _ptr(codes)
+        mode = _weights_mode(weights, with_pred)
+        dist = np.empty((n_q, k), dtype=np.float64) if return_distance else None
+        idx = np.empty((n_q, k), dtype=np.int64) if return_index else None
+        pred = np.empty((n_q, self.n_out), dtype=np.float64) if mode != L.W_NONE else None
+        L.check(self._lib.sknnr_hamming_kneighbors(
+            self._h, cp, n_q, ldq, int(row_offset), int(k),
+            self._flags(exclude_self, deterministic), int(decimals), _ptr(dist), _ptr(idx), mode,
+            _ptr(pred), None))
+        return dist, idx, pred
+
+    def query_device(self, q_ptr, n_q, ldq, k, *, dist_ptr=0, idx_ptr=0, pred_ptr=0, weights=None,
+                     deterministic=True, decimals=10, row_offset=0, stream=0):
+        mode = _weights_mode(weights, bool(pred_ptr))
+        flags = self._flags(False, deterministic) | L.DEVICE_PTRS
+        L.check(self._lib.sknnr_hamming_kneighbors(
+            self._h, C.c_void_p(q_ptr), int(n_q), int(ldq), int(row_offset), int(k), flags,
+            int(decimals), C.c_void_p(dist_ptr or None), C.c_void_p(idx_ptr or None), mode,
+            C.c_void_p(pred_ptr or None), C.c_void_p(stream or None)))
+
+    def weighted_average(self, idx, w):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        out = np.empty((idx.shape[0], self.n_out), dtype=np.float64)
+        L.check(self._lib.sknnr_hamming_weighted_average(self._h, _ptr(idx), _ptr(w), idx.shape[0],
+                                                         idx.shape[1], _ptr(out)))
+        return out

@@ -1,0 +1,838 @@
+// extern "C" entry points of libsknnr_b200.so (see include/sknnr_b200.h for the contract and
+// the reference seams each call replaces).  Host-side orchestration only: fitted-state upload,
+// chunked streaming of query rows through project -> search -> refine -> exact(fallback), and
+// copies.  No CPU compute path exists here: every call needs a CUDA device.
+#include "../../include/sknnr_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace sk;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(expr)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            char _b[512];                                                                     \
+            snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),      \
+                     __FILE__, __LINE__, cudaGetErrorString(_e));                             \
+            return fail(_e == cudaErrorMemoryAllocation ? SKNNR_ENOMEM : SKNNR_ECUDA, _b);    \
+        }                                                                                     \
+    } while (0)
+
+struct Options {
+    int64_t engine = SKNNR_ENGINE_AUTO;
+    int64_t chunk_rows = 1 << 20;
+    int64_t timing = 0;
+} g_opt;
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int pick_kc(int kk, int slack) {
+    const int need = kk + slack;
+    if (need <= 8) return 8;
+    if (need <= 16) return 16;
+    if (need <= 32) return 32;
+    return 0;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// per-chunk device buffers + the stream the chunk runs on
+struct Slot {
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevBuf<unsigned char> x;       // staged query rows (host callers)
+    DevBuf<double> z64;
+    DevBuf<float> qimg;
+    DevBuf<uint32_t> qimg_h;       // Hamming query image
+    DevBuf<int> cand_idx;
+    DevBuf<float> cand_thr;
+    DevBuf<int> cand_cnt;
+    DevBuf<int> fb;                // [0] = count, [1..] = list
+    DevBuf<double> o_dist;
+    DevBuf<long long> o_idx;
+    DevBuf<double> o_pred;
+    DevBuf<double> scratch;        // exact kernel distance scratch [grid, n_ref]
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_pending = false;
+    int *h_fb = nullptr;           // pinned: fallback count of the chunk in flight
+    bool fb_pending = false;
+    void release() {
+        x.release(); z64.release(); qimg.release(); qimg_h.release(); cand_idx.release();
+        cand_thr.release(); cand_cnt.release(); fb.release(); o_dist.release();
+        o_idx.release(); o_pred.release(); scratch.release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (h_fb) cudaFreeHost(h_fb);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+        ev0 = ev1 = nullptr; h_fb = nullptr; stream = nullptr;
+    }
+};
+
+struct IndexBase {
+    int device = 0;
+    int64_t n_ref = 0;
+    int n_out = 0;
+    double *d_y = nullptr;
+    std::mutex lock;
+    Slot slots[2];
+    int exact_grid = 0;
+    sknnr_stats stats{};
+    int n_sm = 148;
+
+    int init_common(int dev, const double *y, int64_t nref, int nout) {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            return fail(SKNNR_ENODEV, "no CUDA device: sknnr_b200 has no CPU fallback");
+        if (dev < 0 || dev >= count) return fail(SKNNR_EINVAL, "bad device ordinal");
+        device = dev;
+        n_ref = nref;
+        n_out = nout;
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(SKNNR_ENODEV, "sknnr_b200 kernels are built for sm_100a (B200) only");
+        n_sm = prop.multiProcessorCount;
+        if (y && nout > 0) {
+            CK(cudaMalloc(&d_y, (size_t)nref * nout * sizeof(double)));
+            CK(cudaMemcpy(d_y, y, (size_t)nref * nout * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        for (auto &s : slots) {
+            CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            s.own_stream = true;
+            CK(cudaEventCreate(&s.ev0));
+            CK(cudaEventCreate(&s.ev1));
+            CK(cudaHostAlloc((void **)&s.h_fb, sizeof(int), cudaHostAllocDefault));
+            *s.h_fb = 0;
+        }
+        return SKNNR_OK;
+    }
+    void release_common() {
+        cudaSetDevice(device);
+        for (auto &s : slots) s.release();
+        if (d_y) cudaFree(d_y);
+        d_y = nullptr;
+    }
+    // collect timing / fallback count of the chunk that last ran on this slot
+    void harvest(Slot &s) {
+        if (s.ev_pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s.ev0, s.ev1) == cudaSuccess) stats.search_ms += ms;
+            s.ev_pending = false;
+        }
+        if (s.fb_pending) {
+            stats.n_fallback += *s.h_fb;
+            s.fb_pending = false;
+        }
+    }
+};
+
+int check_query_args(int64_t n_ref, int n_out, int64_t n_q, int k, uint32_t flags, int weights,
+                     const void *X, const double *out_pred, int &kk) {
+    const bool excl = flags & SKNNR_EXCLUDE_SELF;
+    kk = k + (excl ? 1 : 0);
+    if (k < 1) return fail(SKNNR_EINVAL, "k must be >= 1");
+    if (kk > n_ref)
+        return fail(SKNNR_EINVAL, excl ? "Expected n_neighbors < n_samples_fit"
+                                       : "Expected n_neighbors <= n_samples_fit");
+    if (kk > MAXK) return fail(SKNNR_EUNSUP, "k (+1 with self exclusion) > 32 is not supported");
+    if (excl && X != nullptr) return fail(SKNNR_EINVAL, "X must be NULL with SKNNR_EXCLUDE_SELF");
+    if (!excl && (X == nullptr || n_q < 0)) return fail(SKNNR_EINVAL, "X is NULL");
+    if (weights != SKNNR_W_NONE) {
+        if (weights != SKNNR_W_UNIFORM && weights != SKNNR_W_DISTANCE)
+            return fail(SKNNR_EINVAL, "bad weights mode");
+        if (out_pred == nullptr || n_out <= 0)
+            return fail(SKNNR_EINVAL, "prediction requested but no targets / output buffer");
+    }
+    return SKNNR_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+struct sknnr_index : IndexBase {
+    int d_in = 0, d_out = 0, dpad = 0;
+    double *d_ref64 = nullptr, *d_center = nullptr, *d_scale = nullptr, *d_proj = nullptr,
+           *d_mu = nullptr;
+    float *d_rimg = nullptr;
+    int n_rtiles = 0;
+    double r2max = 0.0;
+};
+
+struct sknnr_hamming_index : IndexBase {
+    int n_trees = 0, n_chunks = 0, n_rtiles = 0;
+    uint16_t *d_rcodes = nullptr;
+    uint32_t *d_rimg = nullptr;
+    double *d_w = nullptr, *d_lut = nullptr;
+    double wsum = 0.0;
+    bool uniform = true;
+};
+
+extern "C" {
+
+const char *sknnr_last_error(void) { return g_err.c_str(); }
+int sknnr_abi_version(void) { return SKNNR_ABI_VERSION; }
+
+int sknnr_device_count(int *count) {
+    if (!count) return fail(SKNNR_EINVAL, "count is NULL");
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0;
+    *count = c;
+    return SKNNR_OK;
+}
+
+int sknnr_set_option(const char *name, int64_t value) {
+    if (!name) return fail(SKNNR_EINVAL, "name is NULL");
+    if (!strcmp(name, "engine")) {
+        if (value < 0 || value > 3) return fail(SKNNR_EINVAL, "engine must be 0..3");
+        g_opt.engine = value;
+    } else if (!strcmp(name, "chunk_rows")) {
+        if (value < 256) return fail(SKNNR_EINVAL, "chunk_rows must be >= 256");
+        g_opt.chunk_rows = (value + 255) / 256 * 256;
+    } else if (!strcmp(name, "timing")) {
+        g_opt.timing = value ? 1 : 0;
+    } else {
+        return fail(SKNNR_EINVAL, std::string("unknown option ") + name);
+    }
+    return SKNNR_OK;
+}
+
+int sknnr_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(SKNNR_EINVAL, "bad arguments");
+    CK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return SKNNR_OK;
+}
+int sknnr_host_free(void *ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
+    return SKNNR_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+int sknnr_index_create(const double *fit_z, int64_t n_ref, int32_t d_out, const double *center,
+                       const double *scale, const double *proj, int32_t d_in, const double *y,
+                       int32_t n_out, int32_t device, sknnr_index **out) {
+    if (!fit_z || !out || n_ref < 1 || d_out < 1 || d_in < 1)
+        return fail(SKNNR_EINVAL, "bad arguments to sknnr_index_create");
+    if (!proj && d_in != d_out) return fail(SKNNR_EINVAL, "d_in != d_out without a projector");
+    if (n_ref >= (1LL << 31) - 64) return fail(SKNNR_EUNSUP, "n_ref too large");
+    if (y == nullptr) n_out = 0;
+    sknnr_index *ix = new sknnr_index();
+    int rc = ix->init_common(device, y, n_ref, n_out);
+    if (rc != SKNNR_OK) {
+        ix->release_common();
+        delete ix;
+        return rc;
+    }
+    ix->d_in = d_in;
+    ix->d_out = d_out;
+    ix->dpad = round_up(d_out, 8);
+    ix->n_rtiles = (int)((n_ref + RTILE - 1) / RTILE);
+
+    // centroid of the reference plots: the search images hold (z - mu) so FP32 keeps its
+    // precision on raw, uncentred features (UTM-like coordinates)
+    std::vector<double> mu(d_out, 0.0);
+    for (int64_t j = 0; j < n_ref; ++j)
+        for (int k = 0; k < d_out; ++k) mu[k] += fit_z[j * d_out + k];
+    for (int k = 0; k < d_out; ++k) mu[k] /= (double)n_ref;
+
+    // reference tile images [(dpad+1)][64] f32, last row = |r|^2 (+inf for padding plots)
+    const size_t tile_floats = (size_t)(ix->dpad + 1) * RTILE;
+    std::vector<float> rimg((size_t)ix->n_rtiles * tile_floats, 0.0f);
+    double r2max = 0.0;
+    for (int t = 0; t < ix->n_rtiles; ++t) {
+        float *img = rimg.data() + (size_t)t * tile_floats;
+        for (int jj = 0; jj < RTILE; ++jj) {
+            const int64_t j = (int64_t)t * RTILE + jj;
+            if (j >= n_ref) {
+                img[(size_t)ix->dpad * RTILE + jj] = INFINITY;
+                continue;
+            }
+            double n32 = 0.0, n64 = 0.0;
+            for (int k = 0; k < d_out; ++k) {
+                const double v = fit_z[j * d_out + k] - mu[k];
+                const float f = (float)v;
+                img[(size_t)k * RTILE + jj] = f;
+                n32 += (double)f * (double)f;
+                n64 += v * v;
+            }
+            img[(size_t)ix->dpad * RTILE + jj] = (float)n32;
+            r2max = std::max(r2max, n64);
+        }
+    }
+    ix->r2max = r2max;
+
+    auto up = [&](double **dst, const double *src, size_t n) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, n * sizeof(double));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = up(&ix->d_ref64, fit_z, (size_t)n_ref * d_out);
+    if (e == cudaSuccess) e = up(&ix->d_mu, mu.data(), d_out);
+    if (e == cudaSuccess && center) e = up(&ix->d_center, center, d_in);
+    if (e == cudaSuccess && scale) e = up(&ix->d_scale, scale, d_in);
+    if (e == cudaSuccess && proj) e = up(&ix->d_proj, proj, (size_t)d_in * d_out);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->d_rimg, rimg.size() * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ix->d_rimg, rimg.data(), rimg.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        sknnr_index_destroy(ix);
+        CK(e);
+    }
+    *out = ix;
+    return SKNNR_OK;
+}
+
+int sknnr_index_destroy(sknnr_index *ix) {
+    if (!ix) return SKNNR_OK;
+    ix->release_common();
+    cudaFree(ix->d_ref64); cudaFree(ix->d_center); cudaFree(ix->d_scale); cudaFree(ix->d_proj);
+    cudaFree(ix->d_mu); cudaFree(ix->d_rimg);
+    delete ix;
+    return SKNNR_OK;
+}
+
+int sknnr_index_stats(sknnr_index *ix, sknnr_stats *out) {
+    if (!ix || !out) return fail(SKNNR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(ix->lock);
+    *out = ix->stats;
+    return SKNNR_OK;
+}
+
+// one chunk of a Euclidean-space query, everything enqueued on s.stream
+static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_t ldx, bool transformed,
+                     int64_t rows, int64_t row0, int k, uint32_t flags, int decimals, int weights,
+                     double *o_dist, long long *o_idx, double *o_pred) {
+    const bool excl = flags & SKNNR_EXCLUDE_SELF;
+    const int kk = k + (excl ? 1 : 0);
+    cudaStream_t st = s.stream;
+    const int64_t n_qtiles = (rows + QTILE - 1) / QTILE;
+
+    int engine = (int)g_opt.engine;
+    int kc = pick_kc(kk, 1);
+    if (engine == SKNNR_ENGINE_AUTO || engine == SKNNR_ENGINE_TENSOR) engine = SKNNR_ENGINE_SIMT;
+    if (kc == 0 || search_simt_pick_stages(ix->dpad, kc ? kc : 8) == 0) engine = SKNNR_ENGINE_EXACT;
+    ix->stats.engine = engine;
+
+    FinishParams fp;
+    fp.k = k;
+    fp.exclude_self = excl ? 1 : 0;
+    fp.deterministic = (flags & SKNNR_DETERMINISTIC) ? 1 : 0;
+    fp.round_scale = std::pow(10.0, (double)decimals);
+    fp.row_offset = row0;
+    fp.out_dist = o_dist;
+    fp.out_idx = o_idx;
+    fp.weights = weights;
+    fp.y = ix->d_y;
+    fp.n_out = ix->n_out;
+    fp.out_pred = o_pred;
+
+    CK(s.z64.reserve((size_t)rows * ix->d_out));
+    CK(s.qimg.reserve((size_t)n_qtiles * ix->dpad * QTILE));
+    CK(launch_project(dX, x_f32, ldx, rows, transformed ? ix->d_out : ix->d_in, ix->d_out, ix->dpad,
+                      transformed ? nullptr : ix->d_center, transformed ? nullptr : ix->d_scale,
+                      transformed ? nullptr : ix->d_proj, ix->d_mu, s.z64.p,
+                      engine == SKNNR_ENGINE_SIMT ? s.qimg.p : nullptr, st));
+    ix->stats.kernel_launches++;
+
+    ExactArgs ea{};
+    ea.metric = 0;
+    ea.z64 = s.z64.p;
+    ea.ref64 = ix->d_ref64;
+    ea.d = ix->d_out;
+    ea.n_q = rows;
+    ea.n_ref = (int)ix->n_ref;
+    ea.grid = (int)std::min<int64_t>(rows, (int64_t)ix->n_sm * 2);
+    CK(s.scratch.reserve((size_t)ix->n_sm * 2 * ix->n_ref));
+    ea.scratch = s.scratch.p;
+
+    if (engine == SKNNR_ENGINE_EXACT) {
+        ea.list = nullptr;
+        ea.count = nullptr;
+        if (g_opt.timing) CK(cudaEventRecord(s.ev0, st));
+        CK(launch_exact(ea, fp, st));
+        if (g_opt.timing) { CK(cudaEventRecord(s.ev1, st)); s.ev_pending = true; }
+        ix->stats.kernel_launches++;
+        return SKNNR_OK;
+    }
+
+    CK(s.cand_idx.reserve((size_t)rows * kc));
+    CK(s.cand_thr.reserve((size_t)rows));
+    CK(s.fb.reserve((size_t)rows + 1));
+    CK(cudaMemsetAsync(s.fb.p, 0, sizeof(int), st));
+    if (g_opt.timing) CK(cudaEventRecord(s.ev0, st));
+    CK(launch_search_simt(s.qimg.p, ix->d_rimg, ix->dpad, ix->n_rtiles, rows, kc, s.cand_idx.p,
+                          s.cand_thr.p, st));
+    if (g_opt.timing) { CK(cudaEventRecord(s.ev1, st)); s.ev_pending = true; }
+    ix->stats.kernel_launches++;
+
+    RefineArgs ra{};
+    ra.z64 = s.z64.p;
+    ra.ref64 = ix->d_ref64;
+    ra.mu = ix->d_mu;
+    ra.cand_idx = s.cand_idx.p;
+    ra.cand_thr = s.cand_thr.p;
+    ra.kc = kc;
+    ra.d = ix->d_out;
+    ra.n_q = rows;
+    ra.n_ref = (int)ix->n_ref;
+    // |approx score - true score| <= eps_s * (|q|^2 + max|r|^2): FP32 rounding of both
+    // operands and of |r|^2, plus dpad sequential FP32 FMAs ("certificate")
+    ra.eps_s = (2.0 * ix->dpad + 8.0) * std::ldexp(1.0, -24) * 1.01;
+    ra.r2max = ix->r2max;
+    ra.fb_count = s.fb.p;
+    ra.fb_list = s.fb.p + 1;
+    CK(launch_refine(ra, fp, st));
+    ix->stats.kernel_launches++;
+
+    ea.list = s.fb.p + 1;
+    ea.count = s.fb.p;
+    CK(launch_exact(ea, fp, st));
+    ix->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(s.h_fb, s.fb.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    s.fb_pending = true;
+    return SKNNR_OK;
+}
+
+int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_q, int64_t ldx,
+                     int64_t row_offset, int32_t k, uint32_t flags, int32_t decimals,
+                     double *out_dist, int64_t *out_idx, int32_t weights, double *out_pred,
+                     void *stream) {
+    if (!ix) return fail(SKNNR_EINVAL, "index is NULL");
+    int kk = 0;
+    int rc = check_query_args(ix->n_ref, ix->n_out, n_q, k, flags, weights, X, out_pred, kk);
+    if (rc != SKNNR_OK) return rc;
+    if (x_dtype != SKNNR_F64 && x_dtype != SKNNR_F32) return fail(SKNNR_EINVAL, "bad x_dtype");
+    std::lock_guard<std::mutex> g(ix->lock);
+    CK(cudaSetDevice(ix->device));
+
+    const bool excl = flags & SKNNR_EXCLUDE_SELF;
+    const bool dev_ptrs = (flags & SKNNR_DEVICE_PTRS) || false;
+    bool transformed = flags & SKNNR_TRANSFORMED;
+    bool x_on_device = dev_ptrs;
+    if (excl) {
+        X = ix->d_ref64;
+        x_dtype = SKNNR_F64;
+        n_q = ix->n_ref;
+        ldx = ix->d_out;
+        transformed = true;
+        x_on_device = true;
+    }
+    const int cols = transformed ? ix->d_out : ix->d_in;
+    if (ldx < cols) return fail(SKNNR_EINVAL, "ldx smaller than the number of features");
+    const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
+
+    ix->stats = sknnr_stats{};
+    ix->stats.n_queries = n_q;
+    if (n_q == 0) return SKNNR_OK;
+
+    cudaStream_t user_stream = (cudaStream_t)stream;
+    const int64_t chunk = std::min<int64_t>(g_opt.chunk_rows, (n_q + 255) / 256 * 256);
+    int ci = 0;
+    for (int64_t r0 = 0; r0 < n_q; r0 += chunk, ++ci) {
+        const int64_t rows = std::min(chunk, n_q - r0);
+        Slot &s = dev_ptrs ? ix->slots[0] : ix->slots[ci & 1];
+        cudaStream_t saved = s.stream;
+        if (dev_ptrs) {
+            s.stream = user_stream;
+        } else {
+            CK(cudaStreamSynchronize(s.stream));  // previous chunk on this slot is done
+            ix->harvest(s);
+        }
+        const void *dX;
+        int64_t dld = ldx;
+        if (x_on_device) {
+            dX = (const unsigned char *)X + (size_t)r0 * ldx * esz;
+        } else {
+            CK(s.x.reserve((size_t)rows * cols * esz));
+            CK(cudaMemcpy2DAsync(s.x.p, (size_t)cols * esz,
+                                 (const unsigned char *)X + (size_t)r0 * ldx * esz, (size_t)ldx * esz,
+                                 (size_t)cols * esz, (size_t)rows, cudaMemcpyHostToDevice, s.stream));
+            ix->stats.h2d_bytes += rows * cols * (int64_t)esz;
+            dX = s.x.p;
+            dld = cols;
+        }
+        double *o_dist = nullptr, *o_pred = nullptr;
+        long long *o_idx = nullptr;
+        if (dev_ptrs) {
+            if (out_dist) o_dist = out_dist + r0 * k;
+            if (out_idx) o_idx = (long long *)out_idx + r0 * k;
+            if (weights != SKNNR_W_NONE) o_pred = out_pred + r0 * ix->n_out;
+        } else {
+            if (out_dist) { CK(s.o_dist.reserve((size_t)rows * k)); o_dist = s.o_dist.p; }
+            if (out_idx) { CK(s.o_idx.reserve((size_t)rows * k)); o_idx = s.o_idx.p; }
+            if (weights != SKNNR_W_NONE) { CK(s.o_pred.reserve((size_t)rows * ix->n_out)); o_pred = s.o_pred.p; }
+        }
+        rc = run_chunk(ix, s, dX, x_dtype == SKNNR_F32, dld, transformed, rows, row_offset + r0, k,
+                       flags, decimals, weights, o_dist, o_idx, o_pred);
+        if (rc != SKNNR_OK) { s.stream = saved; return rc; }
+        if (!dev_ptrs) {
+            if (out_dist) {
+                CK(cudaMemcpyAsync(out_dist + r0 * k, o_dist, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, s.stream));
+                ix->stats.d2h_bytes += rows * k * 8;
+            }
+            if (out_idx) {
+                CK(cudaMemcpyAsync(out_idx + r0 * k, o_idx, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, s.stream));
+                ix->stats.d2h_bytes += rows * k * 8;
+            }
+            if (o_pred) {
+                CK(cudaMemcpyAsync(out_pred + r0 * ix->n_out, o_pred, (size_t)rows * ix->n_out * 8, cudaMemcpyDeviceToHost, s.stream));
+                ix->stats.d2h_bytes += rows * ix->n_out * 8;
+            }
+        }
+        s.stream = saved;
+    }
+    if (!dev_ptrs) {
+        for (auto &s : ix->slots) {
+            CK(cudaStreamSynchronize(s.stream));
+            ix->harvest(s);
+        }
+    } else {
+        // counters of a device-pointer call are harvested by the next call / stats query
+        ix->slots[0].fb_pending = false;
+        ix->slots[0].ev_pending = false;
+    }
+    return SKNNR_OK;
+}
+
+int sknnr_transform(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_q, int64_t ldx,
+                    double *out_z) {
+    if (!ix || !X || !out_z || n_q < 0) return fail(SKNNR_EINVAL, "NULL argument");
+    if (ldx < ix->d_in) return fail(SKNNR_EINVAL, "ldx smaller than the number of features");
+    std::lock_guard<std::mutex> g(ix->lock);
+    CK(cudaSetDevice(ix->device));
+    const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
+    Slot &s = ix->slots[0];
+    const int64_t chunk = g_opt.chunk_rows;
+    for (int64_t r0 = 0; r0 < n_q; r0 += chunk) {
+        const int64_t rows = std::min(chunk, n_q - r0);
+        CK(s.x.reserve((size_t)rows * ix->d_in * esz));
+        CK(s.z64.reserve((size_t)rows * ix->d_out));
+        CK(cudaMemcpy2DAsync(s.x.p, (size_t)ix->d_in * esz, (const unsigned char *)X + (size_t)r0 * ldx * esz,
+                             (size_t)ldx * esz, (size_t)ix->d_in * esz, (size_t)rows,
+                             cudaMemcpyHostToDevice, s.stream));
+        CK(launch_project(s.x.p, x_dtype == SKNNR_F32, ix->d_in, rows, ix->d_in, ix->d_out, ix->dpad,
+                          ix->d_center, ix->d_scale, ix->d_proj, ix->d_mu, s.z64.p, nullptr, s.stream));
+        CK(cudaMemcpyAsync(out_z + r0 * ix->d_out, s.z64.p, (size_t)rows * ix->d_out * 8,
+                           cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    return SKNNR_OK;
+}
+
+static int weighted_average_common(IndexBase *ix, const int64_t *idx, const double *w, int64_t n_q,
+                                   int32_t k, double *out_pred) {
+    if (!ix || !idx || !w || !out_pred || n_q < 0 || k < 1) return fail(SKNNR_EINVAL, "NULL argument");
+    if (!ix->d_y) return fail(SKNNR_EINVAL, "index was built without targets");
+    std::lock_guard<std::mutex> g(ix->lock);
+    CK(cudaSetDevice(ix->device));
+    Slot &s = ix->slots[0];
+    CK(s.o_idx.reserve((size_t)n_q * k));
+    CK(s.o_dist.reserve((size_t)n_q * k));
+    CK(s.o_pred.reserve((size_t)n_q * ix->n_out));
+    CK(cudaMemcpyAsync(s.o_idx.p, idx, (size_t)n_q * k * 8, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.o_dist.p, w, (size_t)n_q * k * 8, cudaMemcpyHostToDevice, s.stream));
+    CK(launch_weighted_average(s.o_idx.p, s.o_dist.p, n_q, k, ix->d_y, ix->n_out, s.o_pred.p, s.stream));
+    CK(cudaMemcpyAsync(out_pred, s.o_pred.p, (size_t)n_q * ix->n_out * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    return SKNNR_OK;
+}
+
+int sknnr_weighted_average(sknnr_index *ix, const int64_t *idx, const double *w, int64_t n_q,
+                           int32_t k, double *out_pred) {
+    return weighted_average_common(ix, idx, w, n_q, k, out_pred);
+}
+
+// -----------------------------------------------------------------------------------------
+int sknnr_hamming_index_create(const uint16_t *ref_codes, int64_t n_ref, int32_t n_trees,
+                               const double *w, const double *y, int32_t n_out, int32_t device,
+                               sknnr_hamming_index **out) {
+    if (!ref_codes || !w || !out || n_ref < 1 || n_trees < 1)
+        return fail(SKNNR_EINVAL, "bad arguments to sknnr_hamming_index_create");
+    if (n_ref >= (1LL << 31) - 64) return fail(SKNNR_EUNSUP, "n_ref too large");
+    for (int64_t e = 0; e < n_ref * (int64_t)n_trees; ++e)
+        if (ref_codes[e] > 31743) return fail(SKNNR_EINVAL, "node codes must be <= 31743");
+    if (y == nullptr) n_out = 0;
+    sknnr_hamming_index *ix = new sknnr_hamming_index();
+    int rc = ix->init_common(device, y, n_ref, n_out);
+    if (rc != SKNNR_OK) {
+        ix->release_common();
+        delete ix;
+        return rc;
+    }
+    ix->n_trees = n_trees;
+    ix->n_chunks = (n_trees + 2 * HAM_WC - 1) / (2 * HAM_WC);
+    ix->n_rtiles = (int)((n_ref + RTILE - 1) / RTILE);
+    ix->uniform = true;
+    for (int t = 1; t < n_trees; ++t)
+        if (w[t] != w[0]) ix->uniform = false;
+    // SciPy's denominators / numerators are left-to-right float64 sums
+    volatile double den = 0.0;
+    for (int t = 0; t < n_trees; ++t) den = den + w[t];
+    ix->wsum = den;
+    std::vector<double> lut(n_trees + 1, 0.0);
+    volatile double acc = 0.0;
+    for (int m = 1; m <= n_trees; ++m) {
+        acc = acc + w[0];
+        lut[m] = acc / den;
+    }
+    cudaError_t e = cudaMalloc(&ix->d_rcodes, (size_t)n_ref * n_trees * 2);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ix->d_rcodes, ref_codes, (size_t)n_ref * n_trees * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->d_w, (size_t)n_trees * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(ix->d_w, w, (size_t)n_trees * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->d_lut, lut.size() * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(ix->d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&ix->d_rimg, (size_t)ix->n_rtiles * ix->n_chunks * HAM_WC * RTILE * 4);
+    if (e == cudaSuccess)
+        e = launch_hamming_pack(ix->d_rcodes, n_ref, n_trees, n_trees, ix->n_chunks, RTILE, 31743,
+                                ix->d_rimg, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        sknnr_hamming_index_destroy(ix);
+        CK(e);
+    }
+    *out = ix;
+    return SKNNR_OK;
+}
+
+int sknnr_hamming_index_destroy(sknnr_hamming_index *ix) {
+    if (!ix) return SKNNR_OK;
+    ix->release_common();
+    cudaFree(ix->d_rcodes); cudaFree(ix->d_rimg); cudaFree(ix->d_w); cudaFree(ix->d_lut);
+    delete ix;
+    return SKNNR_OK;
+}
+
+int sknnr_hamming_index_stats(sknnr_hamming_index *ix, sknnr_stats *out) {
+    if (!ix || !out) return fail(SKNNR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(ix->lock);
+    *out = ix->stats;
+    return SKNNR_OK;
+}
+
+static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *dq, int64_t ldq,
+                             int64_t rows, int64_t row0, int k, uint32_t flags, int decimals,
+                             int weights, double *o_dist, long long *o_idx, double *o_pred) {
+    const bool excl = flags & SKNNR_EXCLUDE_SELF;
+    const int kk = k + (excl ? 1 : 0);
+    cudaStream_t st = s.stream;
+    FinishParams fp;
+    fp.k = k;
+    fp.exclude_self = excl ? 1 : 0;
+    fp.deterministic = (flags & SKNNR_DETERMINISTIC) ? 1 : 0;
+    fp.round_scale = std::pow(10.0, (double)decimals);
+    fp.row_offset = row0;
+    fp.out_dist = o_dist;
+    fp.out_idx = o_idx;
+    fp.weights = weights;
+    fp.y = ix->d_y;
+    fp.n_out = ix->n_out;
+    fp.out_pred = o_pred;
+
+    const int kc = pick_kc(kk, 0);
+    const bool fast = ix->uniform && kc != 0 && ix->n_chunks * HAM_WC <= 2048 &&
+                      g_opt.engine != SKNNR_ENGINE_EXACT;
+    ix->stats.engine = fast ? SKNNR_ENGINE_SIMT : SKNNR_ENGINE_EXACT;
+    if (!fast) {
+        ExactArgs ea{};
+        ea.metric = 1;
+        ea.qcodes = dq;
+        ea.rcodes = ix->d_rcodes;
+        ea.n_trees = ix->n_trees;
+        ea.ldc = ix->n_trees;
+        // queries may have their own row stride
+        ea.w = ix->d_w;
+        ea.wsum = ix->wsum;
+        ea.n_q = rows;
+        ea.n_ref = (int)ix->n_ref;
+        ea.grid = (int)std::min<int64_t>(rows, (int64_t)ix->n_sm * 2);
+        CK(s.scratch.reserve((size_t)ix->n_sm * 2 * ix->n_ref));
+        ea.scratch = s.scratch.p;
+        if (ldq != ix->n_trees) return fail(SKNNR_EUNSUP, "strided codes with unequal weights");
+        if (g_opt.timing) CK(cudaEventRecord(s.ev0, st));
+        CK(launch_exact(ea, fp, st));
+        if (g_opt.timing) { CK(cudaEventRecord(s.ev1, st)); s.ev_pending = true; }
+        ix->stats.kernel_launches++;
+        return SKNNR_OK;
+    }
+    const int64_t n_qtiles = (rows + QTILE - 1) / QTILE;
+    CK(s.qimg_h.reserve((size_t)n_qtiles * ix->n_chunks * HAM_WC * QTILE));
+    CK(s.cand_idx.reserve((size_t)rows * kc));
+    CK(s.cand_cnt.reserve((size_t)rows * kc));
+    CK(launch_hamming_pack(dq, rows, ldq, ix->n_trees, ix->n_chunks, QTILE, 31743, s.qimg_h.p, st));
+    if (g_opt.timing) CK(cudaEventRecord(s.ev0, st));
+    CK(launch_hamming_search(s.qimg_h.p, ix->d_rimg, ix->n_chunks, ix->n_rtiles, rows,
+                             (int)ix->n_ref, kc, s.cand_idx.p, s.cand_cnt.p, st));
+    if (g_opt.timing) { CK(cudaEventRecord(s.ev1, st)); s.ev_pending = true; }
+    CK(launch_hamming_finish(s.cand_idx.p, s.cand_cnt.p, kc, ix->d_lut, rows, fp, st));
+    ix->stats.kernel_launches += 3;
+    return SKNNR_OK;
+}
+
+int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, int64_t n_q,
+                             int64_t ldq, int64_t row_offset, int32_t k, uint32_t flags,
+                             int32_t decimals, double *out_dist, int64_t *out_idx,
+                             int32_t weights, double *out_pred, void *stream) {
+    if (!ix) return fail(SKNNR_EINVAL, "index is NULL");
+    int kk = 0;
+    int rc = check_query_args(ix->n_ref, ix->n_out, n_q, k, flags, weights, q_codes, out_pred, kk);
+    if (rc != SKNNR_OK) return rc;
+    std::lock_guard<std::mutex> g(ix->lock);
+    CK(cudaSetDevice(ix->device));
+    const bool excl = flags & SKNNR_EXCLUDE_SELF;
+    const bool dev_ptrs = flags & SKNNR_DEVICE_PTRS;
+    bool q_on_device = dev_ptrs;
+    if (excl) {
+        q_codes = ix->d_rcodes;
+        n_q = ix->n_ref;
+        ldq = ix->n_trees;
+        q_on_device = true;
+    }
+    if (ldq < ix->n_trees) return fail(SKNNR_EINVAL, "ldq smaller than the number of trees");
+    ix->stats = sknnr_stats{};
+    ix->stats.n_queries = n_q;
+    if (n_q == 0) return SKNNR_OK;
+    cudaStream_t user_stream = (cudaStream_t)stream;
+    const int64_t chunk = std::min<int64_t>(g_opt.chunk_rows, (n_q + 255) / 256 * 256);
+    int ci = 0;
+    for (int64_t r0 = 0; r0 < n_q; r0 += chunk, ++ci) {
+        const int64_t rows = std::min(chunk, n_q - r0);
+        Slot &s = dev_ptrs ? ix->slots[0] : ix->slots[ci & 1];
+        cudaStream_t saved = s.stream;
+        if (dev_ptrs) {
+            s.stream = user_stream;
+        } else {
+            CK(cudaStreamSynchronize(s.stream));
+            ix->harvest(s);
+        }
+        const uint16_t *dq;
+        int64_t dld = ldq;
+        if (q_on_device) {
+            dq = q_codes + (size_t)r0 * ldq;
+        } else {
+            CK(s.x.reserve((size_t)rows * ix->n_trees * 2));
+            CK(cudaMemcpy2DAsync(s.x.p, (size_t)ix->n_trees * 2, q_codes + (size_t)r0 * ldq,
+                                 (size_t)ldq * 2, (size_t)ix->n_trees * 2, (size_t)rows,
+                                 cudaMemcpyHostToDevice, s.stream));
+            ix->stats.h2d_bytes += rows * ix->n_trees * 2;
+            dq = (const uint16_t *)s.x.p;
+            dld = ix->n_trees;
+        }
+        double *o_dist = nullptr, *o_pred = nullptr;
+        long long *o_idx = nullptr;
+        if (dev_ptrs) {
+            if (out_dist) o_dist = out_dist + r0 * k;
+            if (out_idx) o_idx = (long long *)out_idx + r0 * k;
+            if (weights != SKNNR_W_NONE) o_pred = out_pred + r0 * ix->n_out;
+        } else {
+            if (out_dist) { CK(s.o_dist.reserve((size_t)rows * k)); o_dist = s.o_dist.p; }
+            if (out_idx) { CK(s.o_idx.reserve((size_t)rows * k)); o_idx = s.o_idx.p; }
+            if (weights != SKNNR_W_NONE) { CK(s.o_pred.reserve((size_t)rows * ix->n_out)); o_pred = s.o_pred.p; }
+        }
+        rc = run_hamming_chunk(ix, s, dq, dld, rows, row_offset + r0, k, flags, decimals, weights,
+                               o_dist, o_idx, o_pred);
+        if (rc != SKNNR_OK) { s.stream = saved; return rc; }
+        if (!dev_ptrs) {
+            if (out_dist) {
+                CK(cudaMemcpyAsync(out_dist + r0 * k, o_dist, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, s.stream));
+                ix->stats.d2h_bytes += rows * k * 8;
+            }
+            if (out_idx) {
+                CK(cudaMemcpyAsync(out_idx + r0 * k, o_idx, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, s.stream));
+                ix->stats.d2h_bytes += rows * k * 8;
+            }
+            if (o_pred) {
+                CK(cudaMemcpyAsync(out_pred + r0 * ix->n_out, o_pred, (size_t)rows * ix->n_out * 8, cudaMemcpyDeviceToHost, s.stream));
+                ix->stats.d2h_bytes += rows * ix->n_out * 8;
+            }
+        }
+        s.stream = saved;
+    }
+    if (!dev_ptrs) {
+        for (auto &s : ix->slots) {
+            CK(cudaStreamSynchronize(s.stream));
+            ix->harvest(s);
+        }
+    } else {
+        ix->slots[0].ev_pending = false;
+    }
+    return SKNNR_OK;
+}
+
+int sknnr_hamming_weighted_average(sknnr_hamming_index *ix, const int64_t *idx, const double *w,
+                                   int64_t n_q, int32_t k, double *out_pred) {
+    return weighted_average_common(ix, idx, w, n_q, k, out_pred);
+}
+
+// -----------------------------------------------------------------------------------------
+int sknnr_measure_fp32_peak(int32_t device, double *tflops) {
+    if (!tflops) return fail(SKNNR_EINVAL, "NULL argument");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(SKNNR_ENODEV, "no CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    float *sink = nullptr;
+    CK(cudaMalloc(&sink, 4));
+    const int grid = prop.multiProcessorCount * 8, iters = 20000;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    CK(launch_fp32_peak(sink, 1000, grid, 0));  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(a, 0));
+        CK(launch_fp32_peak(sink, iters, grid, 0));
+        CK(cudaEventRecord(b, 0));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        const double flops = (double)grid * 256 * iters * 4 * 8 * 2 * 2;  // FFMA2 = 2 FMA = 4 FLOP
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    *tflops = best;
+    return SKNNR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+// Shared device helpers for the sknnr_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <math.h>
+
+#define SK_FULL 0xffffffffu
+#define SK_INF_F __int_as_float(0x7f800000)
+#define SK_INF_D __longlong_as_double(0x7ff0000000000000LL)
+
+namespace sk {
+
+constexpr int QTILE = 256;      // queries per CTA tile (8 compute warps x 32 queries)
+constexpr int RTILE = 64;       // reference plots per staged tile
+constexpr int NCOMPUTE_WARPS = 8;
+constexpr int SEARCH_THREADS = (NCOMPUTE_WARPS + 1) * 32;  // + 1 TMA producer warp
+constexpr int MAXK = 32;        // entries handled by one warp-wide sort
+
+// ---------------------------------------------------------------------------------------
+// mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// warp-wide bitonic sort of one (key, id) per lane, ascending by (key, id)
+// ---------------------------------------------------------------------------------------
+template <typename K>
+__device__ __forceinline__ bool pair_less(K ka, int ia, K kb, int ib) {
+    return (ka < kb) || (ka == kb && ia < ib);
+}
+
+template <typename K>
+__device__ __forceinline__ K shfl_xor_any(K v, int m);
+template <>
+__device__ __forceinline__ float shfl_xor_any<float>(float v, int m) {
+    return __shfl_xor_sync(SK_FULL, v, m);
+}
+template <>
+__device__ __forceinline__ int shfl_xor_any<int>(int v, int m) {
+    return __shfl_xor_sync(SK_FULL, v, m);
+}
+template <>
+__device__ __forceinline__ double shfl_xor_any<double>(double v, int m) {
+    return __shfl_xor_sync(SK_FULL, v, m);
+}
+template <>
+__device__ __forceinline__ long long shfl_xor_any<long long>(long long v, int m) {
+    return __shfl_xor_sync(SK_FULL, v, m);
+}
+
+template <typename K>
+__device__ __forceinline__ void warp_sort_pairs(K &key, int &id, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            K ok = shfl_xor_any<K>(key, stride);
+            int oi = __shfl_xor_sync(SK_FULL, id, stride);
+            bool lower = (lane & stride) == 0;          // I hold the lower slot of the pair
+            bool asc = (lane & size) == 0;              // this block sorts ascending
+            bool other_less = pair_less<K>(ok, oi, key, id);
+            // lower slot of an ascending block keeps the smaller element
+            bool take = (lower == asc) ? other_less : !other_less && !(ok == key && oi == id);
+            if (take) {
+                key = ok;
+                id = oi;
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Sorted candidate lists in shared memory (one list of KC (key, id) entries per query,
+// ascending).  Only the owning warp touches a query's list and lane L only ever touches
+// slot L, so no barrier or atomic is needed.  Returns true when (key, id) was inserted and
+// reports the list's new last entry.
+//   LEX = false : accept only key <  last key            (float scores; exact ties are the
+//                                                          certificate's business)
+//   LEX = true  : accept (key, id) < (last key, last id)  (integer Hamming counts: the lowest
+//                                                          index must win every tie)
+// ---------------------------------------------------------------------------------------
+template <typename K> __device__ __forceinline__ K key_sentinel();
+template <> __device__ __forceinline__ float key_sentinel<float>() { return SK_INF_F; }
+template <> __device__ __forceinline__ int key_sentinel<int>() { return 0x7fffffff; }
+
+template <int KC, typename K, bool LEX>
+__device__ __forceinline__ bool list_insert(K *list_k, int *list_i, int qs, K key, int id,
+                                            int lane, K &last_k, int &last_i) {
+    K ck = key_sentinel<K>();
+    int ci = 0x7fffffff;
+    if (lane < KC) {
+        ck = list_k[qs * KC + lane];
+        ci = list_i[qs * KC + lane];
+    }
+    const K cur_k = __shfl_sync(SK_FULL, ck, KC - 1);
+    const int cur_i = __shfl_sync(SK_FULL, ci, KC - 1);
+    const bool accept = LEX ? pair_less<K>(key, id, cur_k, cur_i) : (key < cur_k);
+    if (!accept) {
+        last_k = cur_k;
+        last_i = cur_i;
+        return false;
+    }
+    const unsigned lt = __ballot_sync(SK_FULL, pair_less<K>(ck, ci, key, id));
+    const int pos = __popc(lt);
+    const K pk = __shfl_up_sync(SK_FULL, ck, 1);
+    const int pi = __shfl_up_sync(SK_FULL, ci, 1);
+    if (lane == pos) {
+        ck = key;
+        ci = id;
+    } else if (lane > pos) {
+        ck = pk;
+        ci = pi;
+    }
+    if (lane < KC) {
+        list_k[qs * KC + lane] = ck;
+        list_i[qs * KC + lane] = ci;
+    }
+    last_k = __shfl_sync(SK_FULL, ck, KC - 1);
+    last_i = __shfl_sync(SK_FULL, ci, KC - 1);
+    return true;
+}
+
+// thread <-> tile coordinates shared by the float and Hamming search kernels: lanes form a
+// 4 (query groups, ty) x 8 (reference groups, tx) grid; a thread's 8 queries are two runs of
+// 4 (LDS.128 each), likewise its 8 references.
+__device__ __forceinline__ int tile_query_slot(int warp, int ty, int i) {
+    return warp * 32 + ((i < 4) ? (ty * 4 + i) : (16 + ty * 4 + (i - 4)));
+}
+__device__ __forceinline__ int tile_ref_slot(int tx, int c) {
+    return (c < 4) ? (tx * 4 + c) : (32 + tx * 4 + (c - 4));
+}
+
+// ---------------------------------------------------------------------------------------
+// finish_query: everything sknnr/sklearn do AFTER the k(+1) nearest are known.
+//   lanes 0..kk-1 hold the exact neighbours sorted ascending by (dist, id).
+//   * X=None self exclusion          $SP/sklearn/neighbors/_base.py:929-958
+//   * deterministic re-ordering      ref:src/sknnr/_base.py:166-175
+//   * outputs f64 / i64              ref:src/sknnr/_base.py:182
+//   * weighted multi-output average  $SP/sklearn/neighbors/_regression.py:254-267 with
+//     weights from _get_weights      $SP/sklearn/neighbors/_base.py:74-117
+// One warp per query.
+// ---------------------------------------------------------------------------------------
+struct FinishParams {
+    int k;              // neighbours to return
+    int exclude_self;   // 1: lanes hold k+1 entries, drop the query itself
+    int deterministic;
+    double round_scale; // 10^decimals
+    long long row_offset;
+    double *out_dist;   // [n_q, k] or null
+    long long *out_idx; // [n_q, k] or null
+    int weights;        // SKNNR_W_*
+    const double *y;    // [n_ref, n_out]
+    int n_out;
+    double *out_pred;   // [n_q, n_out]
+};
+
+__device__ __forceinline__ void finish_query(const FinishParams &p, long long q, double dist,
+                                             int id, int lane) {
+    const long long row = p.row_offset + q;
+    int kk = p.k + (p.exclude_self ? 1 : 0);
+    if (lane >= kk) {
+        dist = SK_INF_D;
+        id = 0x7fffffff;
+    }
+    if (p.exclude_self) {
+        unsigned m = __ballot_sync(SK_FULL, lane < kk && (long long)id == row);
+        int pos = m ? (__ffs(m) - 1) : 0;
+        double nd = __shfl_down_sync(SK_FULL, dist, 1);
+        int ni = __shfl_down_sync(SK_FULL, id, 1);
+        if (lane >= pos) {
+            dist = nd;
+            id = ni;
+        }
+        if (lane >= p.k) {
+            dist = SK_INF_D;
+            id = 0x7fffffff;
+        }
+    }
+    if (p.deterministic) {
+        // row_scale = max(rowmax, 1); rounded = rint(dist / row_scale * 10^dec) / 10^dec
+        double rowmax = __shfl_sync(SK_FULL, dist, p.k - 1);  // ascending -> last is max
+        double scale = fmax(rowmax, 1.0);
+        double key = (lane < p.k) ? rint((dist / scale) * p.round_scale) / p.round_scale : SK_INF_D;
+        long long diff = (long long)id - row;
+        if (diff < 0) diff = -diff;
+        // sort by (key, diff, id): fold (diff, id) into one 64-bit secondary key.  ids and
+        // diffs are < 2^31 for any index this library accepts.
+        long long sec = (lane < p.k) ? ((diff << 31) | (long long)id) : 0x7fffffffffffffffLL;
+        // bitonic network on (key, sec) carrying dist
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                double ok = __shfl_xor_sync(SK_FULL, key, stride);
+                long long os = __shfl_xor_sync(SK_FULL, sec, stride);
+                double od = __shfl_xor_sync(SK_FULL, dist, stride);
+                bool lower = (lane & stride) == 0;
+                bool asc = (lane & size) == 0;
+                bool other_less = (ok < key) || (ok == key && os < sec);
+                bool same = (ok == key && os == sec);
+                bool take = (lower == asc) ? other_less : (!other_less && !same);
+                if (take) {
+                    key = ok;
+                    sec = os;
+                    dist = od;
+                }
+            }
+        }
+        id = (int)(sec & 0x7fffffffLL);
+    }
+    if (lane < p.k) {
+        if (p.out_dist) p.out_dist[q * p.k + lane] = dist;
+        if (p.out_idx) p.out_idx[q * p.k + lane] = (long long)id;
+    }
+    if (p.weights != 0 && p.out_pred != nullptr) {
+        double w = 1.0;
+        if (p.weights == 2) {
+            unsigned zm = __ballot_sync(SK_FULL, lane < p.k && dist == 0.0);
+            if (zm)
+                w = (dist == 0.0) ? 1.0 : 0.0;
+            else
+                w = 1.0 / dist;
+        }
+        if (lane >= p.k) w = 0.0;
+        double denom = 0.0;
+        for (int c = 0; c < p.k; ++c) denom += __shfl_sync(SK_FULL, w, c);
+        for (int j0 = 0; j0 < p.n_out; j0 += 32) {
+            int j = j0 + lane;
+            double num = 0.0;
+            for (int c = 0; c < p.k; ++c) {
+                double wc = __shfl_sync(SK_FULL, w, c);
+                int ic = __shfl_sync(SK_FULL, id, c);
+                if (j < p.n_out) {
+                    double yv = p.y[(long long)ic * p.n_out + j];
+                    num = (p.weights == 1) ? (num + yv) : (num + yv * wc);
+                }
+            }
+            if (j < p.n_out) {
+                p.out_pred[q * p.n_out + j] = (p.weights == 1) ? (num / (double)p.k) : (num / denom);
+            }
+        }
+    }
+}
+
+}  // namespace sk

@@ -1,0 +1,269 @@
+// Integer Hamming distance over random-forest terminal-node IDs + fused top-k
+// (north_star piece 4).  Replaces sklearn's brute Hamming branch -> scipy cdist_hamming
+// ($SP/sklearn/neighbors/_base.py:879-908,715-754; $SP/scipy/spatial/distance.py:1718-1723)
+// reached by RFNNRegressor with metric="hamming" (ref:src/sknnr/_weighted_trees.py:46-59).
+//
+// With equal tree weights (RFNN: ref:src/sknnr/transformers/_rfnode_transformer.py:227-232,
+// ref:src/sknnr/_weighted_trees.py:74-75) the float64 distance is a strictly increasing
+// function of the integer mismatch count, so the kernel ranks by (count, index) - bit-exact -
+// and a host-built table turns counts into the float64 values SciPy produces.
+//
+// Node IDs only need equality, so the host maps them to dense 16-bit codes < 31744.  Read as
+// IEEE half precision those codes are distinct non-negative finite numbers, hence two trees are
+// compared per instruction with HSET2.NE (1.0 / 0.0 per half) and accumulated with HADD2
+// (exact up to 2048 per half): one instruction per ID compare.
+//
+// Same decomposition as search_simt.cu (256 queries per CTA, 8 compute warps + 1 TMA producer
+// warp, 8x8 register tile of accumulators per thread), except that the tree axis is long
+// (T = 500), so both operands stream through the shared-memory ring in chunks of 64 trees:
+// stage = query chunk [32 words][256] + reference chunk [32 words][64] (40 KB).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sk {
+
+constexpr int HAM_QCH = HAM_WC * QTILE;   // u32 words of a query chunk
+constexpr int HAM_RCH = HAM_WC * RTILE;   // u32 words of a reference chunk
+constexpr int HAM_STAGE = HAM_QCH + HAM_RCH;
+
+// ---- pack: u16 codes [n, ldc] -> [n_tiles][n_chunks][HAM_WC][tile] u32 -----------------
+__global__ void __launch_bounds__(256)
+hamming_pack_kernel(const uint16_t *__restrict__ codes, long long n, long long ldc, int n_trees,
+                    int n_chunks, int tile, uint16_t pad_code, uint32_t *__restrict__ img) {
+    __shared__ uint32_t buf[HAM_WC][QTILE + 1];
+    const long long tileno = blockIdx.x;
+    const int chunk = blockIdx.y;
+    const long long row0 = tileno * tile;
+    for (int e = threadIdx.x; e < tile * HAM_WC; e += 256) {
+        const int r = e / HAM_WC, w = e - r * HAM_WC;
+        const long long row = row0 + r;
+        const int t0 = 2 * (chunk * HAM_WC + w);
+        uint32_t lo = 0, hi = 0;
+        if (row < n) {
+            if (t0 < n_trees) lo = codes[row * ldc + t0];
+            if (t0 + 1 < n_trees) hi = codes[row * ldc + t0 + 1];
+        } else {
+            if (t0 < n_trees) lo = pad_code;
+            if (t0 + 1 < n_trees) hi = pad_code;
+        }
+        buf[w][r] = lo | (hi << 16);
+    }
+    __syncthreads();
+    uint32_t *out = img + ((size_t)tileno * n_chunks + chunk) * HAM_WC * tile;
+    for (int e = threadIdx.x; e < tile * HAM_WC; e += 256) {
+        const int w = e / tile, r = e - w * tile;
+        out[e] = buf[w][r];
+    }
+}
+
+cudaError_t launch_hamming_pack(const uint16_t *codes, long long n, long long ldc, int n_trees,
+                                int n_chunks, int tile, uint16_t pad_code, uint32_t *img,
+                                cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const long long tiles = (n + tile - 1) / tile;
+    dim3 grid((unsigned)tiles, (unsigned)n_chunks);
+    hamming_pack_kernel<<<grid, 256, 0, st>>>(codes, n, ldc, n_trees, n_chunks, tile, pad_code, img);
+    return cudaGetLastError();
+}
+
+// ---- search ---------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(SEARCH_THREADS, 1)
+hamming_search_kernel(const uint32_t *__restrict__ qimg, const uint32_t *__restrict__ rimg,
+                      int n_chunks, int n_rtiles, int nstage, long long n_q, int n_ref,
+                      int *__restrict__ cand_idx, int *__restrict__ cand_cnt) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *stage0 = reinterpret_cast<uint32_t *>(smem_raw);
+    int *list_c = reinterpret_cast<int *>(stage0 + (size_t)nstage * HAM_STAGE);
+    int *list_i = list_c + QTILE * KC;
+    uint64_t *full = reinterpret_cast<uint64_t *>(list_i + QTILE * KC);
+    uint64_t *empty = full + nstage;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCOMPUTE_WARPS);
+        }
+        fence_mbar_init();
+    }
+    for (int e = threadIdx.x; e < QTILE * KC; e += SEARCH_THREADS) {
+        list_c[e] = 0x7fffffff;
+        list_i[e] = 0x7fffffff;
+    }
+    __syncthreads();
+
+    const long long qtile = blockIdx.x;
+    const int n_steps = n_rtiles * n_chunks;
+
+    if (warp == NCOMPUTE_WARPS) {
+        if (lane == 0) {
+            int c = 0, t = 0;
+            for (int step = 0; step < n_steps; ++step) {
+                const int s = step % nstage;
+                if (step >= nstage) mbar_wait(&empty[s], ((step / nstage) - 1) & 1);
+                uint32_t *dst = stage0 + (size_t)s * HAM_STAGE;
+                mbar_expect_tx(&full[s], HAM_STAGE * 4u);
+                bulk_g2s(dst, qimg + ((size_t)qtile * n_chunks + c) * HAM_QCH, HAM_QCH * 4u, &full[s]);
+                bulk_g2s(dst + HAM_QCH, rimg + ((size_t)t * n_chunks + c) * HAM_RCH, HAM_RCH * 4u,
+                         &full[s]);
+                if (++c == n_chunks) {
+                    c = 0;
+                    ++t;
+                }
+            }
+        }
+        return;
+    }
+
+    const int ty = lane >> 3, tx = lane & 7;
+    int thr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) thr[i] = 0x7fffffff;
+
+    __half2 acc[8][8];
+    int step = 0;
+    for (int t = 0; t < n_rtiles; ++t) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = __floats2half2_rn(0.f, 0.f);
+
+        for (int c = 0; c < n_chunks; ++c, ++step) {
+            const int s = step % nstage;
+            mbar_wait(&full[s], (step / nstage) & 1);
+            const uint32_t *qp = stage0 + (size_t)s * HAM_STAGE + warp * 32 + ty * 4;
+            const uint32_t *rp = stage0 + (size_t)s * HAM_STAGE + HAM_QCH + tx * 4;
+#pragma unroll 4
+            for (int w = 0; w < HAM_WC; ++w) {
+                const uint4 qa = *reinterpret_cast<const uint4 *>(qp + w * QTILE);
+                const uint4 qb = *reinterpret_cast<const uint4 *>(qp + w * QTILE + 16);
+                const uint4 ra = *reinterpret_cast<const uint4 *>(rp + w * RTILE);
+                const uint4 rb = *reinterpret_cast<const uint4 *>(rp + w * RTILE + 32);
+                const uint32_t qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                const uint32_t rv[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __half2 qh = *reinterpret_cast<const __half2 *>(&qv[i]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const __half2 rh = *reinterpret_cast<const __half2 *>(&rv[j]);
+                        acc[i][j] = __hadd2(acc[i][j], __hne2(qh, rh));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+        // ---- selection on exact integer counts, ties broken by the lowest index ----
+        int cnt[8][8];
+        bool rowhit[8];
+        bool anyhit = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int mn = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                cnt[i][j] = (int)(__low2float(acc[i][j]) + __high2float(acc[i][j]));
+                mn = min(mn, cnt[i][j]);
+            }
+            rowhit[i] = mn <= thr[i];
+            anyhit |= rowhit[i];
+        }
+        if (__any_sync(SK_FULL, anyhit)) {
+            const int idbase = t * RTILE;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned mrow = __ballot_sync(SK_FULL, rowhit[i]);
+                if (mrow == 0) continue;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int myid = idbase + tile_ref_slot(tx, c);
+                    unsigned m = __ballot_sync(SK_FULL, cnt[i][c] <= thr[i] && myid < n_ref);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int c_l = __shfl_sync(SK_FULL, cnt[i][c], src);
+                        const int ty_l = src >> 3, tx_l = src & 7;
+                        const int qs = tile_query_slot(warp, ty_l, i);
+                        const int id_l = idbase + tile_ref_slot(tx_l, c);
+                        int nthr, nid;
+                        list_insert<KC, int, true>(list_c, list_i, qs, c_l, id_l, lane, nthr, nid);
+                        if (ty == ty_l) thr[i] = nthr;
+                    }
+                }
+            }
+        }
+    }
+
+    for (int ql = 0; ql < 32; ++ql) {
+        const int qs = warp * 32 + ql;
+        const long long q = qtile * QTILE + qs;
+        if (q >= n_q) break;
+        if (lane < KC) {
+            cand_idx[q * KC + lane] = list_i[qs * KC + lane];
+            cand_cnt[q * KC + lane] = list_c[qs * KC + lane];
+        }
+    }
+}
+
+static size_t hamming_smem_bytes(int kc, int nstage) {
+    return (size_t)nstage * HAM_STAGE * 4 + (size_t)QTILE * kc * 8 + (size_t)2 * nstage * 8;
+}
+
+template <int KC>
+static cudaError_t launch_ham_kc(const uint32_t *qimg, const uint32_t *rimg, int n_chunks,
+                                 int n_rtiles, long long n_q, int n_ref, int *cand_idx,
+                                 int *cand_cnt, cudaStream_t st) {
+    int nstage = 4;
+    while (nstage > 2 && hamming_smem_bytes(KC, nstage) > 227 * 1024) --nstage;
+    const size_t smem = hamming_smem_bytes(KC, nstage);
+    cudaError_t e = cudaFuncSetAttribute(hamming_search_kernel<KC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    const long long n_qtiles = (n_q + QTILE - 1) / QTILE;
+    hamming_search_kernel<KC><<<(unsigned)n_qtiles, SEARCH_THREADS, smem, st>>>(
+        qimg, rimg, n_chunks, n_rtiles, nstage, n_q, n_ref, cand_idx, cand_cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hamming_search(const uint32_t *qimg, const uint32_t *rimg, int n_chunks,
+                                  int n_rtiles, long long n_q, int n_ref, int kc, int *cand_idx,
+                                  int *cand_cnt, cudaStream_t st) {
+    if (n_q <= 0) return cudaSuccess;
+    switch (kc) {
+        case 8: return launch_ham_kc<8>(qimg, rimg, n_chunks, n_rtiles, n_q, n_ref, cand_idx, cand_cnt, st);
+        case 16: return launch_ham_kc<16>(qimg, rimg, n_chunks, n_rtiles, n_q, n_ref, cand_idx, cand_cnt, st);
+        case 32: return launch_ham_kc<32>(qimg, rimg, n_chunks, n_rtiles, n_q, n_ref, cand_idx, cand_cnt, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---- counts -> float64 distances, then the common epilogue ------------------------------
+__global__ void __launch_bounds__(256)
+hamming_finish_kernel(const int *__restrict__ cand_idx, const int *__restrict__ cand_cnt, int kc,
+                      const double *__restrict__ lut, long long n_q, FinishParams fp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * 8 + warp;
+    if (q >= n_q) return;
+    double d = SK_INF_D;
+    int id = 0x7fffffff;
+    if (lane < kc) {
+        id = cand_idx[q * kc + lane];
+        const int c = cand_cnt[q * kc + lane];
+        if (id != 0x7fffffff) d = lut[c];
+    }
+    finish_query(fp, q, d, id, lane);
+}
+
+cudaError_t launch_hamming_finish(const int *cand_idx, const int *cand_cnt, int kc,
+                                  const double *lut, long long n_q, const FinishParams &fp,
+                                  cudaStream_t st) {
+    if (n_q <= 0) return cudaSuccess;
+    const long long grid = (n_q + 7) / 8;
+    hamming_finish_kernel<<<(unsigned)grid, 256, 0, st>>>(cand_idx, cand_cnt, kc, lut, n_q, fp);
+    return cudaGetLastError();
+}
+
+}  // namespace sk

@@ -1,0 +1,89 @@
+// Host-callable launchers of the sknnr_b200 kernels (internal; the public ABI is
+// include/sknnr_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace sk {
+
+struct FinishParams;
+
+// ---- project.cu: Z = ((X - center) / scale) @ proj  (S2, a1-a4) -----------------------
+// Writes Z as float64 rows (exact re-rank operand) and as the search kernel's query tile
+// image [n_qtiles][dpad][256] f32 = -2 * (Z - mu).
+cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long n_q, int d_in,
+                           int d_out, int dpad, const double *center, const double *scale,
+                           const double *proj, const double *mu, double *z64, float *qimg,
+                           cudaStream_t st);
+
+// ---- search_simt.cu --------------------------------------------------------------------
+size_t search_simt_smem_bytes(int dpad, int kc, int nstage);
+int search_simt_pick_stages(int dpad, int kc);
+cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, int n_rtiles,
+                               long long n_q, int kc, int *cand_idx, float *cand_thr,
+                               cudaStream_t st);
+
+// ---- refine.cu -------------------------------------------------------------------------
+struct RefineArgs {
+    const double *z64;      // [n_q, d] queries in the estimator's space
+    const double *ref64;    // [n_ref, d]
+    const double *mu;       // [d] centroid used by the search images
+    const int *cand_idx;    // [n_q, kc]
+    const float *cand_thr;  // [n_q]
+    int kc;
+    int d;
+    long long n_q;
+    int n_ref;
+    double eps_s;           // relative error bound of the approximate score
+    double r2max;           // max_j |ref_j - mu|^2
+    int *fb_count;          // number of uncertified queries (device)
+    int *fb_list;           // their row numbers (device, capacity n_q)
+};
+cudaError_t launch_refine(const RefineArgs &a, const FinishParams &fp, cudaStream_t st);
+
+// Exhaustive float64 search for the rows in list[0..*count) (or all rows when list==null):
+// one CTA per row, all references, exact (distance, index) top-k, then finish_query.
+struct ExactArgs {
+    int metric;             // 0 = Euclidean (z64/ref64), 1 = weighted Hamming (codes + w)
+    const double *z64;
+    const double *ref64;
+    int d;
+    const uint16_t *qcodes; // [n_q, ldc]
+    const uint16_t *rcodes; // [n_ref, ldc]
+    int n_trees;
+    int ldc;
+    const double *w;        // [n_trees]
+    double wsum;
+    long long n_q;
+    int n_ref;
+    const int *list;
+    const int *count;
+    double *scratch;        // [grid, n_ref]
+    int grid;
+};
+cudaError_t launch_exact(const ExactArgs &a, const FinishParams &fp, cudaStream_t st);
+
+// S3 with caller weights
+cudaError_t launch_weighted_average(const long long *idx, const double *w, long long n_q, int k,
+                                    const double *y, int n_out, double *out_pred,
+                                    cudaStream_t st);
+
+// ---- hamming.cu ------------------------------------------------------------------------
+constexpr int HAM_WC = 32;  // packed 32-bit words (= 64 trees) per staged chunk
+// pack u16 codes [n, ldc] into tile images [n_tiles][n_chunks][HAM_WC][tile] u32
+cudaError_t launch_hamming_pack(const uint16_t *codes, long long n, long long ldc, int n_trees,
+                                int n_chunks, int tile, uint16_t pad_code, uint32_t *img,
+                                cudaStream_t st);
+cudaError_t launch_hamming_search(const uint32_t *qimg, const uint32_t *rimg, int n_chunks,
+                                  int n_rtiles, long long n_q, int n_ref, int kc, int *cand_idx,
+                                  int *cand_cnt, cudaStream_t st);
+// mismatch counts -> float64 distances through the host-built table, then finish_query
+cudaError_t launch_hamming_finish(const int *cand_idx, const int *cand_cnt, int kc,
+                                  const double *lut, long long n_q, const FinishParams &fp,
+                                  cudaStream_t st);
+
+// ---- misc ------------------------------------------------------------------------------
+cudaError_t launch_fp32_peak(float *sink, int iters, int grid, cudaStream_t st);
+
+}  // namespace sk

@@ -1,0 +1,107 @@
+// Projection into the estimator's feature space (north_star piece 1; seam S2,
+// ref:src/sknnr/_base.py:236-239).  One affine map covers the four float transformers:
+//     Z = ((X - center) / scale) @ proj
+//   StandardScalerWithDOF   $SP/sklearn/preprocessing/_data.py:1131-1134
+//   MahalanobisTransformer  ref:src/sknnr/transformers/_mahalanobis_transformer.py:55
+//   CCorATransformer        ref:src/sknnr/transformers/_ccora_transformer.py:70
+//   CCATransformer          ref:src/sknnr/transformers/_cca_transformer.py:87
+// computed in float64 exactly as written (true division, centre first).  Raw map pixels are
+// read from HBM once; the kernel emits both operands the rest of the path needs:
+//   z64  [n_q, d_out] float64          - exact re-rank operand
+//   qimg [n_qtiles][dpad][256] float32 - search-kernel query tile image, -2 * (Z - mu)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sk {
+
+constexpr int PROJ_THREADS = QTILE;  // one thread per query row of the tile
+constexpr int PROJ_KCHUNK = 8;
+
+template <typename TX>
+__global__ void __launch_bounds__(PROJ_THREADS)
+project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in, int d_out,
+               int dpad, const double *__restrict__ center, const double *__restrict__ scale,
+               const double *__restrict__ proj, const double *__restrict__ mu,
+               double *__restrict__ z64, float *__restrict__ qimg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int xs_ld = d_in | 1;  // odd row stride (in doubles): conflict-free row reads
+    double *xs = reinterpret_cast<double *>(smem_raw);           // [256][xs_ld]
+    double *ps = xs + (size_t)PROJ_THREADS * xs_ld;              // [d_in][d_out] (if proj)
+    const long long q0 = (long long)blockIdx.x * QTILE;
+    const int rows = (int)min((long long)QTILE, n_q - q0);
+
+    // coalesced load of the tile's rows, centring and scaling on the way in
+    for (int e = threadIdx.x; e < QTILE * d_in; e += PROJ_THREADS) {
+        const int r = e / d_in, c = e - r * d_in;
+        double v = 0.0;
+        if (r < rows) {
+            v = (double)X[(q0 + r) * ldx + c];
+            if (center) v -= center[c];
+            if (scale) v /= scale[c];
+        }
+        xs[r * xs_ld + c] = v;
+    }
+    if (proj)
+        for (int e = threadIdx.x; e < d_in * d_out; e += PROJ_THREADS) ps[e] = proj[e];
+    __syncthreads();
+
+    const int r = threadIdx.x;
+    const double *xr = xs + r * xs_ld;
+    float *qt = qimg ? qimg + (size_t)blockIdx.x * dpad * QTILE + r : nullptr;
+    for (int k0 = 0; k0 < dpad; k0 += PROJ_KCHUNK) {
+        double z[PROJ_KCHUNK];
+#pragma unroll
+        for (int kk = 0; kk < PROJ_KCHUNK; ++kk) z[kk] = 0.0;
+        if (proj) {
+            for (int i = 0; i < d_in; ++i) {
+                const double xv = xr[i];
+                const double *pr = ps + i * d_out + k0;
+#pragma unroll
+                for (int kk = 0; kk < PROJ_KCHUNK; ++kk)
+                    if (k0 + kk < d_out) z[kk] += xv * pr[kk];
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < PROJ_KCHUNK; ++kk)
+                if (k0 + kk < d_out) z[kk] = xr[k0 + kk];
+        }
+#pragma unroll
+        for (int kk = 0; kk < PROJ_KCHUNK; ++kk) {
+            const int k = k0 + kk;
+            float sv = 0.0f;
+            if (k < d_out && r < rows) {
+                z64[(q0 + r) * d_out + k] = z[kk];
+                sv = (float)(-2.0 * (z[kk] - mu[k]));
+            }
+            if (qt) qt[(size_t)k * QTILE] = sv;
+        }
+    }
+}
+
+cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long n_q, int d_in,
+                           int d_out, int dpad, const double *center, const double *scale,
+                           const double *proj, const double *mu, double *z64, float *qimg,
+                           cudaStream_t st) {
+    if (n_q <= 0) return cudaSuccess;
+    const int xs_ld = d_in | 1;
+    const size_t smem = ((size_t)PROJ_THREADS * xs_ld + (proj ? (size_t)d_in * d_out : 0)) * 8;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    const long long grid = (n_q + QTILE - 1) / QTILE;
+    cudaError_t e;
+    if (x_is_f32) {
+        e = cudaFuncSetAttribute(project_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024);
+        if (e != cudaSuccess) return e;
+        project_kernel<float><<<(unsigned)grid, PROJ_THREADS, smem, st>>>(
+            (const float *)X, ldx, n_q, d_in, d_out, dpad, center, scale, proj, mu, z64, qimg);
+    } else {
+        e = cudaFuncSetAttribute(project_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024);
+        if (e != cudaSuccess) return e;
+        project_kernel<double><<<(unsigned)grid, PROJ_THREADS, smem, st>>>(
+            (const double *)X, ldx, n_q, d_in, d_out, dpad, center, scale, proj, mu, z64, qimg);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sk

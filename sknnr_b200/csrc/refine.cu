@@ -1,0 +1,211 @@
+// Exact float64 epilogue of the search (SURVEY.md build-plan step 5):
+//   refine_kernel  - re-evaluates the <= KC survivors of the FP32/TF32 search in float64,
+//                    sorts them by (distance, index), proves with a rigorous error bound that
+//                    no reference outside the survivor list can belong to the k nearest (the
+//                    "certificate"), and finishes the row (self exclusion, sknnr's
+//                    deterministic ordering, outputs, weighted average);
+//   exact_kernel   - exhaustive float64 search for the rows whose certificate failed (and the
+//                    engine for shapes the fast kernels do not cover / unequal Hamming weights);
+//   weighted_average_kernel - seam S3 with caller-supplied weights.
+//
+// The reference computes distances from the float64 expansion |x|^2 - 2x.y + |y|^2
+// ($SP/sklearn/metrics/_pairwise_distances_reduction/_argkmin.pyx.tp:494-502) and returns
+// sqrt of it (:285-295); here the k winners' distances come from direct float64 differences,
+// which agree with it to the reference's own rounding noise (<= 1e-7 relative on raw features).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sk {
+
+constexpr int REFINE_WARPS = 8;
+
+__global__ void __launch_bounds__(REFINE_WARPS * 32)
+refine_kernel(RefineArgs a, FinishParams fp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * REFINE_WARPS + warp;
+    if (q >= a.n_q) return;
+    const double *zq = a.z64 + q * a.d;
+
+    int id = 0x7fffffff;
+    double d2 = SK_INF_D;
+    if (lane < a.kc) {
+        const int c = a.cand_idx[q * a.kc + lane];
+        if (c >= 0 && c < a.n_ref) {
+            id = c;
+            const double *r = a.ref64 + (long long)c * a.d;
+            double acc = 0.0;
+            for (int k = 0; k < a.d; ++k) {
+                const double df = zq[k] - r[k];
+                acc += df * df;
+            }
+            d2 = acc;
+        }
+    }
+    // |z_q - mu|^2 (lanes stride the features, then butterfly-reduce)
+    double qn = 0.0;
+    for (int k = lane; k < a.d; k += 32) {
+        const double df = zq[k] - a.mu[k];
+        qn += df * df;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(SK_FULL, qn, o);
+
+    warp_sort_pairs<double>(d2, id, lane);
+
+    const int kk = fp.k + (fp.exclude_self ? 1 : 0);
+    const double kth = __shfl_sync(SK_FULL, d2, kk - 1);
+    const float thr = a.cand_thr[q];
+    // every reference outside the list has approximate score >= thr, hence true squared
+    // distance >= thr + |q|^2 - E with E = eps_s * (|q|^2 + max|r|^2)
+    bool ok;
+    if (thr == SK_INF_F) {
+        ok = true;  // the list holds every reference
+    } else {
+        const double bound = (double)thr + qn - a.eps_s * (qn + a.r2max);
+        ok = kth < bound;
+    }
+    if (!ok) {
+        if (lane == 0) {
+            const int pos = atomicAdd(a.fb_count, 1);
+            a.fb_list[pos] = (int)q;
+        }
+        return;
+    }
+    finish_query(fp, q, sqrt(d2), id, lane);
+}
+
+cudaError_t launch_refine(const RefineArgs &a, const FinishParams &fp, cudaStream_t st) {
+    if (a.n_q <= 0) return cudaSuccess;
+    const long long grid = (a.n_q + REFINE_WARPS - 1) / REFINE_WARPS;
+    refine_kernel<<<(unsigned)grid, REFINE_WARPS * 32, 0, st>>>(a, fp);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+constexpr int EXACT_THREADS = 256;
+
+__device__ __forceinline__ double exact_pair(const ExactArgs &a, long long q, int j) {
+    if (a.metric == 0) {
+        const double *zq = a.z64 + q * a.d;
+        const double *r = a.ref64 + (long long)j * a.d;
+        double acc = 0.0;
+        for (int k = 0; k < a.d; ++k) {
+            const double df = zq[k] - r[k];
+            acc += df * df;
+        }
+        return acc;
+    }
+    // weighted Hamming: left-to-right float64 sum of w_t over mismatching trees / sum(w)
+    // ($SP/scipy/spatial/distance.py:1718-1723 -> cdist_hamming)
+    const uint16_t *qc = a.qcodes + q * a.ldc;
+    const uint16_t *rc = a.rcodes + (long long)j * a.ldc;
+    double num = 0.0;
+    for (int t = 0; t < a.n_trees; ++t) {
+        if (qc[t] != rc[t]) num = __dadd_rn(num, a.w[t]);
+    }
+    return num / a.wsum;
+}
+
+__global__ void __launch_bounds__(EXACT_THREADS)
+exact_kernel(ExactArgs a, FinishParams fp) {
+    __shared__ double red_d[EXACT_THREADS / 32];
+    __shared__ int red_i[EXACT_THREADS / 32];
+    __shared__ double sel_d[MAXK];
+    __shared__ int sel_i[MAXK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_rows = a.list ? (long long)(*a.count) : a.n_q;
+    double *scr = a.scratch + (size_t)blockIdx.x * a.n_ref;
+    const int kk = fp.k + (fp.exclude_self ? 1 : 0);
+
+    for (long long it = blockIdx.x; it < n_rows; it += gridDim.x) {
+        const long long q = a.list ? (long long)a.list[it] : it;
+        for (int j = threadIdx.x; j < a.n_ref; j += EXACT_THREADS) scr[j] = exact_pair(a, q, j);
+        __syncthreads();
+        double last_d = -1.0;
+        int last_i = -1;
+        for (int r = 0; r < kk; ++r) {
+            double bd = SK_INF_D;
+            int bi = 0x7fffffff;
+            for (int j = threadIdx.x; j < a.n_ref; j += EXACT_THREADS) {
+                const double d = scr[j];
+                const bool after = (d > last_d) || (d == last_d && j > last_i);
+                if (after && pair_less<double>(d, j, bd, bi)) {
+                    bd = d;
+                    bi = j;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(SK_FULL, bd, o);
+                const int oi = __shfl_xor_sync(SK_FULL, bi, o);
+                if (pair_less<double>(od, oi, bd, bi)) {
+                    bd = od;
+                    bi = oi;
+                }
+            }
+            if (lane == 0) {
+                red_d[warp] = bd;
+                red_i[warp] = bi;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < EXACT_THREADS / 32; ++w)
+                    if (pair_less<double>(red_d[w], red_i[w], bd, bi)) {
+                        bd = red_d[w];
+                        bi = red_i[w];
+                    }
+                sel_d[r] = bd;
+                sel_i[r] = bi;
+                red_d[0] = bd;
+                red_i[0] = bi;
+            }
+            __syncthreads();
+            last_d = red_d[0];
+            last_i = red_i[0];
+            __syncthreads();
+        }
+        if (warp == 0) {
+            double d = (lane < kk) ? sel_d[lane] : SK_INF_D;
+            const int id = (lane < kk) ? sel_i[lane] : 0x7fffffff;
+            if (a.metric == 0) d = sqrt(d);
+            finish_query(fp, q, d, id, lane);
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_exact(const ExactArgs &a, const FinishParams &fp, cudaStream_t st) {
+    if (a.grid <= 0) return cudaSuccess;
+    exact_kernel<<<a.grid, EXACT_THREADS, 0, st>>>(a, fp);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void weighted_average_kernel(const long long *__restrict__ idx,
+                                        const double *__restrict__ w, long long n_q, int k,
+                                        const double *__restrict__ y, int n_out,
+                                        double *__restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= n_q) return;
+    double denom = 0.0;
+    for (int c = 0; c < k; ++c) denom += w[q * k + c];
+    for (int j = lane; j < n_out; j += 32) {
+        double num = 0.0;
+        for (int c = 0; c < k; ++c) num += y[idx[q * k + c] * n_out + j] * w[q * k + c];
+        out[q * n_out + j] = num / denom;
+    }
+}
+
+cudaError_t launch_weighted_average(const long long *idx, const double *w, long long n_q, int k,
+                                    const double *y, int n_out, double *out_pred,
+                                    cudaStream_t st) {
+    if (n_q <= 0) return cudaSuccess;
+    const int warps = 8;
+    const long long grid = (n_q + warps - 1) / warps;
+    weighted_average_kernel<<<(unsigned)grid, warps * 32, 0, st>>>(idx, w, n_q, k, y, n_out,
+                                                                  out_pred);
+    return cudaGetLastError();
+}
+
+}  // namespace sk

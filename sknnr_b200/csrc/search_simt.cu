@@ -1,0 +1,220 @@
+// Fused FP32 distance + top-KC candidate selection (north_star pieces 2 + 3), SIMT engine.
+//
+// Replaces the hot loop of scikit-learn's EuclideanArgKmin64
+// ($SP/sklearn/metrics/_pairwise_distances_reduction/_argkmin.pyx.tp:401-510: dgemm tile,
+// d2 = |x|^2 - 2x.y + |y|^2, one heap test per pair), reached from
+// ref:src/sknnr/_base.py:162-164.  The n_q x n_ref distance matrix never reaches HBM.
+//
+// Work decomposition (one CTA = 256 queries, 8 compute warps + 1 TMA producer warp):
+//   * the CTA's query tile image [dpad][256] f32 (pre-scaled by -2, centroid-shifted) is
+//     staged once with one 1-D TMA bulk copy;
+//   * reference tiles of 64 plots, image [(dpad+1)][64] f32 whose last row holds |r|^2, stream
+//     through an NSTAGE-deep ring filled by the producer warp (cp.async.bulk + mbarrier
+//     complete_tx) and released by the compute warps through "empty" mbarriers;
+//   * each compute warp owns 32 queries; lanes form a 4 (query groups) x 8 (reference groups)
+//     grid and every thread keeps an 8 query x 8 reference register tile of FP32 scores
+//     s = |r|^2 - 2 q.r accumulated with packed FFMA2 (two references per instruction);
+//   * selection: one compare per pair against the query's current KC-th best score; hits
+//     (k*ln(n_ref/k) per query) are inserted into the query's sorted list in shared memory
+//     with a warp-wide ballot/shift.  Only the owning warp touches a query's list and lane L
+//     only touches slot L, so the hit path needs no atomics and no barrier.
+//
+// Output: for every query the KC best references by approximate score (ascending) and the
+// KC-th score.  Exact float64 distances, ordering and the certificate that no better
+// reference was missed are the refine kernel's job (refine.cu).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sk {
+
+template <int KC>
+__global__ void __launch_bounds__(SEARCH_THREADS, 1)
+search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int dpad,
+                   int n_rtiles, int nstage, long long n_q, int *__restrict__ cand_idx,
+                   float *__restrict__ cand_thr) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int rtile_floats = (dpad + 1) * RTILE;
+    float *Qs = reinterpret_cast<float *>(smem_raw);
+    float *Rs = Qs + (size_t)dpad * QTILE;
+    float *list_s = Rs + (size_t)nstage * rtile_floats;
+    int *list_i = reinterpret_cast<int *>(list_s + QTILE * KC);
+    uint64_t *full = reinterpret_cast<uint64_t *>(list_i + QTILE * KC);
+    uint64_t *empty = full + nstage;
+    uint64_t *qbar = empty + nstage;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCOMPUTE_WARPS);
+        }
+        mbar_init(qbar, 1);
+        fence_mbar_init();
+    }
+    for (int e = threadIdx.x; e < QTILE * KC; e += SEARCH_THREADS) {
+        list_s[e] = SK_INF_F;
+        list_i[e] = -1;
+    }
+    __syncthreads();
+
+    const long long qtile = blockIdx.x;
+
+    if (warp == NCOMPUTE_WARPS) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            const uint32_t qbytes = (uint32_t)dpad * QTILE * 4u;
+            const uint32_t rbytes = (uint32_t)rtile_floats * 4u;
+            mbar_expect_tx(qbar, qbytes);
+            bulk_g2s(Qs, qimg + (size_t)qtile * dpad * QTILE, qbytes, qbar);
+            for (int t = 0; t < n_rtiles; ++t) {
+                const int s = t % nstage;
+                if (t >= nstage) mbar_wait(&empty[s], ((t / nstage) - 1) & 1);
+                mbar_expect_tx(&full[s], rbytes);
+                bulk_g2s(Rs + (size_t)s * rtile_floats, rimg + (size_t)t * rtile_floats, rbytes,
+                         &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    const int ty = lane >> 3;  // query group 0..3
+    const int tx = lane & 7;   // reference group 0..7
+    const float *qp = Qs + warp * 32 + ty * 4;
+    float thr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) thr[i] = SK_INF_F;
+
+    mbar_wait(qbar, 0);
+
+    for (int t = 0; t < n_rtiles; ++t) {
+        const int s = t % nstage;
+        mbar_wait(&full[s], (t / nstage) & 1);
+        const float *rp = Rs + (size_t)s * rtile_floats + tx * 4;
+
+        float2 acc[8][4];
+        {
+            const float4 n0 = *reinterpret_cast<const float4 *>(rp + dpad * RTILE);
+            const float4 n1 = *reinterpret_cast<const float4 *>(rp + dpad * RTILE + 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc[i][0] = make_float2(n0.x, n0.y);
+                acc[i][1] = make_float2(n0.z, n0.w);
+                acc[i][2] = make_float2(n1.x, n1.y);
+                acc[i][3] = make_float2(n1.z, n1.w);
+            }
+        }
+        for (int k0 = 0; k0 < dpad; k0 += 8) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int k = k0 + kk;
+                const float4 qa = *reinterpret_cast<const float4 *>(qp + k * QTILE);
+                const float4 qb = *reinterpret_cast<const float4 *>(qp + k * QTILE + 16);
+                const float4 ra = *reinterpret_cast<const float4 *>(rp + k * RTILE);
+                const float4 rb = *reinterpret_cast<const float4 *>(rp + k * RTILE + 32);
+                const float2 r0 = make_float2(ra.x, ra.y), r1 = make_float2(ra.z, ra.w);
+                const float2 r2 = make_float2(rb.x, rb.y), r3 = make_float2(rb.z, rb.w);
+                const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 qd = make_float2(qv[i], qv[i]);
+                    acc[i][0] = __ffma2_rn(qd, r0, acc[i][0]);
+                    acc[i][1] = __ffma2_rn(qd, r1, acc[i][1]);
+                    acc[i][2] = __ffma2_rn(qd, r2, acc[i][2]);
+                    acc[i][3] = __ffma2_rn(qd, r3, acc[i][3]);
+                }
+            }
+        }
+        // the staged tile is no longer needed: hand the slot back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+
+        // ---------------- selection ----------------
+        bool rowhit[8];
+        bool anyhit = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float m0 = fminf(fminf(acc[i][0].x, acc[i][0].y), fminf(acc[i][1].x, acc[i][1].y));
+            const float m1 = fminf(fminf(acc[i][2].x, acc[i][2].y), fminf(acc[i][3].x, acc[i][3].y));
+            rowhit[i] = fminf(m0, m1) < thr[i];
+            anyhit |= rowhit[i];
+        }
+        if (__any_sync(SK_FULL, anyhit)) {
+            const int idbase = t * RTILE;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned mrow = __ballot_sync(SK_FULL, rowhit[i]);
+                if (mrow == 0) continue;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float sc = (c & 1) ? acc[i][c >> 1].y : acc[i][c >> 1].x;
+                    unsigned m = __ballot_sync(SK_FULL, sc < thr[i]);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float s_l = __shfl_sync(SK_FULL, sc, src);
+                        const int ty_l = src >> 3, tx_l = src & 7;
+                        const int qs = tile_query_slot(warp, ty_l, i);
+                        const int id_l = idbase + tile_ref_slot(tx_l, c);
+                        float nthr;
+                        int nid;
+                        list_insert<KC, float, false>(list_s, list_i, qs, s_l, id_l, lane, nthr, nid);
+                        if (ty == ty_l) thr[i] = nthr;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---------------- write candidates ----------------
+    for (int ql = 0; ql < 32; ++ql) {
+        const int qs = warp * 32 + ql;
+        const long long q = qtile * QTILE + qs;
+        if (q >= n_q) break;
+        if (lane < KC) {
+            cand_idx[q * KC + lane] = list_i[qs * KC + lane];
+            if (lane == KC - 1) cand_thr[q] = list_s[qs * KC + lane];
+        }
+    }
+}
+
+size_t search_simt_smem_bytes(int dpad, int kc, int nstage) {
+    return (size_t)dpad * QTILE * 4 + (size_t)nstage * (dpad + 1) * RTILE * 4 +
+           (size_t)QTILE * kc * 8 + (size_t)(2 * nstage + 1) * 8;
+}
+
+int search_simt_pick_stages(int dpad, int kc) {
+    for (int s = 4; s >= 2; --s)
+        if (search_simt_smem_bytes(dpad, kc, s) <= 227 * 1024) return s;
+    return 0;
+}
+
+template <int KC>
+static cudaError_t launch_kc(const float *qimg, const float *rimg, int dpad, int n_rtiles,
+                             long long n_q, int *cand_idx, float *cand_thr, cudaStream_t st) {
+    const int nstage = search_simt_pick_stages(dpad, KC);
+    if (nstage == 0) return cudaErrorInvalidValue;
+    const size_t smem = search_simt_smem_bytes(dpad, KC, nstage);
+    cudaError_t e = cudaFuncSetAttribute(search_simt_kernel<KC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    const long long n_qtiles = (n_q + QTILE - 1) / QTILE;
+    search_simt_kernel<KC><<<(unsigned)n_qtiles, SEARCH_THREADS, smem, st>>>(
+        qimg, rimg, dpad, n_rtiles, nstage, n_q, cand_idx, cand_thr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, int n_rtiles,
+                               long long n_q, int kc, int *cand_idx, float *cand_thr,
+                               cudaStream_t st) {
+    switch (kc) {
+        case 8: return launch_kc<8>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, st);
+        case 16: return launch_kc<16>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, st);
+        case 32: return launch_kc<32>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace sk

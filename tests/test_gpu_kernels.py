@@ -1,0 +1,252 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle and golden fixtures."""
+
+import numpy as np
+import pytest
+
+from oracle import sknnr_oracle as orc
+from tests.conftest import FLOAT_CASES, load_golden, state_from_golden
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances (BASELINE.json north_star): distances / predictions within 1e-5 relative,
+# with an absolute floor for d -> 0 where the reference's own float64 expansion is noisy.
+RTOL = 1e-5
+
+
+def _index(st):
+    from sknnr_b200._engine import KNNIndex
+
+    return KNNIndex(st.fit_Z, st.center, st.scale, st.proj, st.y)
+
+
+def _atol(st):
+    # the reference's expansion error scales with the squared norms of the operands
+    z = st.fit_Z
+    return 1e-7 * float(np.sqrt((z * z).sum(1).max())) + 1e-12
+
+
+@pytest.mark.parametrize(("name", "comp"), FLOAT_CASES)
+def test_golden_kneighbors_and_predict(name, comp):
+    g = load_golden(f"moscow_{name}_{comp}.npz")
+    sp = load_golden("moscow_split.npz")
+    st = state_from_golden(g)
+    ix = _index(st)
+    atol = _atol(st)
+    # X given: projection + search + ordering
+    d, i, p = ix.query(sp["X_test"], 5, weights="uniform", with_pred=True)
+    np.testing.assert_array_equal(i, g["refgold_tgt_index_nn"])
+    np.testing.assert_allclose(d, g["refgold_tgt_index_dist"], rtol=RTOL, atol=atol)
+    np.testing.assert_allclose(p, g["refgold_tgt_unweighted_pred"], rtol=RTOL, atol=1e-8)
+    # X=None: k+1 with self excluded, independent prediction and score
+    d, i, p = ix.query(None, 5, exclude_self=True, weights="uniform", with_pred=True)
+    np.testing.assert_array_equal(i, g["refgold_ref_index_nn"])
+    np.testing.assert_allclose(d, g["refgold_ref_index_dist"], rtol=RTOL, atol=atol)
+    np.testing.assert_allclose(p, g["refgold_ref_unweighted_pred"], rtol=RTOL, atol=1e-8)
+    assert orc.r2_score_uniform(sp["y_train"], p) == pytest.approx(
+        float(g["refgold_ref_unweighted_score"]), abs=1e-6)
+    # distance weights
+    _, _, p = ix.query(sp["X_test"], 5, weights="distance", with_pred=True)
+    np.testing.assert_allclose(p, g["live_tgt_pred_distance"], rtol=RTOL, atol=1e-8)
+    # callable weights: evaluated on host, averaged on device
+    d, i, _ = ix.query(sp["X_test"], 5)
+    p = ix.weighted_average(i, 1.0 / (1.0 + d))
+    np.testing.assert_allclose(p, g["refgold_tgt_weighted_pred"], rtol=RTOL, atol=1e-8)
+    # raw (non-deterministic) ordering is plain ascending distance
+    d, i, _ = ix.query(sp["X_test"], 5, deterministic=False)
+    np.testing.assert_allclose(d, g["live_tgt_dist_raw"], rtol=RTOL, atol=atol)
+    # S2 alone
+    np.testing.assert_allclose(ix.transform(sp["X_train"]), g["state_fit_Z"], rtol=1e-9, atol=1e-9)
+
+
+def test_config1_swo_msn():
+    g = load_golden("c1_swo_msn_k5.npz")
+    st = state_from_golden(g)
+    ix = _index(st)
+    d, i, p = ix.query(None, 5, exclude_self=True, weights="uniform", with_pred=True)
+    orc.assert_tie_aware_equal(d, i, g["live_ref_dist"], g["live_ref_nn"], rtol=RTOL, atol=_atol(st))
+    assert orc.r2_score_uniform(g["y_targets"], p) == pytest.approx(float(g["live_ref_score"]), abs=1e-6)
+    d, i, p = ix.query(g["X"], 5, weights="distance", with_pred=True)
+    orc.assert_tie_aware_equal(d, i, g["live_self_dist"], g["live_self_nn"], rtol=RTOL, atol=1e-5)
+    assert ix.stats()["n_queries"] == 3005
+
+
+def test_config2_moscow_gnn_independent_score():
+    g = load_golden("c2_moscow_gnn_k5.npz")
+    st = state_from_golden(g)
+    ix = _index(st)
+    d, i, p = ix.query(None, 5, exclude_self=True, weights="uniform", with_pred=True)
+    np.testing.assert_array_equal(i, g["live_ref_nn"])
+    np.testing.assert_allclose(d, g["live_ref_dist"], rtol=RTOL, atol=_atol(st))
+    np.testing.assert_allclose(p, g["live_ref_pred"], rtol=RTOL, atol=1e-8)
+    assert orc.r2_score_uniform(g["y_targets"], p) == pytest.approx(float(g["live_ref_score"]), abs=1e-6)
+
+
+def _synthetic(n_ref, n_q, d, n_out=4, seed=0, corr=False):
+    rng = np.random.default_rng(seed)
+    R = rng.standard_normal((n_ref, d))
+    Q = np.random.default_rng(seed + 2).standard_normal((n_q, d))
+    if corr:
+        A = np.random.default_rng(3).standard_normal((d, d)) / np.sqrt(d)
+        R, Q = R @ A, Q @ A
+    y = np.random.default_rng(seed + 1).standard_normal((n_ref, n_out))
+    return R, Q, y
+
+
+@pytest.mark.parametrize(("n_ref", "n_q", "d", "k"), [
+    (5000, 3000, 32, 7), (777, 1001, 17, 5), (20000, 2048, 64, 7), (300, 257, 3, 1),
+    (4096, 512, 40, 15), (5000, 700, 8, 24),
+])
+def test_synthetic_euclidean_matches_oracle(n_ref, n_q, d, k):
+    R, Q, y = _synthetic(n_ref, n_q, d)
+    mean, scale = R.mean(0), R.std(0, ddof=1)
+    st = orc.FittedState("euclidean", fit_Z=(R - mean) / scale, y=y, center=mean, scale=scale)
+    ix = _index(st)
+    d_o, i_o = orc.kneighbors(st, Q, k=k)
+    p_o = orc.weighted_average(y, i_o, orc.get_weights(d_o, "distance"))
+    d_g, i_g, p_g = ix.query(Q, k, weights="distance", with_pred=True)
+    orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=RTOL, atol=1e-7)
+    same = (i_g == i_o).all(axis=1)
+    np.testing.assert_allclose(p_g[same], p_o[same], rtol=RTOL, atol=1e-8)
+    # float32 queries take the same path (converted to float64 on the device)
+    d32, i32, _ = ix.query(Q.astype(np.float32), k)
+    assert (i32 == i_o).mean() > 0.99
+    # sharded call with row offsets == one call
+    h = n_q // 2
+    d_a, i_a, _ = ix.query(Q[:h], k)
+    d_b, i_b, _ = ix.query(Q[h:], k, row_offset=h)
+    np.testing.assert_array_equal(np.vstack([i_a, i_b]), i_g)
+    np.testing.assert_array_equal(np.vstack([d_a, d_b]), d_g)
+
+
+def test_mahalanobis_projection_and_engines_agree():
+    from sknnr_b200 import _lib as L
+
+    R, Q, y = _synthetic(6000, 1500, 24, corr=True)
+    mean, scale = R.mean(0), R.std(0, ddof=1)
+    Rs = (R - mean) / scale
+    W = np.linalg.inv(np.linalg.cholesky(np.cov(Rs, rowvar=False)).T)
+    st = orc.FittedState("euclidean", fit_Z=Rs @ W, y=y, center=mean, scale=scale, proj=W)
+    ix = _index(st)
+    d_o, i_o = orc.kneighbors(st, Q, k=7)
+    d_g, i_g, _ = ix.query(Q, 7)
+    orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=RTOL, atol=1e-7)
+    assert ix.stats()["engine"] == L.ENGINE_SIMT
+    L.set_option("engine", L.ENGINE_EXACT)
+    try:
+        d_e, i_e, _ = ix.query(Q, 7)
+        assert ix.stats()["engine"] == L.ENGINE_EXACT
+    finally:
+        L.set_option("engine", L.ENGINE_AUTO)
+    np.testing.assert_array_equal(i_e, i_g)
+    np.testing.assert_array_equal(d_e, d_g)
+
+
+def test_adversarial_duplicates_offsets_and_self_queries():
+    rng = np.random.default_rng(5)
+    R = rng.standard_normal((2000, 6))
+    R[:, 0] += 500.0 * R[:, 0].std()          # constant-offset feature (mean/std = 500)
+    R[100:140] = R[100]                        # 40 exact duplicates (> k+1)
+    R[300:303] = R[300]
+    y = rng.standard_normal((2000, 3))
+    st = orc.FittedState("euclidean", fit_Z=R.copy(), y=y)
+    ix = _index(st)
+    Q = np.vstack([R[:500], R[100:102] + 1e-9, rng.standard_normal((50, 6)) + R.mean(0)])
+    d_o, i_o = orc.kneighbors(st, Q, k=5)
+    d_g, i_g, _ = ix.query(Q, 5, transformed=True)
+    # the reference's expansion is noisy at d -> 0 with a 500-sigma offset: absolute floor
+    orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=RTOL, atol=2e-4, gap_rtol=1e-6)
+    # exact duplicates: the lowest indices win, exactly like the reference's heap
+    assert i_g[100].tolist() == [100, 101, 102, 103, 104]
+    assert np.all(d_g[100] == 0)
+    # X=None with >= k+1 duplicates drops column 0 when the row itself is not returned
+    d_s, i_s, _ = ix.query(None, 5, exclude_self=True, deterministic=False)
+    assert i_s[139].tolist() == [101, 102, 103, 104, 105]
+    assert i_s[100].tolist() == [101, 102, 103, 104, 105]
+    d_so, i_so = orc.kneighbors(st, None, k=5, deterministic=False)
+    np.testing.assert_array_equal(i_s[100:140], i_so[100:140])
+    assert ix.stats()["n_fallback"] >= 40      # the tie certificate routed them to the exact kernel
+
+
+def test_ordering_known_answers():
+    """ref:tests/test_estimators.py:306-378 through the device epilogue."""
+    from sknnr_b200._engine import KNNIndex
+
+    ix = KNNIndex(np.array([1e-11, 1e-12, 1.0]).reshape(-1, 1), y=np.array([0.0, 1.0, 2.0]))
+    q = np.array([[0.0], [0.0]])
+    assert ix.query(q[:1], 2, deterministic=False)[1][0].tolist() == [1, 0]
+    assert ix.query(q[:1], 2, deterministic=True)[1][0].tolist() == [0, 1]
+    assert ix.query(q, 2)[1].tolist() == [[0, 1], [1, 0]]
+    assert ix.query(q[:1], 2, row_offset=1)[1].tolist() == [[1, 0]]
+    ix = KNNIndex(np.array([1e-3, 1e-6, 1e-9, 1.0]).reshape(-1, 1))
+    for dec, exp in ((8, [2, 1, 0]), (5, [1, 2, 0]), (2, [0, 1, 2])):
+        assert ix.query(np.array([[0.0]]), 3, decimals=dec)[1][0].tolist() == exp
+
+
+def test_error_behaviour():
+    from sknnr_b200._engine import KNNIndex
+
+    ix = KNNIndex(np.random.default_rng(0).standard_normal((10, 3)))
+    with pytest.raises(ValueError, match="n_neighbors <= n_samples_fit"):
+        ix.query(np.zeros((2, 3)), 11)
+    with pytest.raises(ValueError, match="n_neighbors < n_samples_fit"):
+        ix.query(None, 10, exclude_self=True)
+    with pytest.raises(ValueError, match="features"):
+        ix.query(np.zeros((2, 4)), 2)
+    with pytest.raises(NotImplementedError):
+        KNNIndex(np.random.default_rng(0).standard_normal((100, 3))).query(np.zeros((2, 3)), 40)
+    d, i, _ = ix.query(np.zeros((0, 3)), 2)
+    assert d.shape == (0, 2) and i.shape == (0, 2)
+
+
+# ---- Hamming / RFNN -------------------------------------------------------------------
+def _ham_index(codes, w, y=None):
+    from sknnr_b200._engine import HammingIndex
+
+    return HammingIndex(codes, w, y)
+
+
+def test_hamming_golden_rfnn_bit_exact():
+    g = load_golden("moscow_rfnn.npz")
+    ref = g["ids_train"].astype(np.int64)
+    tgt = g["ids_test"].astype(np.int64)
+    st = orc.FittedState("hamming", fit_Z=ref, y=g["y"], hamming_w=g["hamming_w"])
+    ix = _ham_index(ref.astype(np.uint16), g["hamming_w"], g["y"])
+    d_o, i_o = orc.kneighbors(st, tgt, k=5)
+    d_g, i_g, p_g = ix.query(tgt.astype(np.uint16), 5, weights="uniform", with_pred=True)
+    np.testing.assert_array_equal(i_g, i_o)          # canonical oracle: bit-exact indices
+    assert np.array_equal(d_g, d_o)                  # and bit-exact float64 distances
+    assert np.array_equal(d_g, g["live_tgt_dist"])   # == the live reference's distances
+    orc.assert_tie_aware_equal(d_g, i_g, g["live_tgt_dist"], g["live_tgt_nn"], rtol=0, atol=0, gap_rtol=0)
+    np.testing.assert_allclose(p_g, orc.weighted_average(g["y"], i_o), rtol=1e-12)
+    d_o, i_o = orc.kneighbors(st, None, k=5)
+    d_g, i_g, _ = ix.query(None, 5, exclude_self=True)
+    np.testing.assert_array_equal(i_g, i_o)
+    assert np.array_equal(d_g, d_o)
+    # unequal (user-supplied forest) weights: exact float64 kernel, still bit-exact
+    w2 = g["hamming_w_nonuniform"]
+    st2 = orc.FittedState("hamming", fit_Z=ref, y=g["y"], hamming_w=w2)
+    ix2 = _ham_index(ref.astype(np.uint16), w2, g["y"])
+    d_o, i_o = orc.kneighbors(st2, tgt, k=5)
+    d_g, i_g, _ = ix2.query(tgt.astype(np.uint16), 5)
+    np.testing.assert_array_equal(i_g, i_o)
+    assert np.array_equal(d_g, d_o)
+    assert np.array_equal(d_g, g["live_tgt_dist_nonuniform"])
+
+
+@pytest.mark.parametrize(("n_ref", "n_q", "T", "k", "n_codes"), [
+    (3000, 1000, 500, 7, 40), (500, 300, 63, 5, 3), (1000, 257, 130, 1, 31743), (2000, 400, 64, 12, 8),
+])
+def test_hamming_synthetic_bit_exact(n_ref, n_q, T, k, n_codes):
+    rng = np.random.default_rng(7)
+    R = rng.integers(0, n_codes, size=(n_ref, T))
+    # queries resemble references (as forest leaves do) so that small counts occur
+    Q = R[rng.integers(0, n_ref, size=n_q)].copy()
+    flip = rng.random(Q.shape) < 0.4
+    Q[flip] = rng.integers(0, n_codes, size=int(flip.sum()))
+    w = np.full(T, 1.0 / T / 3)
+    st = orc.FittedState("hamming", fit_Z=R, y=np.zeros((n_ref, 1)), hamming_w=w)
+    d_o, i_o = orc.kneighbors(st, Q, k=k)
+    ix = _ham_index(R.astype(np.uint16), w)
+    d_g, i_g, _ = ix.query(Q.astype(np.uint16), k)
+    np.testing.assert_array_equal(i_g, i_o)
+    assert np.array_equal(d_g, d_o)
