@@ -40,6 +40,7 @@ struct Options {
     int64_t engine = SKNNR_ENGINE_AUTO;
     int64_t chunk_rows = 1 << 20;
     int64_t timing = 0;
+    int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
 } g_opt;
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -88,19 +89,30 @@ struct Slot {
     DevBuf<long long> o_idx;
     DevBuf<double> o_pred;
     DevBuf<double> scratch;        // exact kernel distance scratch [grid, n_ref]
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_pending = false;
+    std::vector<cudaEvent_t> evs;  // pooled (start, stop) pairs around the search kernels
+    size_t ev_used = 0;            // events handed out since the last harvest
     int *h_fb = nullptr;           // pinned: fallback count of the chunk in flight
     bool fb_pending = false;
     void release() {
         x.release(); z64.release(); qimg.release(); qimg_h.release(); cand_idx.release();
         cand_thr.release(); cand_cnt.release(); fb.release(); o_dist.release();
         o_idx.release(); o_pred.release(); scratch.release();
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
+        for (auto e : evs) cudaEventDestroy(e);
+        evs.clear();
+        ev_used = 0;
         if (h_fb) cudaFreeHost(h_fb);
         if (own_stream && stream) cudaStreamDestroy(stream);
-        ev0 = ev1 = nullptr; h_fb = nullptr; stream = nullptr;
+        h_fb = nullptr; stream = nullptr;
+    }
+    // record a timing event on `st` (pairs: even = start, odd = stop)
+    cudaError_t mark(cudaStream_t st) {
+        if (ev_used == evs.size()) {
+            cudaEvent_t e;
+            cudaError_t rc = cudaEventCreate(&e);
+            if (rc != cudaSuccess) return rc;
+            evs.push_back(e);
+        }
+        return cudaEventRecord(evs[ev_used++], st);
     }
 };
 
@@ -136,8 +148,6 @@ struct IndexBase {
         for (auto &s : slots) {
             CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             s.own_stream = true;
-            CK(cudaEventCreate(&s.ev0));
-            CK(cudaEventCreate(&s.ev1));
             CK(cudaHostAlloc((void **)&s.h_fb, sizeof(int), cudaHostAllocDefault));
             *s.h_fb = 0;
         }
@@ -151,11 +161,13 @@ struct IndexBase {
     }
     // collect timing / fallback count of the chunk that last ran on this slot
     void harvest(Slot &s) {
-        if (s.ev_pending) {
+        for (size_t i = 0; i + 1 < s.ev_used; i += 2) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, s.ev0, s.ev1) == cudaSuccess) stats.search_ms += ms;
-            s.ev_pending = false;
+            if (cudaEventSynchronize(s.evs[i + 1]) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, s.evs[i], s.evs[i + 1]) == cudaSuccess)
+                stats.search_ms += ms;
         }
+        s.ev_used = 0;
         if (s.fb_pending) {
             stats.n_fallback += *s.h_fb;
             s.fb_pending = false;
@@ -227,6 +239,10 @@ int sknnr_set_option(const char *name, int64_t value) {
         g_opt.chunk_rows = (value + 255) / 256 * 256;
     } else if (!strcmp(name, "timing")) {
         g_opt.timing = value ? 1 : 0;
+    } else if (!strcmp(name, "kc")) {
+        if (value != 0 && value != 8 && value != 16 && value != 32)
+            return fail(SKNNR_EINVAL, "kc must be 0, 8, 16 or 32");
+        g_opt.kc = value;
     } else {
         return fail(SKNNR_EINVAL, std::string("unknown option ") + name);
     }
@@ -330,6 +346,8 @@ int sknnr_index_destroy(sknnr_index *ix) {
 int sknnr_index_stats(sknnr_index *ix, sknnr_stats *out) {
     if (!ix || !out) return fail(SKNNR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> g(ix->lock);
+    cudaSetDevice(ix->device);
+    for (auto &s : ix->slots) ix->harvest(s);
     *out = ix->stats;
     return SKNNR_OK;
 }
@@ -345,6 +363,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
 
     int engine = (int)g_opt.engine;
     int kc = pick_kc(kk, 1);
+    if (g_opt.kc > kc) kc = (int)g_opt.kc;
     if (engine == SKNNR_ENGINE_AUTO || engine == SKNNR_ENGINE_TENSOR) engine = SKNNR_ENGINE_SIMT;
     if (kc == 0 || search_simt_pick_stages(ix->dpad, kc ? kc : 8) == 0) engine = SKNNR_ENGINE_EXACT;
     ix->stats.engine = engine;
@@ -384,9 +403,9 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     if (engine == SKNNR_ENGINE_EXACT) {
         ea.list = nullptr;
         ea.count = nullptr;
-        if (g_opt.timing) CK(cudaEventRecord(s.ev0, st));
+        if (g_opt.timing) CK(s.mark(st));
         CK(launch_exact(ea, fp, st));
-        if (g_opt.timing) { CK(cudaEventRecord(s.ev1, st)); s.ev_pending = true; }
+        if (g_opt.timing) CK(s.mark(st));
         ix->stats.kernel_launches++;
         return SKNNR_OK;
     }
@@ -395,10 +414,10 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     CK(s.cand_thr.reserve((size_t)rows));
     CK(s.fb.reserve((size_t)rows + 1));
     CK(cudaMemsetAsync(s.fb.p, 0, sizeof(int), st));
-    if (g_opt.timing) CK(cudaEventRecord(s.ev0, st));
+    if (g_opt.timing) CK(s.mark(st));
     CK(launch_search_simt(s.qimg.p, ix->d_rimg, ix->dpad, ix->n_rtiles, rows, kc, s.cand_idx.p,
                           s.cand_thr.p, st));
-    if (g_opt.timing) { CK(cudaEventRecord(s.ev1, st)); s.ev_pending = true; }
+    if (g_opt.timing) CK(s.mark(st));
     ix->stats.kernel_launches++;
 
     RefineArgs ra{};
@@ -457,6 +476,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     if (ldx < cols) return fail(SKNNR_EINVAL, "ldx smaller than the number of features");
     const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
 
+    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; }
     ix->stats = sknnr_stats{};
     ix->stats.n_queries = n_q;
     if (n_q == 0) return SKNNR_OK;
@@ -522,11 +542,8 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             CK(cudaStreamSynchronize(s.stream));
             ix->harvest(s);
         }
-    } else {
-        // counters of a device-pointer call are harvested by the next call / stats query
-        ix->slots[0].fb_pending = false;
-        ix->slots[0].ev_pending = false;
     }
+    // a device-pointer call is not synchronised: its counters are harvested by the stats query
     return SKNNR_OK;
 }
 
@@ -643,6 +660,8 @@ int sknnr_hamming_index_destroy(sknnr_hamming_index *ix) {
 int sknnr_hamming_index_stats(sknnr_hamming_index *ix, sknnr_stats *out) {
     if (!ix || !out) return fail(SKNNR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> g(ix->lock);
+    cudaSetDevice(ix->device);
+    for (auto &s : ix->slots) ix->harvest(s);
     *out = ix->stats;
     return SKNNR_OK;
 }
@@ -686,9 +705,9 @@ static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *d
         CK(s.scratch.reserve((size_t)ix->n_sm * 2 * ix->n_ref));
         ea.scratch = s.scratch.p;
         if (ldq != ix->n_trees) return fail(SKNNR_EUNSUP, "strided codes with unequal weights");
-        if (g_opt.timing) CK(cudaEventRecord(s.ev0, st));
+        if (g_opt.timing) CK(s.mark(st));
         CK(launch_exact(ea, fp, st));
-        if (g_opt.timing) { CK(cudaEventRecord(s.ev1, st)); s.ev_pending = true; }
+        if (g_opt.timing) CK(s.mark(st));
         ix->stats.kernel_launches++;
         return SKNNR_OK;
     }
@@ -697,10 +716,10 @@ static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *d
     CK(s.cand_idx.reserve((size_t)rows * kc));
     CK(s.cand_cnt.reserve((size_t)rows * kc));
     CK(launch_hamming_pack(dq, rows, ldq, ix->n_trees, ix->n_chunks, QTILE, 31743, s.qimg_h.p, st));
-    if (g_opt.timing) CK(cudaEventRecord(s.ev0, st));
+    if (g_opt.timing) CK(s.mark(st));
     CK(launch_hamming_search(s.qimg_h.p, ix->d_rimg, ix->n_chunks, ix->n_rtiles, rows,
                              (int)ix->n_ref, kc, s.cand_idx.p, s.cand_cnt.p, st));
-    if (g_opt.timing) { CK(cudaEventRecord(s.ev1, st)); s.ev_pending = true; }
+    if (g_opt.timing) CK(s.mark(st));
     CK(launch_hamming_finish(s.cand_idx.p, s.cand_cnt.p, kc, ix->d_lut, rows, fp, st));
     ix->stats.kernel_launches += 3;
     return SKNNR_OK;
@@ -726,6 +745,7 @@ int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, i
         q_on_device = true;
     }
     if (ldq < ix->n_trees) return fail(SKNNR_EINVAL, "ldq smaller than the number of trees");
+    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; }
     ix->stats = sknnr_stats{};
     ix->stats.n_queries = n_q;
     if (n_q == 0) return SKNNR_OK;
@@ -790,8 +810,6 @@ int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, i
             CK(cudaStreamSynchronize(s.stream));
             ix->harvest(s);
         }
-    } else {
-        ix->slots[0].ev_pending = false;
     }
     return SKNNR_OK;
 }

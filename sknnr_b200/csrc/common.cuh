@@ -12,10 +12,10 @@
 
 namespace sk {
 
-constexpr int QTILE = 256;      // queries per CTA tile (8 compute warps x 32 queries)
+constexpr int NCOMPUTE_WARPS = 12;
+constexpr int QTILE = 32 * NCOMPUTE_WARPS;  // queries per CTA tile (32 per compute warp)
 constexpr int RTILE = 64;       // reference plots per staged tile
-constexpr int NCOMPUTE_WARPS = 8;
-constexpr int SEARCH_THREADS = (NCOMPUTE_WARPS + 1) * 32;  // + 1 TMA producer warp
+constexpr int SEARCH_THREADS = NCOMPUTE_WARPS * 32;  // lane 0 of warp 0 also issues the TMA copies
 constexpr int MAXK = 32;        // entries handled by one warp-wide sort
 
 // ---------------------------------------------------------------------------------------
@@ -173,6 +173,79 @@ __device__ __forceinline__ int tile_query_slot(int warp, int ty, int i) {
 }
 __device__ __forceinline__ int tile_ref_slot(int tx, int c) {
     return (c < 4) ? (tx * 4 + c) : (32 + tx * 4 + (c - 4));
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Register-resident candidate lists (KC = 8 * EPL <= 16).  The 8 lanes that share a query
+// (same ty, tx = 0..7) hold its sorted list in registers: lane tx keeps list positions
+// tx*EPL .. tx*EPL+EPL-1 of each of its 8 queries, so an insertion is a handful of width-8
+// shuffles and the four lane groups of a warp insert into four different queries at once.
+// No shared memory, no atomics, no barrier.
+// ---------------------------------------------------------------------------------------
+template <int EPL, typename K, bool LEX>
+__device__ __forceinline__ void group_insert(K (&lk)[EPL], int (&li)[EPL], bool valid, K key,
+                                             int id, int tx, int ty, K &thr_k) {
+    const K last_k = __shfl_sync(SK_FULL, lk[EPL - 1], 7, 8);
+    const int last_i = __shfl_sync(SK_FULL, li[EPL - 1], 7, 8);
+    const bool accept = valid && (LEX ? pair_less<K>(key, id, last_k, last_i) : (key < last_k));
+    int pos = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+        const unsigned b = __ballot_sync(SK_FULL, pair_less<K>(lk[e], li[e], key, id));
+        pos += __popc((b >> (ty * 8)) & 0xffu);
+    }
+    const K prev_k = __shfl_up_sync(SK_FULL, lk[EPL - 1], 1, 8);
+    const int prev_i = __shfl_up_sync(SK_FULL, li[EPL - 1], 1, 8);
+    if (accept) {
+#pragma unroll
+        for (int e = EPL - 1; e >= 0; --e) {
+            const int p = tx * EPL + e;
+            const K sk = (e > 0) ? lk[e > 0 ? e - 1 : 0] : prev_k;
+            const int si = (e > 0) ? li[e > 0 ? e - 1 : 0] : prev_i;
+            if (p > pos) {
+                lk[e] = sk;
+                li[e] = si;
+            } else if (p == pos) {
+                lk[e] = key;
+                li[e] = id;
+            }
+        }
+    }
+    thr_k = __shfl_sync(SK_FULL, lk[EPL - 1], 7, 8);
+}
+
+template <typename T>
+__device__ __forceinline__ T select8(const T (&v)[8], int c) {
+    const T a = (c & 1) ? v[1] : v[0];
+    const T b = (c & 1) ? v[3] : v[2];
+    const T d = (c & 1) ? v[5] : v[4];
+    const T e = (c & 1) ? v[7] : v[6];
+    const T ab = (c & 2) ? b : a;
+    const T de = (c & 2) ? e : d;
+    return (c & 4) ? de : ab;
+}
+
+// Drain the hits of one tile row (one of the thread's 8 queries): `sc` are this thread's 8
+// scores for the row, `hm` the bit mask of those still below the threshold.  Every iteration
+// each lane group elects its first lane with a pending hit and inserts that hit.
+template <int EPL, typename K, bool LEX>
+__device__ __forceinline__ void drain_row(const K (&sc)[8], unsigned hm, K (&lk)[EPL], int (&li)[EPL],
+                                          K &thr, int idbase, int id_limit, int tx, int ty) {
+    while (true) {
+        const unsigned act = __ballot_sync(SK_FULL, hm != 0);
+        if (act == 0) break;
+        const unsigned g = (act >> (ty * 8)) & 0xffu;
+        const bool gvalid = g != 0;
+        const int ltx = gvalid ? (__ffs(g) - 1) : 0;
+        const int c = (hm != 0) ? (__ffs(hm) - 1) : 0;
+        const K my = select8<K>(sc, c);
+        const int myid = idbase + tile_ref_slot(tx, c);
+        const K key = __shfl_sync(SK_FULL, my, ltx, 8);
+        const int id = __shfl_sync(SK_FULL, myid, ltx, 8);
+        if (gvalid && tx == ltx) hm &= hm - 1;
+        group_insert<EPL, K, LEX>(lk, li, gvalid && id < id_limit, key, id, tx, ty, thr);
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -13,10 +13,10 @@
 // compared per instruction with HSET2.NE (1.0 / 0.0 per half) and accumulated with HADD2
 // (exact up to 2048 per half): one instruction per ID compare.
 //
-// Same decomposition as search_simt.cu (256 queries per CTA, 8 compute warps + 1 TMA producer
-// warp, 8x8 register tile of accumulators per thread), except that the tree axis is long
+// Same decomposition as search_simt.cu (384 queries per CTA, 12 warps, lane 0 of warp 0 issues
+// the TMA copies, 8x8 register tile of accumulators per thread), except that the tree axis is long
 // (T = 500), so both operands stream through the shared-memory ring in chunks of 64 trees:
-// stage = query chunk [32 words][256] + reference chunk [32 words][64] (40 KB).
+// stage = query chunk [32 words][384] + reference chunk [32 words][64] (56 KB).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,29 +30,34 @@ constexpr int HAM_STAGE = HAM_QCH + HAM_RCH;
 __global__ void __launch_bounds__(256)
 hamming_pack_kernel(const uint16_t *__restrict__ codes, long long n, long long ldc, int n_trees,
                     int n_chunks, int tile, uint16_t pad_code, uint32_t *__restrict__ img) {
-    __shared__ uint32_t buf[HAM_WC][QTILE + 1];
+    constexpr int SUB = 128;  // rows transposed per pass through shared memory
+    __shared__ uint32_t buf[HAM_WC][SUB + 1];
     const long long tileno = blockIdx.x;
     const int chunk = blockIdx.y;
-    const long long row0 = tileno * tile;
-    for (int e = threadIdx.x; e < tile * HAM_WC; e += 256) {
-        const int r = e / HAM_WC, w = e - r * HAM_WC;
-        const long long row = row0 + r;
-        const int t0 = 2 * (chunk * HAM_WC + w);
-        uint32_t lo = 0, hi = 0;
-        if (row < n) {
-            if (t0 < n_trees) lo = codes[row * ldc + t0];
-            if (t0 + 1 < n_trees) hi = codes[row * ldc + t0 + 1];
-        } else {
-            if (t0 < n_trees) lo = pad_code;
-            if (t0 + 1 < n_trees) hi = pad_code;
-        }
-        buf[w][r] = lo | (hi << 16);
-    }
-    __syncthreads();
     uint32_t *out = img + ((size_t)tileno * n_chunks + chunk) * HAM_WC * tile;
-    for (int e = threadIdx.x; e < tile * HAM_WC; e += 256) {
-        const int w = e / tile, r = e - w * tile;
-        out[e] = buf[w][r];
+    for (int sub = 0; sub < tile; sub += SUB) {
+        const int nsub = min(SUB, tile - sub);
+        const long long row0 = tileno * tile + sub;
+        for (int e = threadIdx.x; e < nsub * HAM_WC; e += 256) {
+            const int r = e / HAM_WC, w = e - r * HAM_WC;
+            const long long row = row0 + r;
+            const int t0 = 2 * (chunk * HAM_WC + w);
+            uint32_t lo = 0, hi = 0;
+            if (row < n) {
+                if (t0 < n_trees) lo = codes[row * ldc + t0];
+                if (t0 + 1 < n_trees) hi = codes[row * ldc + t0 + 1];
+            } else {
+                if (t0 < n_trees) lo = pad_code;
+                if (t0 + 1 < n_trees) hi = pad_code;
+            }
+            buf[w][r] = lo | (hi << 16);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nsub * HAM_WC; e += 256) {
+            const int w = e / nsub, r = e - w * nsub;
+            out[(size_t)w * tile + sub + r] = buf[w][r];
+        }
+        __syncthreads();
     }
 }
 
@@ -74,9 +79,12 @@ hamming_search_kernel(const uint32_t *__restrict__ qimg, const uint32_t *__restr
                       int *__restrict__ cand_idx, int *__restrict__ cand_cnt) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *stage0 = reinterpret_cast<uint32_t *>(smem_raw);
+    constexpr bool kRegLists = KC <= 16;          // lists live in registers (8-lane groups)
+    constexpr int EPL = kRegLists ? KC / 8 : 1;
+    constexpr int kListSlots = kRegLists ? 0 : QTILE * KC;
     int *list_c = reinterpret_cast<int *>(stage0 + (size_t)nstage * HAM_STAGE);
-    int *list_i = list_c + QTILE * KC;
-    uint64_t *full = reinterpret_cast<uint64_t *>(list_i + QTILE * KC);
+    int *list_i = list_c + kListSlots;
+    uint64_t *full = reinterpret_cast<uint64_t *>(list_i + kListSlots);
     uint64_t *empty = full + nstage;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,7 +95,7 @@ hamming_search_kernel(const uint32_t *__restrict__ qimg, const uint32_t *__restr
         }
         fence_mbar_init();
     }
-    for (int e = threadIdx.x; e < QTILE * KC; e += SEARCH_THREADS) {
+    for (int e = threadIdx.x; e < kListSlots; e += SEARCH_THREADS) {
         list_c[e] = 0x7fffffff;
         list_i[e] = 0x7fffffff;
     }
@@ -96,30 +104,31 @@ hamming_search_kernel(const uint32_t *__restrict__ qimg, const uint32_t *__restr
     const long long qtile = blockIdx.x;
     const int n_steps = n_rtiles * n_chunks;
 
-    if (warp == NCOMPUTE_WARPS) {
-        if (lane == 0) {
-            int c = 0, t = 0;
-            for (int step = 0; step < n_steps; ++step) {
-                const int s = step % nstage;
-                if (step >= nstage) mbar_wait(&empty[s], ((step / nstage) - 1) & 1);
-                uint32_t *dst = stage0 + (size_t)s * HAM_STAGE;
-                mbar_expect_tx(&full[s], HAM_STAGE * 4u);
-                bulk_g2s(dst, qimg + ((size_t)qtile * n_chunks + c) * HAM_QCH, HAM_QCH * 4u, &full[s]);
-                bulk_g2s(dst + HAM_QCH, rimg + ((size_t)t * n_chunks + c) * HAM_RCH, HAM_RCH * 4u,
-                         &full[s]);
-                if (++c == n_chunks) {
-                    c = 0;
-                    ++t;
-                }
-            }
-        }
-        return;
-    }
+    // TMA producer: lane 0 of warp 0, inline (step+nstage-2 is requested at the top of `step`)
+    auto issue_step = [&](int sn_step) {
+        const int sn = sn_step % nstage;
+        const int tt = sn_step / n_chunks, cc = sn_step - tt * n_chunks;
+        if (sn_step >= nstage) mbar_wait(&empty[sn], ((sn_step / nstage) - 1) & 1);
+        uint32_t *dst = stage0 + (size_t)sn * HAM_STAGE;
+        mbar_expect_tx(&full[sn], HAM_STAGE * 4u);
+        bulk_g2s(dst, qimg + ((size_t)qtile * n_chunks + cc) * HAM_QCH, HAM_QCH * 4u, &full[sn]);
+        bulk_g2s(dst + HAM_QCH, rimg + ((size_t)tt * n_chunks + cc) * HAM_RCH, HAM_RCH * 4u, &full[sn]);
+    };
+    if (threadIdx.x == 0)
+        for (int sn_step = 0; sn_step < nstage - 1 && sn_step < n_steps; ++sn_step) issue_step(sn_step);
 
     const int ty = lane >> 3, tx = lane & 7;
     int thr[8];
+    int lk[8][EPL], li[8][EPL];  // register lists (counts, ids)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) thr[i] = 0x7fffffff;
+    for (int i = 0; i < 8; ++i) {
+        thr[i] = 0x7fffffff;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            lk[i][e] = 0x7fffffff;
+            li[i][e] = 0x7fffffff;
+        }
+    }
 
     __half2 acc[8][8];
     int step = 0;
@@ -130,6 +139,8 @@ hamming_search_kernel(const uint32_t *__restrict__ qimg, const uint32_t *__restr
             for (int j = 0; j < 8; ++j) acc[i][j] = __floats2half2_rn(0.f, 0.f);
 
         for (int c = 0; c < n_chunks; ++c, ++step) {
+            if (threadIdx.x == 0 && step >= 1 && step + nstage - 2 < n_steps) issue_step(step + nstage - 2);
+            __syncwarp();
             const int s = step % nstage;
             mbar_wait(&full[s], (step / nstage) & 1);
             const uint32_t *qp = stage0 + (size_t)s * HAM_STAGE + warp * 32 + ty * 4;
@@ -177,26 +188,47 @@ hamming_search_kernel(const uint32_t *__restrict__ qimg, const uint32_t *__restr
             for (int i = 0; i < 8; ++i) {
                 const unsigned mrow = __ballot_sync(SK_FULL, rowhit[i]);
                 if (mrow == 0) continue;
+                if constexpr (kRegLists) {
+                    unsigned hm = 0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int myid = idbase + tile_ref_slot(tx, c);
-                    unsigned m = __ballot_sync(SK_FULL, cnt[i][c] <= thr[i] && myid < n_ref);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int c_l = __shfl_sync(SK_FULL, cnt[i][c], src);
-                        const int ty_l = src >> 3, tx_l = src & 7;
-                        const int qs = tile_query_slot(warp, ty_l, i);
-                        const int id_l = idbase + tile_ref_slot(tx_l, c);
-                        int nthr, nid;
-                        list_insert<KC, int, true>(list_c, list_i, qs, c_l, id_l, lane, nthr, nid);
-                        if (ty == ty_l) thr[i] = nthr;
+                    for (int c = 0; c < 8; ++c) hm |= (cnt[i][c] <= thr[i]) ? (1u << c) : 0u;
+                    drain_row<EPL, int, true>(cnt[i], hm, lk[i], li[i], thr[i], idbase, n_ref, tx, ty);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int myid = idbase + tile_ref_slot(tx, c);
+                        unsigned m = __ballot_sync(SK_FULL, cnt[i][c] <= thr[i] && myid < n_ref);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int c_l = __shfl_sync(SK_FULL, cnt[i][c], src);
+                            const int ty_l = src >> 3, tx_l = src & 7;
+                            const int qs = tile_query_slot(warp, ty_l, i);
+                            const int id_l = idbase + tile_ref_slot(tx_l, c);
+                            int nthr, nid;
+                            list_insert<KC, int, true>(list_c, list_i, qs, c_l, id_l, lane, nthr, nid);
+                            if (ty == ty_l) thr[i] = nthr;
+                        }
                     }
                 }
             }
         }
     }
 
+    if constexpr (kRegLists) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long q = qtile * QTILE + tile_query_slot(warp, ty, i);
+            if (q < n_q) {
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    cand_idx[q * KC + tx * EPL + e] = li[i][e];
+                    cand_cnt[q * KC + tx * EPL + e] = lk[i][e];
+                }
+            }
+        }
+        return;
+    }
     for (int ql = 0; ql < 32; ++ql) {
         const int qs = warp * 32 + ql;
         const long long q = qtile * QTILE + qs;
@@ -209,7 +241,8 @@ hamming_search_kernel(const uint32_t *__restrict__ qimg, const uint32_t *__restr
 }
 
 static size_t hamming_smem_bytes(int kc, int nstage) {
-    return (size_t)nstage * HAM_STAGE * 4 + (size_t)QTILE * kc * 8 + (size_t)2 * nstage * 8;
+    const size_t lists = kc <= 16 ? 0 : (size_t)QTILE * kc * 8;  // <= 16: register lists
+    return (size_t)nstage * HAM_STAGE * 4 + lists + (size_t)2 * nstage * 8;
 }
 
 template <int KC>

@@ -14,7 +14,7 @@
 
 namespace sk {
 
-constexpr int PROJ_THREADS = QTILE;  // one thread per query row of the tile
+constexpr int PROJ_THREADS = 128;  // one thread per query row; 128 rows per CTA
 constexpr int PROJ_KCHUNK = 8;
 
 template <typename TX>
@@ -25,13 +25,13 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
                double *__restrict__ z64, float *__restrict__ qimg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int xs_ld = d_in | 1;  // odd row stride (in doubles): conflict-free row reads
-    double *xs = reinterpret_cast<double *>(smem_raw);           // [256][xs_ld]
+    double *xs = reinterpret_cast<double *>(smem_raw);           // [128][xs_ld]
     double *ps = xs + (size_t)PROJ_THREADS * xs_ld;              // [d_in][d_out] (if proj)
-    const long long q0 = (long long)blockIdx.x * QTILE;
-    const int rows = (int)min((long long)QTILE, n_q - q0);
+    const long long q0 = (long long)blockIdx.x * PROJ_THREADS;
+    const int rows = (int)min((long long)PROJ_THREADS, n_q - q0);
 
     // coalesced load of the tile's rows, centring and scaling on the way in
-    for (int e = threadIdx.x; e < QTILE * d_in; e += PROJ_THREADS) {
+    for (int e = threadIdx.x; e < PROJ_THREADS * d_in; e += PROJ_THREADS) {
         const int r = e / d_in, c = e - r * d_in;
         double v = 0.0;
         if (r < rows) {
@@ -47,7 +47,9 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
 
     const int r = threadIdx.x;
     const double *xr = xs + r * xs_ld;
-    float *qt = qimg ? qimg + (size_t)blockIdx.x * dpad * QTILE + r : nullptr;
+    // row (q0 + r) lives in query tile (q0 + r) / QTILE at column (q0 + r) % QTILE
+    const long long qrow = q0 + r;
+    float *qt = qimg ? qimg + (size_t)(qrow / QTILE) * dpad * QTILE + (qrow % QTILE) : nullptr;
     for (int k0 = 0; k0 < dpad; k0 += PROJ_KCHUNK) {
         double z[PROJ_KCHUNK];
 #pragma unroll
@@ -86,7 +88,9 @@ cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long
     const int xs_ld = d_in | 1;
     const size_t smem = ((size_t)PROJ_THREADS * xs_ld + (proj ? (size_t)d_in * d_out : 0)) * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    const long long grid = (n_q + QTILE - 1) / QTILE;
+    // cover whole query tiles so that padding columns of the last tile are zero-filled
+    const long long padded = (n_q + QTILE - 1) / QTILE * QTILE;
+    const long long grid = (padded + PROJ_THREADS - 1) / PROJ_THREADS;
     cudaError_t e;
     if (x_is_f32) {
         e = cudaFuncSetAttribute(project_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -5,19 +5,21 @@
 // d2 = |x|^2 - 2x.y + |y|^2, one heap test per pair), reached from
 // ref:src/sknnr/_base.py:162-164.  The n_q x n_ref distance matrix never reaches HBM.
 //
-// Work decomposition (one CTA = 256 queries, 8 compute warps + 1 TMA producer warp):
-//   * the CTA's query tile image [dpad][256] f32 (pre-scaled by -2, centroid-shifted) is
+// Work decomposition (one CTA = 384 queries, 12 warps; lane 0 of warp 0 doubles as the TMA
+// producer, so the warp count stays a multiple of 4 and the register budget is 168/thread):
+//   * the CTA's query tile image [dpad][384] f32 (pre-scaled by -2, centroid-shifted) is
 //     staged once with one 1-D TMA bulk copy;
 //   * reference tiles of 64 plots, image [(dpad+1)][64] f32 whose last row holds |r|^2, stream
-//     through an NSTAGE-deep ring filled by the producer warp (cp.async.bulk + mbarrier
-//     complete_tx) and released by the compute warps through "empty" mbarriers;
+//     through an NSTAGE-deep ring filled with cp.async.bulk + mbarrier complete_tx and
+//     released by the compute warps through "empty" mbarriers;
 //   * each compute warp owns 32 queries; lanes form a 4 (query groups) x 8 (reference groups)
 //     grid and every thread keeps an 8 query x 8 reference register tile of FP32 scores
 //     s = |r|^2 - 2 q.r accumulated with packed FFMA2 (two references per instruction);
 //   * selection: one compare per pair against the query's current KC-th best score; hits
-//     (k*ln(n_ref/k) per query) are inserted into the query's sorted list in shared memory
-//     with a warp-wide ballot/shift.  Only the owning warp touches a query's list and lane L
-//     only touches slot L, so the hit path needs no atomics and no barrier.
+//     (k*ln(n_ref/k) per query) are inserted into the query's sorted list, which the 8 lanes
+//     sharing the query keep in registers (width-8 shuffles; the four lane groups of a warp
+//     insert into four queries at once).  No atomics, no barrier, no shared memory (lists of
+//     more than 16 entries fall back to a shared-memory list owned by the warp).
 //
 // Output: for every query the KC best references by approximate score (ascending) and the
 // KC-th score.  Exact float64 distances, ordering and the certificate that no better
@@ -36,9 +38,12 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
     const int rtile_floats = (dpad + 1) * RTILE;
     float *Qs = reinterpret_cast<float *>(smem_raw);
     float *Rs = Qs + (size_t)dpad * QTILE;
+    constexpr bool kRegLists = KC <= 16;          // lists live in registers (8-lane groups)
+    constexpr int EPL = kRegLists ? KC / 8 : 1;   // list entries per lane
+    constexpr int kListSlots = kRegLists ? 0 : QTILE * KC;
     float *list_s = Rs + (size_t)nstage * rtile_floats;
-    int *list_i = reinterpret_cast<int *>(list_s + QTILE * KC);
-    uint64_t *full = reinterpret_cast<uint64_t *>(list_i + QTILE * KC);
+    int *list_i = reinterpret_cast<int *>(list_s + kListSlots);
+    uint64_t *full = reinterpret_cast<uint64_t *>(list_i + kListSlots);
     uint64_t *empty = full + nstage;
     uint64_t *qbar = empty + nstage;
 
@@ -53,7 +58,7 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
         mbar_init(qbar, 1);
         fence_mbar_init();
     }
-    for (int e = threadIdx.x; e < QTILE * KC; e += SEARCH_THREADS) {
+    for (int e = threadIdx.x; e < kListSlots; e += SEARCH_THREADS) {
         list_s[e] = SK_INF_F;
         list_i[e] = -1;
     }
@@ -61,22 +66,21 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
 
     const long long qtile = blockIdx.x;
 
-    if (warp == NCOMPUTE_WARPS) {
-        // ---------------- TMA producer ----------------
-        if (lane == 0) {
-            const uint32_t qbytes = (uint32_t)dpad * QTILE * 4u;
-            const uint32_t rbytes = (uint32_t)rtile_floats * 4u;
-            mbar_expect_tx(qbar, qbytes);
-            bulk_g2s(Qs, qimg + (size_t)qtile * dpad * QTILE, qbytes, qbar);
-            for (int t = 0; t < n_rtiles; ++t) {
-                const int s = t % nstage;
-                if (t >= nstage) mbar_wait(&empty[s], ((t / nstage) - 1) & 1);
-                mbar_expect_tx(&full[s], rbytes);
-                bulk_g2s(Rs + (size_t)s * rtile_floats, rimg + (size_t)t * rtile_floats, rbytes,
-                         &full[s]);
-            }
-        }
-        return;
+    // ---------------- TMA producer: lane 0 of warp 0, inline ----------------
+    // Tile t+nstage-2 is requested at the top of iteration t, so the slot it overwrites was
+    // released two iterations ago and the wait below is normally already satisfied.
+    const uint32_t rbytes = (uint32_t)rtile_floats * 4u;
+    auto issue_tile = [&](int tn) {
+        const int sn = tn % nstage;
+        if (tn >= nstage) mbar_wait(&empty[sn], ((tn / nstage) - 1) & 1);
+        mbar_expect_tx(&full[sn], rbytes);
+        bulk_g2s(Rs + (size_t)sn * rtile_floats, rimg + (size_t)tn * rtile_floats, rbytes, &full[sn]);
+    };
+    if (threadIdx.x == 0) {
+        const uint32_t qbytes = (uint32_t)dpad * QTILE * 4u;
+        mbar_expect_tx(qbar, qbytes);
+        bulk_g2s(Qs, qimg + (size_t)qtile * dpad * QTILE, qbytes, qbar);
+        for (int tn = 0; tn < nstage - 1 && tn < n_rtiles; ++tn) issue_tile(tn);
     }
 
     // ---------------- compute warps ----------------
@@ -84,12 +88,23 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
     const int tx = lane & 7;   // reference group 0..7
     const float *qp = Qs + warp * 32 + ty * 4;
     float thr[8];
+    float lk[8][EPL];  // register lists: lane tx holds positions tx*EPL.. of its 8 queries
+    int li[8][EPL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) thr[i] = SK_INF_F;
+    for (int i = 0; i < 8; ++i) {
+        thr[i] = SK_INF_F;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            lk[i][e] = SK_INF_F;
+            li[i][e] = -1;
+        }
+    }
 
     mbar_wait(qbar, 0);
 
     for (int t = 0; t < n_rtiles; ++t) {
+        if (threadIdx.x == 0 && t >= 1 && t + nstage - 2 < n_rtiles) issue_tile(t + nstage - 2);
+        __syncwarp();
         const int s = t % nstage;
         mbar_wait(&full[s], (t / nstage) & 1);
         const float *rp = Rs + (size_t)s * rtile_floats + tx * 4;
@@ -147,21 +162,31 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
             for (int i = 0; i < 8; ++i) {
                 const unsigned mrow = __ballot_sync(SK_FULL, rowhit[i]);
                 if (mrow == 0) continue;
+                if constexpr (kRegLists) {
+                    const float sc[8] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y,
+                                         acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y};
+                    unsigned hm = 0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float sc = (c & 1) ? acc[i][c >> 1].y : acc[i][c >> 1].x;
-                    unsigned m = __ballot_sync(SK_FULL, sc < thr[i]);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const float s_l = __shfl_sync(SK_FULL, sc, src);
-                        const int ty_l = src >> 3, tx_l = src & 7;
-                        const int qs = tile_query_slot(warp, ty_l, i);
-                        const int id_l = idbase + tile_ref_slot(tx_l, c);
-                        float nthr;
-                        int nid;
-                        list_insert<KC, float, false>(list_s, list_i, qs, s_l, id_l, lane, nthr, nid);
-                        if (ty == ty_l) thr[i] = nthr;
+                    for (int c = 0; c < 8; ++c) hm |= (sc[c] < thr[i]) ? (1u << c) : 0u;
+                    drain_row<EPL, float, false>(sc, hm, lk[i], li[i], thr[i], idbase, 0x7fffffff,
+                                                 tx, ty);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float sc = (c & 1) ? acc[i][c >> 1].y : acc[i][c >> 1].x;
+                        unsigned m = __ballot_sync(SK_FULL, sc < thr[i]);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const float s_l = __shfl_sync(SK_FULL, sc, src);
+                            const int ty_l = src >> 3, tx_l = src & 7;
+                            const int qs = tile_query_slot(warp, ty_l, i);
+                            const int id_l = idbase + tile_ref_slot(tx_l, c);
+                            float nthr;
+                            int nid;
+                            list_insert<KC, float, false>(list_s, list_i, qs, s_l, id_l, lane, nthr, nid);
+                            if (ty == ty_l) thr[i] = nthr;
+                        }
                     }
                 }
             }
@@ -169,20 +194,33 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
     }
 
     // ---------------- write candidates ----------------
-    for (int ql = 0; ql < 32; ++ql) {
-        const int qs = warp * 32 + ql;
-        const long long q = qtile * QTILE + qs;
-        if (q >= n_q) break;
-        if (lane < KC) {
-            cand_idx[q * KC + lane] = list_i[qs * KC + lane];
-            if (lane == KC - 1) cand_thr[q] = list_s[qs * KC + lane];
+    if constexpr (kRegLists) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long q = qtile * QTILE + tile_query_slot(warp, ty, i);
+            if (q < n_q) {
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) cand_idx[q * KC + tx * EPL + e] = li[i][e];
+                if (tx == 7) cand_thr[q] = lk[i][EPL - 1];
+            }
+        }
+    } else {
+        for (int ql = 0; ql < 32; ++ql) {
+            const int qs = warp * 32 + ql;
+            const long long q = qtile * QTILE + qs;
+            if (q >= n_q) break;
+            if (lane < KC) {
+                cand_idx[q * KC + lane] = list_i[qs * KC + lane];
+                if (lane == KC - 1) cand_thr[q] = list_s[qs * KC + lane];
+            }
         }
     }
 }
 
 size_t search_simt_smem_bytes(int dpad, int kc, int nstage) {
-    return (size_t)dpad * QTILE * 4 + (size_t)nstage * (dpad + 1) * RTILE * 4 +
-           (size_t)QTILE * kc * 8 + (size_t)(2 * nstage + 1) * 8;
+    const size_t lists = kc <= 16 ? 0 : (size_t)QTILE * kc * 8;  // <= 16: register lists
+    return (size_t)dpad * QTILE * 4 + (size_t)nstage * (dpad + 1) * RTILE * 4 + lists +
+           (size_t)(2 * nstage + 1) * 8;
 }
 
 int search_simt_pick_stages(int dpad, int kc) {

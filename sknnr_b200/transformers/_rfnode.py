@@ -1,0 +1,172 @@
+"""Random-forest node transformer for RFNN: one forest per target, ``transform`` returns the
+terminal-node ID of every tree (mirrors ref:src/sknnr/transformers/_tree_node_transformer.py
+and _rfnode_transformer.py).  Forest TRAINING is scikit-learn's (out of the hot-path scope);
+``transform`` still walks the trees with scikit-learn's ``apply`` on the host - the GPU forest
+walk is row f1 of the scope table (next) - and hands int64 node IDs to the Hamming kernels.
+"""
+
+from __future__ import annotations
+
+from collections import Counter
+
+import numpy as np
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.ensemble import RandomForestClassifier, RandomForestRegressor
+from sklearn.utils.validation import check_array, check_is_fitted, validate_data
+
+
+def _is_nan_like(v) -> bool:
+    return v is None or (isinstance(v, float) and np.isnan(v)) or type(v).__name__ == "NAType"
+
+
+def _target_names(y) -> list:
+    if hasattr(y, "columns") and hasattr(y, "dtypes"):
+        return list(y.columns)
+    if hasattr(y, "name") and hasattr(y, "dtype") and not isinstance(y, np.ndarray):
+        return ["0"] if y.name is None else [y.name]
+    arr = np.asarray(y, dtype=object)
+    return [str(i) for i in range(1 if arr.ndim == 1 else arr.shape[1])]
+
+
+def _target_dtypes(y) -> list:
+    """Smallest NumPy dtype holding each target column; pandas categoricals keep their tag."""
+    arr = np.asarray(y, dtype=object)
+    if arr.ndim == 1:
+        arr = arr.reshape(-1, 1)
+    promoted = [np.asarray(arr[:, i].tolist()).dtype for i in range(arr.shape[1])]
+    native = None
+    if hasattr(y, "columns") and hasattr(y, "dtypes"):
+        native = list(getattr(y.dtypes, "values", y.dtypes))
+    elif hasattr(y, "name") and hasattr(y, "dtype") and not isinstance(y, np.ndarray):
+        native = [y.dtype]
+    if native is None:
+        return promoted
+    return [n if str(n) == "category" else p for p, n in zip(promoted, native)]
+
+
+def _is_numeric(dt) -> bool:
+    try:
+        return bool(np.issubdtype(np.dtype(dt), np.number))
+    except TypeError:
+        kind = getattr(dt, "kind", None)
+        if kind:
+            return kind in "iuf"
+        raise TypeError(f"Unsupported type {dt}") from None
+
+
+class RFNodeTransformer(TransformerMixin, BaseEstimator):
+    def __init__(self, n_estimators=50, criterion_reg="squared_error", criterion_clf="gini",
+                 max_depth=None, min_samples_split=2, min_samples_leaf=5,
+                 min_weight_fraction_leaf=0.0, max_features_reg=1.0, max_features_clf="sqrt",
+                 max_leaf_nodes=None, min_impurity_decrease=0.0, bootstrap=True, oob_score=False,
+                 n_jobs=None, random_state=None, verbose=0, warm_start=False,
+                 class_weight_clf=None, ccp_alpha=0.0, max_samples=None, monotonic_cst=None):
+        self.n_estimators = n_estimators
+        self.criterion_reg = criterion_reg
+        self.criterion_clf = criterion_clf
+        self.max_depth = max_depth
+        self.min_samples_split = min_samples_split
+        self.min_samples_leaf = min_samples_leaf
+        self.min_weight_fraction_leaf = min_weight_fraction_leaf
+        self.max_features_reg = max_features_reg
+        self.max_features_clf = max_features_clf
+        self.max_leaf_nodes = max_leaf_nodes
+        self.min_impurity_decrease = min_impurity_decrease
+        self.bootstrap = bootstrap
+        self.oob_score = oob_score
+        self.n_jobs = n_jobs
+        self.random_state = random_state
+        self.verbose = verbose
+        self.warm_start = warm_start
+        self.class_weight_clf = class_weight_clf
+        self.ccp_alpha = ccp_alpha
+        self.max_samples = max_samples
+        self.monotonic_cst = monotonic_cst
+
+    # -- fit (cold path) ----------------------------------------------------------------
+    def _prepare_targets(self, y, info):
+        arr = np.asarray(y, dtype=object)
+        if arr.ndim == 1:
+            arr = arr.reshape(-1, 1)
+        out = []
+        for i, (name, dt) in enumerate(info.items()):
+            col = arr[:, i]
+            if any(_is_nan_like(v) for v in col):
+                raise ValueError(f"Target {name} has NaN-like elements.")
+            if str(dt) == "category":
+                col = np.asarray(col.tolist())
+            else:
+                try:
+                    npdt = np.dtype(dt)
+                except TypeError:
+                    npdt = None
+                if npdt is not None:
+                    if np.issubdtype(npdt, np.str_):
+                        odd = {type(v) for v in col if not np.issubdtype(type(v), np.str_)}
+                        if odd:
+                            raise ValueError(
+                                f"Target {name} has non-string types ({odd}) that cannot be "
+                                f"safely converted to a string dtype ({npdt}).")
+                    col = col.astype(npdt)
+            out.append(check_array(col, ensure_all_finite=True, dtype=None, ensure_2d=False, estimator=self))
+        return out
+
+    def fit(self, X, y):
+        X_arr = validate_data(self, X=X, reset=True)
+        if y is None:
+            raise ValueError(f"{type(self).__name__} requires y to be passed, but the target y is None.")
+        names = _target_names(y)
+        if len(set(names)) != len(names):
+            dup = [n for n, c in Counter(names).items() if c > 1]
+            raise ValueError(f"Duplicate feature names found: {dup}.")
+        info = dict(zip(names, _target_dtypes(y)))
+        targets = self._prepare_targets(y, info)
+        self.estimator_type_dict_ = {
+            n: ("regression" if _is_numeric(dt) else "classification") for n, dt in info.items()}
+        common = dict(
+            n_estimators=self.n_estimators, max_depth=self.max_depth,
+            min_samples_split=self.min_samples_split, min_samples_leaf=self.min_samples_leaf,
+            min_weight_fraction_leaf=self.min_weight_fraction_leaf,
+            max_leaf_nodes=self.max_leaf_nodes, min_impurity_decrease=self.min_impurity_decrease,
+            bootstrap=self.bootstrap, oob_score=self.oob_score, n_jobs=self.n_jobs,
+            random_state=self.random_state, verbose=self.verbose, warm_start=self.warm_start,
+            ccp_alpha=self.ccp_alpha, max_samples=self.max_samples, monotonic_cst=self.monotonic_cst)
+        kinds = list(self.estimator_type_dict_.values())
+        self.estimators_ = []
+        for kind, target in zip(kinds, targets):
+            if kind == "regression":
+                est = RandomForestRegressor(criterion=self.criterion_reg, max_features=self.max_features_reg, **common)
+            else:
+                est = RandomForestClassifier(criterion=self.criterion_clf, max_features=self.max_features_clf,
+                                             class_weight=self.class_weight_clf, **common)
+            self.estimators_.append(est.fit(X_arr, target))
+        self.n_forests_ = len(self.estimators_)
+        self.n_trees_per_iteration_ = [1] * self.n_forests_
+        self.tree_weights_ = [np.full(self.n_estimators, 1.0 / self.n_estimators) for _ in range(self.n_forests_)]
+        return self
+
+    def get_feature_names_out(self, input_features=None):
+        check_is_fitted(self, "estimators_")
+        return np.asarray([f"rf{i}_tree{j}" for i, e in enumerate(self.estimators_)
+                           for j in range(e.n_estimators)], dtype=object)
+
+    # -- transform ----------------------------------------------------------------------
+    def transform(self, X):
+        check_is_fitted(self)
+        X_arr = validate_data(self, X=X, reset=False, ensure_min_features=1, ensure_min_samples=1)
+        ids = []
+        for est in self.estimators_:
+            a = est.apply(X_arr)
+            if a.ndim == 3:
+                a = np.swapaxes(a, 1, 2).reshape(a.shape[0], -1)
+            ids.append(a)
+        return np.hstack(ids).astype("int64")
+
+    def fit_transform(self, X, y):
+        return self.fit(X, y).transform(X)
+
+    def __sklearn_tags__(self):
+        tags = super().__sklearn_tags__()
+        tags.target_tags.required = True
+        tags.transformer_tags.preserves_dtype = ["int64"]
+        return tags
