@@ -352,19 +352,35 @@ def run_ours(a, rank, world, local_rank):
             peaks = json.load(f)
     except OSError:
         pass
-    roofline = {
-        "kernel": "search_simt_kernel" if engine == L.ENGINE_SIMT else f"engine{engine}",
-        "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": (achieved / fp32_peak) if achieved else None,
-        "peak_source": "measured in this run: register-resident FFMA2 probe on all SMs "
-                       "(sknnr_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-        "traffic": None,
-        "algorithmic_flops_per_launch": flops / n_chunks,
-        "launches_per_step": n_chunks, "kernel_ms_per_step": search_ms,
-        "hbm": {"algorithmic_bytes_per_step": n_q * (8 * d + k * 16 + 8 * n_out) + 4 * a.n_ref * dpad,
-                "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json"
-                if peaks else "absent"},
-    }
+    hbm = {"algorithmic_bytes_per_step": n_q * (8 * d + k * 16 + 8 * n_out) + 4 * a.n_ref * dpad,
+           "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"}
+    if engine == L.ENGINE_TENSOR:
+        # tcgen05 kind::tf32 runs at half the bf16 rate: peak = measured cuBLAS bf16 burst / 2
+        bf16 = peaks.get("bf16_tflops", 1590.0)
+        tf32_peak = bf16 / 2.0
+        roofline = {
+            "kernel": "search_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": tf32_peak,
+            "unit": "TFLOP/s", "frac": (achieved / tf32_peak) if achieved else None,
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst) / 2 = dense TF32" if peaks
+                            else "fallback 1590 bf16 / 2 (B200_PROFILING.md)"),
+            "traffic": None, "algorithmic_flops_per_launch": flops / n_chunks,
+            "launches_per_step": n_chunks, "kernel_ms_per_step": search_ms,
+            "fp32_simt_peak_measured": fp32_peak,
+            "note": "algorithmic FLOPs 2*d'*n_q*n_ref; the kernel also spends 8 extra K per pair "
+                    "folding |r|^2 into the MMA and is paced by its TMEM epilogue (one compare "
+                    "per pair), not by the tensor pipe", "hbm": hbm,
+        }
+    else:
+        roofline = {
+            "kernel": "search_simt_kernel" if engine == L.ENGINE_SIMT else f"engine{engine}",
+            "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": (achieved / fp32_peak) if achieved else None,
+            "peak_source": "measured in this run: register-resident FFMA2 probe on all SMs "
+                           "(sknnr_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+            "traffic": None,
+            "algorithmic_flops_per_launch": flops / n_chunks,
+            "launches_per_step": n_chunks, "kernel_ms_per_step": search_ms, "hbm": hbm,
+        }
     if roofline["hbm"]["peak_gbs"] and search_ms > 0:
         roofline["hbm"]["achieved_gbs_whole_step"] = (
             roofline["hbm"]["algorithmic_bytes_per_step"] / (ms_total / a.steps * 1e-3) / 1e9)
@@ -384,7 +400,7 @@ def run_ours(a, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 search + f64 refine",
+        "scaling": "weak", "vs_baseline": None, "dtype": ("tf32 filter + f64 refine" if engine == L.ENGINE_TENSOR else "f32 filter + f64 refine"),
         "data": "synthetic",
         "config": {"workload": workload_name(a), "n_ref": a.n_ref, "dim": a.dim, "k": k,
                    "queries_per_gpu": n_q, "l2": f"inputs {n_q * d * 8 / 1e9:.2f} GB per step exceed the 126 MB L2 (no flush needed)",

@@ -1,5 +1,5 @@
 set -x
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$?; tail -15 gpurun_out/pytest_gpu.log
-for kc in 8 16; do
-timeout 600 python bench.py --steps 2 --warmup 1 --n-queries 2097152 --no-cpu-baseline --kc $kc > gpurun_out/bench_kc$kc.log 2>&1; echo kc${kc}_exit=$?; tail -c 1800 gpurun_out/bench_kc$kc.log
-done
+timeout 180 python scripts/tc_smoke.py > gpurun_out/tc_smoke.log 2>&1; echo tc_smoke_exit=$?; tail -14 gpurun_out/tc_smoke.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$?; tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 2 --warmup 1 --n-queries 4194304 --no-cpu-baseline > gpurun_out/bench_tc.log 2>&1; echo bench_exit=$?; tail -c 2400 gpurun_out/bench_tc.log
+timeout 600 python bench.py --steps 2 --warmup 1 --n-queries 4194304 --no-cpu-baseline --dim 64 > gpurun_out/bench_tc64.log 2>&1; echo bench64_exit=$?; tail -c 2400 gpurun_out/bench_tc64.log

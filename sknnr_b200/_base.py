@@ -19,6 +19,7 @@ import numpy as np
 from sklearn.base import BaseEstimator
 from sklearn.metrics import r2_score
 from sklearn.neighbors import KNeighborsRegressor
+from sklearn.utils import assert_all_finite
 from sklearn.utils.validation import _is_arraylike, check_is_fitted, validate_data
 
 from . import _lib as L
@@ -163,6 +164,11 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
             return ix.query(None, k, exclude_self=True, **kw)
         if not raw:
             X = validate_data(self, X, ensure_all_finite=True, accept_sparse=False, reset=False, order="C")
+        else:
+            # the reference rejects non-finite values when the regressor validates the
+            # transformed array ($SP/sklearn/neighbors/_base.py:831-838); an affine map keeps
+            # NaN/inf, so checking the raw array raises the same ValueError
+            assert_all_finite(X)
         k = self._check_k(n_neighbors, False, X.shape[0])
         if isinstance(ix, HammingIndex):
             return ix.query(_encode_nodes(np.asarray(X).astype(np.int64), self._node_tables), k, **kw)

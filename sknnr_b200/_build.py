@@ -16,11 +16,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libsknnr_b200.so"
-SOURCES = ["api.cu", "search_simt.cu", "refine.cu", "project.cu", "hamming.cu", "misc.cu"]
+SOURCES = ["api.cu", "search_simt.cu", "search_tc.cu", "refine.cu", "project.cu", "hamming.cu", "misc.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "sknnr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas=-v",
+    "-Xcompiler", "-fPIC", "-Xptxas=-v",
 ]
 
 
@@ -61,7 +61,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         return o
 
-    with ThreadPoolExecutor(max_workers=6) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     out = lib_path()
     if force or _stale(out, objs):

@@ -80,6 +80,9 @@ struct Slot {
     DevBuf<unsigned char> x;       // staged query rows (host callers)
     DevBuf<double> z64;
     DevBuf<float> qimg;
+    DevBuf<float> qimg_tc;         // tensor-core engine query image
+    DevBuf<double> z64c;           // compacted rows of the cascade's second stage
+    DevBuf<int> fb2;               // second-stage failures: [0] = count, [1..] = list
     DevBuf<uint32_t> qimg_h;       // Hamming query image
     DevBuf<int> cand_idx;
     DevBuf<float> cand_thr;
@@ -91,10 +94,12 @@ struct Slot {
     DevBuf<double> scratch;        // exact kernel distance scratch [grid, n_ref]
     std::vector<cudaEvent_t> evs;  // pooled (start, stop) pairs around the search kernels
     size_t ev_used = 0;            // events handed out since the last harvest
-    int *h_fb = nullptr;           // pinned: fallback count of the chunk in flight
+    int *h_fb = nullptr;           // pinned: [0] first-stage, [1] second-stage failures in flight
     bool fb_pending = false;
+    long long rows_in_flight = 0;
     void release() {
-        x.release(); z64.release(); qimg.release(); qimg_h.release(); cand_idx.release();
+        x.release(); z64.release(); qimg.release(); qimg_tc.release(); z64c.release(); fb2.release();
+        qimg_h.release(); cand_idx.release();
         cand_thr.release(); cand_cnt.release(); fb.release(); o_dist.release();
         o_idx.release(); o_pred.release(); scratch.release();
         for (auto e : evs) cudaEventDestroy(e);
@@ -126,6 +131,9 @@ struct IndexBase {
     int exact_grid = 0;
     sknnr_stats stats{};
     int n_sm = 148;
+    long long n_exact_rows = 0;     // rows that reached the exhaustive kernel (last call)
+    long long chunk_rows_seen = 0;  // adaptive engine choice: rows / first-stage failures seen
+    long long chunk_fb_seen = 0;
 
     int init_common(int dev, const double *y, int64_t nref, int nout) {
         int count = 0;
@@ -148,8 +156,8 @@ struct IndexBase {
         for (auto &s : slots) {
             CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             s.own_stream = true;
-            CK(cudaHostAlloc((void **)&s.h_fb, sizeof(int), cudaHostAllocDefault));
-            *s.h_fb = 0;
+            CK(cudaHostAlloc((void **)&s.h_fb, 2 * sizeof(int), cudaHostAllocDefault));
+            s.h_fb[0] = s.h_fb[1] = 0;
         }
         return SKNNR_OK;
     }
@@ -169,7 +177,10 @@ struct IndexBase {
         }
         s.ev_used = 0;
         if (s.fb_pending) {
-            stats.n_fallback += *s.h_fb;
+            stats.n_fallback += s.h_fb[0];
+            n_exact_rows += s.h_fb[1];
+            chunk_rows_seen += s.rows_in_flight;
+            chunk_fb_seen += s.h_fb[0];
             s.fb_pending = false;
         }
     }
@@ -205,6 +216,10 @@ struct sknnr_index : IndexBase {
     float *d_rimg = nullptr;
     int n_rtiles = 0;
     double r2max = 0.0;
+    float *d_rimg_tc = nullptr;    // tensor-core engine reference image
+    int n_rtiles_tc = 0, kc_tot = 0, tc_mt = 0, tc_nstage = 0;
+    bool tensor_ok = false;        // shape fits the tensor engine
+    bool tensor_demoted = false;   // too many uncertified rows: fall back to the SIMT engine
 };
 
 struct sknnr_hamming_index : IndexBase {
@@ -326,6 +341,52 @@ int sknnr_index_create(const double *fit_z, int64_t n_ref, int32_t d_out, const 
     if (e == cudaSuccess) e = cudaMalloc(&ix->d_rimg, rimg.size() * sizeof(float));
     if (e == cudaSuccess)
         e = cudaMemcpy(ix->d_rimg, rimg.data(), rimg.size() * sizeof(float), cudaMemcpyHostToDevice);
+
+    // tensor-core engine image: tiles of 64 plots, [chunk][row][4] TF32 (round to nearest),
+    // K padded to dpad plus one extra block whose first chunk holds a 3-way TF32 split of |r|^2
+    // (+inf for padding plots) and whose second chunk is zero
+    ix->kc_tot = ix->dpad / 4 + 2;
+    ix->n_rtiles_tc = (int)((n_ref + TC_N - 1) / TC_N);
+    search_tc_pick_shape(ix->kc_tot, &ix->tc_mt, &ix->tc_nstage);
+    ix->tensor_ok = ix->tc_mt != 0;
+    if (e == cudaSuccess && ix->tensor_ok) {
+        auto tf32 = [](float x) -> float {
+            uint32_t b;
+            memcpy(&b, &x, 4);
+            if ((b & 0x7f800000u) != 0x7f800000u) b = (b + 0x1000u) & 0xffffe000u;
+            float r;
+            memcpy(&r, &b, 4);
+            return r;
+        };
+        const size_t op_floats = (size_t)ix->kc_tot * TC_N * 4;
+        std::vector<float> timg((size_t)ix->n_rtiles_tc * op_floats, 0.0f);
+        for (int t = 0; t < ix->n_rtiles_tc; ++t) {
+            float *img = timg.data() + (size_t)t * op_floats;
+            for (int jj = 0; jj < TC_N; ++jj) {
+                const int64_t j = (int64_t)t * TC_N + jj;
+                float *nrm = img + ((size_t)(ix->dpad / 4) * TC_N + jj) * 4;
+                if (j >= n_ref) {
+                    nrm[0] = INFINITY;
+                    continue;
+                }
+                double n32 = 0.0;
+                for (int k = 0; k < d_out; ++k) {
+                    const float f = tf32((float)(fit_z[j * d_out + k] - mu[k]));
+                    img[((size_t)(k / 4) * TC_N + jj) * 4 + (k % 4)] = f;
+                    n32 += (double)f * (double)f;
+                }
+                const float hi = tf32((float)n32);
+                const float mid = tf32((float)(n32 - (double)hi));
+                const float lo = tf32((float)(n32 - (double)hi - (double)mid));
+                nrm[0] = hi;
+                nrm[1] = mid;
+                nrm[2] = lo;
+            }
+        }
+        e = cudaMalloc(&ix->d_rimg_tc, timg.size() * sizeof(float));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(ix->d_rimg_tc, timg.data(), timg.size() * sizeof(float), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         sknnr_index_destroy(ix);
         CK(e);
@@ -338,7 +399,7 @@ int sknnr_index_destroy(sknnr_index *ix) {
     if (!ix) return SKNNR_OK;
     ix->release_common();
     cudaFree(ix->d_ref64); cudaFree(ix->d_center); cudaFree(ix->d_scale); cudaFree(ix->d_proj);
-    cudaFree(ix->d_mu); cudaFree(ix->d_rimg);
+    cudaFree(ix->d_mu); cudaFree(ix->d_rimg); cudaFree(ix->d_rimg_tc);
     delete ix;
     return SKNNR_OK;
 }
@@ -352,23 +413,33 @@ int sknnr_index_stats(sknnr_index *ix, sknnr_stats *out) {
     return SKNNR_OK;
 }
 
-// one chunk of a Euclidean-space query, everything enqueued on s.stream
+// one chunk of a Euclidean-space query, everything enqueued on s.stream.
+//
+// Engine cascade (every stage is a filter whose result the float64 refine kernel certifies):
+//   1. tensor (tcgen05, TF32 scores, eps 2^-10)        -> refine -> uncertified rows list L1
+//   2. SIMT   (FP32 FFMA2 scores, eps ~(2d+8) 2^-24) on the compacted rows of L1 -> refine -> L2
+//   3. exact  (float64, exhaustive) on L2
+// With engine = SIMT stage 1 is skipped (L1 = all rows); with engine = EXACT only stage 3 runs.
 static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_t ldx, bool transformed,
                      int64_t rows, int64_t row0, int k, uint32_t flags, int decimals, int weights,
                      double *o_dist, long long *o_idx, double *o_pred) {
     const bool excl = flags & SKNNR_EXCLUDE_SELF;
     const int kk = k + (excl ? 1 : 0);
     cudaStream_t st = s.stream;
-    const int64_t n_qtiles = (rows + QTILE - 1) / QTILE;
+    const int64_t prow = padded_rows(rows);
 
-    int engine = (int)g_opt.engine;
     int kc = pick_kc(kk, 1);
     if (g_opt.kc > kc) kc = (int)g_opt.kc;
-    if (engine == SKNNR_ENGINE_AUTO || engine == SKNNR_ENGINE_TENSOR) engine = SKNNR_ENGINE_SIMT;
-    if (kc == 0 || search_simt_pick_stages(ix->dpad, kc ? kc : 8) == 0) engine = SKNNR_ENGINE_EXACT;
+    const bool simt_ok = kc != 0 && search_simt_pick_stages(ix->dpad, kc) != 0;
+    const bool tensor_ok = ix->tensor_ok && !ix->tensor_demoted && kc != 0 && kc <= 16 && simt_ok;
+    int engine = (int)g_opt.engine;
+    if (engine == SKNNR_ENGINE_AUTO) engine = tensor_ok ? SKNNR_ENGINE_TENSOR : SKNNR_ENGINE_SIMT;
+    if (engine == SKNNR_ENGINE_TENSOR && !(ix->tensor_ok && kc != 0 && kc <= 16 && simt_ok))
+        engine = SKNNR_ENGINE_SIMT;
+    if (engine == SKNNR_ENGINE_SIMT && !simt_ok) engine = SKNNR_ENGINE_EXACT;
     ix->stats.engine = engine;
 
-    FinishParams fp;
+    FinishParams fp{};
     fp.k = k;
     fp.exclude_self = excl ? 1 : 0;
     fp.deterministic = (flags & SKNNR_DETERMINISTIC) ? 1 : 0;
@@ -378,15 +449,20 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     fp.out_idx = o_idx;
     fp.weights = weights;
     fp.y = ix->d_y;
+    fp.n_ref = (int)ix->n_ref;
+    fp.row_map = nullptr;
     fp.n_out = ix->n_out;
     fp.out_pred = o_pred;
 
+    const bool use_tc = engine == SKNNR_ENGINE_TENSOR;
+    const bool use_simt_first = engine == SKNNR_ENGINE_SIMT;
     CK(s.z64.reserve((size_t)rows * ix->d_out));
-    CK(s.qimg.reserve((size_t)n_qtiles * ix->dpad * QTILE));
+    if (engine != SKNNR_ENGINE_EXACT) CK(s.qimg.reserve((size_t)prow * ix->dpad));
+    if (use_tc) CK(s.qimg_tc.reserve((size_t)prow * ix->kc_tot * 4));
     CK(launch_project(dX, x_f32, ldx, rows, transformed ? ix->d_out : ix->d_in, ix->d_out, ix->dpad,
                       transformed ? nullptr : ix->d_center, transformed ? nullptr : ix->d_scale,
                       transformed ? nullptr : ix->d_proj, ix->d_mu, s.z64.p,
-                      engine == SKNNR_ENGINE_SIMT ? s.qimg.p : nullptr, st));
+                      use_simt_first ? s.qimg.p : nullptr, use_tc ? s.qimg_tc.p : nullptr, ix->tc_mt, nullptr, st));
     ix->stats.kernel_launches++;
 
     ExactArgs ea{};
@@ -413,38 +489,74 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     CK(s.cand_idx.reserve((size_t)rows * kc));
     CK(s.cand_thr.reserve((size_t)rows));
     CK(s.fb.reserve((size_t)rows + 1));
+    CK(s.fb2.reserve((size_t)rows + 1));
     CK(cudaMemsetAsync(s.fb.p, 0, sizeof(int), st));
-    if (g_opt.timing) CK(s.mark(st));
-    CK(launch_search_simt(s.qimg.p, ix->d_rimg, ix->dpad, ix->n_rtiles, rows, kc, s.cand_idx.p,
-                          s.cand_thr.p, st));
-    if (g_opt.timing) CK(s.mark(st));
-    ix->stats.kernel_launches++;
+    CK(cudaMemsetAsync(s.fb2.p, 0, sizeof(int), st));
 
     RefineArgs ra{};
-    ra.z64 = s.z64.p;
     ra.ref64 = ix->d_ref64;
     ra.mu = ix->d_mu;
     ra.cand_idx = s.cand_idx.p;
     ra.cand_thr = s.cand_thr.p;
     ra.kc = kc;
     ra.d = ix->d_out;
-    ra.n_q = rows;
     ra.n_ref = (int)ix->n_ref;
-    // |approx score - true score| <= eps_s * (|q|^2 + max|r|^2): FP32 rounding of both
-    // operands and of |r|^2, plus dpad sequential FP32 FMAs ("certificate")
-    ra.eps_s = (2.0 * ix->dpad + 8.0) * std::ldexp(1.0, -24) * 1.01;
     ra.r2max = ix->r2max;
-    ra.fb_count = s.fb.p;
-    ra.fb_list = s.fb.p + 1;
-    CK(launch_refine(ra, fp, st));
-    ix->stats.kernel_launches++;
+    // |approx score - true score| <= eps_s * (|q|^2 + max|r|^2)   ("certificate")
+    //   SIMT  : FP32 rounding of both operands and of |r|^2, plus dpad sequential FP32 FMAs
+    //   tensor: TF32 (round-to-nearest, 2^-11) operands, exact products, FP32 accumulation
+    const double eps_simt = (2.0 * ix->dpad + 8.0) * std::ldexp(1.0, -24) * 1.01;
+    const double eps_tc = std::ldexp(1.0, -10) * 1.02 + (4.0 * ix->kc_tot) * std::ldexp(1.0, -20);
 
-    ea.list = s.fb.p + 1;
-    ea.count = s.fb.p;
+    const int *stage2_count = nullptr;  // null: stage 2 covers every row of the chunk
+    if (use_tc) {
+        if (g_opt.timing) CK(s.mark(st));
+        CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, kc, ix->tc_mt,
+                            ix->tc_nstage, s.cand_idx.p, s.cand_thr.p, st));
+        if (g_opt.timing) CK(s.mark(st));
+        ra.z64 = s.z64.p;
+        ra.n_q = rows;
+        ra.eps_s = eps_tc;
+        ra.fb_count = s.fb.p;
+        ra.fb_list = s.fb.p + 1;
+        ra.n_rows_dev = nullptr;
+        ra.row_map = nullptr;
+        CK(launch_refine(ra, fp, st));
+        // stage 2 input: gather the uncertified rows and rebuild their FP32 query image
+        CK(s.z64c.reserve((size_t)rows * ix->d_out));
+        CK(launch_gather_rows(s.z64.p, ix->d_out, s.fb.p + 1, s.fb.p, rows, s.z64c.p, st));
+        CK(launch_project(s.z64c.p, 0, ix->d_out, rows, ix->d_out, ix->d_out, ix->dpad, nullptr, nullptr,
+                          nullptr, ix->d_mu, nullptr, s.qimg.p, nullptr, 0, s.fb.p, st));
+        ix->stats.kernel_launches += 4;
+        stage2_count = s.fb.p;
+    }
+
+    // stage 2 (or the only fast stage): FP32 SIMT engine
+    if (g_opt.timing && !use_tc) CK(s.mark(st));
+    CK(launch_search_simt(s.qimg.p, ix->d_rimg, ix->dpad, ix->n_rtiles, rows, kc, s.cand_idx.p,
+                          s.cand_thr.p, stage2_count, st));
+    if (g_opt.timing && !use_tc) CK(s.mark(st));
+    FinishParams fp2 = fp;
+    fp2.row_map = use_tc ? s.fb.p + 1 : nullptr;
+    ra.z64 = use_tc ? s.z64c.p : s.z64.p;
+    ra.n_q = rows;
+    ra.eps_s = eps_simt;
+    ra.fb_count = s.fb2.p;
+    ra.fb_list = s.fb2.p + 1;
+    ra.n_rows_dev = stage2_count;
+    ra.row_map = fp2.row_map;
+    CK(launch_refine(ra, fp2, st));
+    ix->stats.kernel_launches += 2;
+
+    // stage 3: exhaustive float64 search of whatever is still uncertified (exact ties etc.)
+    ea.list = s.fb2.p + 1;
+    ea.count = s.fb2.p;
     CK(launch_exact(ea, fp, st));
     ix->stats.kernel_launches++;
-    CK(cudaMemcpyAsync(s.h_fb, s.fb.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&s.h_fb[0], use_tc ? s.fb.p : s.fb2.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&s.h_fb[1], s.fb2.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     s.fb_pending = true;
+    s.rows_in_flight = use_tc ? rows : 0;
     return SKNNR_OK;
 }
 
@@ -493,6 +605,11 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
         } else {
             CK(cudaStreamSynchronize(s.stream));  // previous chunk on this slot is done
             ix->harvest(s);
+            // adaptive engine choice: if the TF32 filter cannot certify > 5 % of the rows
+            // (ill-conditioned features: huge norms relative to neighbour distances) the FP32
+            // engine is the better first stage for this index
+            if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen)
+                ix->tensor_demoted = true;
         }
         const void *dX;
         int64_t dld = ldx;
@@ -564,7 +681,8 @@ int sknnr_transform(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_q
                              (size_t)ldx * esz, (size_t)ix->d_in * esz, (size_t)rows,
                              cudaMemcpyHostToDevice, s.stream));
         CK(launch_project(s.x.p, x_dtype == SKNNR_F32, ix->d_in, rows, ix->d_in, ix->d_out, ix->dpad,
-                          ix->d_center, ix->d_scale, ix->d_proj, ix->d_mu, s.z64.p, nullptr, s.stream));
+                          ix->d_center, ix->d_scale, ix->d_proj, ix->d_mu, s.z64.p, nullptr, nullptr, 0, nullptr,
+                          s.stream));
         CK(cudaMemcpyAsync(out_z + r0 * ix->d_out, s.z64.p, (size_t)rows * ix->d_out * 8,
                            cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
@@ -672,7 +790,7 @@ static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *d
     const bool excl = flags & SKNNR_EXCLUDE_SELF;
     const int kk = k + (excl ? 1 : 0);
     cudaStream_t st = s.stream;
-    FinishParams fp;
+    FinishParams fp{};
     fp.k = k;
     fp.exclude_self = excl ? 1 : 0;
     fp.deterministic = (flags & SKNNR_DETERMINISTIC) ? 1 : 0;
@@ -682,6 +800,7 @@ static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *d
     fp.out_idx = o_idx;
     fp.weights = weights;
     fp.y = ix->d_y;
+    fp.n_ref = (int)ix->n_ref;
     fp.n_out = ix->n_out;
     fp.out_pred = o_pred;
 

@@ -17,6 +17,9 @@ constexpr int QTILE = 32 * NCOMPUTE_WARPS;  // queries per CTA tile (32 per comp
 constexpr int RTILE = 64;       // reference plots per staged tile
 constexpr int SEARCH_THREADS = NCOMPUTE_WARPS * 32;  // lane 0 of warp 0 also issues the TMA copies
 constexpr int MAXK = 32;        // entries handled by one warp-wide sort
+// tensor-core engine tile shape: M = 128 queries per MMA (2 or 3 M tiles per CTA), N = 64 plots
+constexpr int TC_M = 128;
+constexpr int TC_N = 64;
 
 // ---------------------------------------------------------------------------------------
 // mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP)
@@ -63,6 +66,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         ::"r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// round-to-nearest conversion to TF32 (10 explicit mantissa bits), result as FP32 bits
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -186,9 +196,15 @@ __device__ __forceinline__ int tile_ref_slot(int tx, int c) {
 template <int EPL, typename K, bool LEX>
 __device__ __forceinline__ void group_insert(K (&lk)[EPL], int (&li)[EPL], bool valid, K key,
                                              int id, int tx, int ty, K &thr_k) {
-    const K last_k = __shfl_sync(SK_FULL, lk[EPL - 1], 7, 8);
-    const int last_i = __shfl_sync(SK_FULL, li[EPL - 1], 7, 8);
-    const bool accept = valid && (LEX ? pair_less<K>(key, id, last_k, last_i) : (key < last_k));
+    // thr_k always mirrors the list's last key; only the tie-breaking (LEX) variant needs the
+    // last index as well
+    bool accept;
+    if constexpr (LEX) {
+        const int last_i = __shfl_sync(SK_FULL, li[EPL - 1], 7, 8);
+        accept = valid && pair_less<K>(key, id, thr_k, last_i);
+    } else {
+        accept = valid && (key < thr_k);
+    }
     int pos = 0;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
@@ -268,12 +284,15 @@ struct FinishParams {
     long long *out_idx; // [n_q, k] or null
     int weights;        // SKNNR_W_*
     const double *y;    // [n_ref, n_out]
+    int n_ref;          // guards the target gather against invalid ids (non-finite input)
+    const int *row_map; // compacted launches: row_map[q] is the row of the original chunk
     int n_out;
     double *out_pred;   // [n_q, n_out]
 };
 
 __device__ __forceinline__ void finish_query(const FinishParams &p, long long q, double dist,
                                              int id, int lane) {
+    if (p.row_map) q = p.row_map[q];
     const long long row = p.row_offset + q;
     int kk = p.k + (p.exclude_self ? 1 : 0);
     if (lane >= kk) {
@@ -348,7 +367,7 @@ __device__ __forceinline__ void finish_query(const FinishParams &p, long long q,
             for (int c = 0; c < p.k; ++c) {
                 double wc = __shfl_sync(SK_FULL, w, c);
                 int ic = __shfl_sync(SK_FULL, id, c);
-                if (j < p.n_out) {
+                if (j < p.n_out && ic >= 0 && ic < p.n_ref) {
                     double yv = p.y[(long long)ic * p.n_out + j];
                     num = (p.weights == 1) ? (num + yv) : (num + yv * wc);
                 }

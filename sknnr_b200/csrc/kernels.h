@@ -12,17 +12,32 @@ struct FinishParams;
 // ---- project.cu: Z = ((X - center) / scale) @ proj  (S2, a1-a4) -----------------------
 // Writes Z as float64 rows (exact re-rank operand) and as the search kernel's query tile
 // image [n_qtiles][dpad][256] f32 = -2 * (Z - mu).
+// Also (optionally) the tensor-core engine's image [n_tiles][tc_mt][dpad/4+2][128][4] TF32
+// (tc_mt = M tiles per CTA of the tensor kernel).
+// Both images are zero-padded to a multiple of 768 rows (padded_rows).  n_rows_dev != null makes
+// the launch "compacted": only the first *n_rows_dev rows exist (device-side count).
+inline long long padded_rows(long long n) { return (n + 767) / 768 * 768; }
 cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long n_q, int d_in,
                            int d_out, int dpad, const double *center, const double *scale,
                            const double *proj, const double *mu, double *z64, float *qimg,
-                           cudaStream_t st);
+                           float *qimg_tc, int tc_mt, const int *n_rows_dev, cudaStream_t st);
+// z64c[i, :] = z64[list[i], :] for i < *count (rows whose certificate failed)
+cudaError_t launch_gather_rows(const double *z64, int d, const int *list, const int *count,
+                               long long max_rows, double *z64c, cudaStream_t st);
 
 // ---- search_simt.cu --------------------------------------------------------------------
 size_t search_simt_smem_bytes(int dpad, int kc, int nstage);
 int search_simt_pick_stages(int dpad, int kc);
 cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, int n_rtiles,
                                long long n_q, int kc, int *cand_idx, float *cand_thr,
-                               cudaStream_t st);
+                               const int *n_rows_dev, cudaStream_t st);
+
+// ---- search_tc.cu (tcgen05 / TMEM engine) ------------------------------------------------
+size_t search_tc_smem_bytes(int kc_tot, int nstage, int mt);
+void search_tc_pick_shape(int kc_tot, int *mt, int *nstage);
+cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,
+                             long long n_q, int kc, int mt, int nstage, int *cand_idx,
+                             float *cand_thr, cudaStream_t st);
 
 // ---- refine.cu -------------------------------------------------------------------------
 struct RefineArgs {
@@ -39,6 +54,8 @@ struct RefineArgs {
     double r2max;           // max_j |ref_j - mu|^2
     int *fb_count;          // number of uncertified queries (device)
     int *fb_list;           // their row numbers (device, capacity n_q)
+    const int *n_rows_dev;  // compacted launch: only the first *n_rows_dev rows exist
+    const int *row_map;     // compacted launch: row of the original chunk (goes into fb_list)
 };
 cudaError_t launch_refine(const RefineArgs &a, const FinishParams &fp, cudaStream_t st);
 

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(REFINE_WARPS * 32)
 refine_kernel(RefineArgs a, FinishParams fp) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * REFINE_WARPS + warp;
-    if (q >= a.n_q) return;
+    if (q >= a.n_q || (a.n_rows_dev && q >= *a.n_rows_dev)) return;
     const double *zq = a.z64 + q * a.d;
 
     int id = 0x7fffffff;
@@ -67,7 +67,7 @@ refine_kernel(RefineArgs a, FinishParams fp) {
     if (!ok) {
         if (lane == 0) {
             const int pos = atomicAdd(a.fb_count, 1);
-            a.fb_list[pos] = (int)q;
+            a.fb_list[pos] = a.row_map ? a.row_map[q] : (int)q;
         }
         return;
     }
@@ -195,6 +195,26 @@ __global__ void weighted_average_kernel(const long long *__restrict__ idx,
         for (int c = 0; c < k; ++c) num += y[idx[q * k + c] * n_out + j] * w[q * k + c];
         out[q * n_out + j] = num / denom;
     }
+}
+
+__global__ void gather_rows_kernel(const double *__restrict__ z64, int d, const int *__restrict__ list,
+                                   const int *__restrict__ count, double *__restrict__ z64c) {
+    const long long n = *count;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n * d;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / d;
+        const int k = (int)(e - i * d);
+        z64c[e] = z64[(long long)list[i] * d + k];
+    }
+}
+
+cudaError_t launch_gather_rows(const double *z64, int d, const int *list, const int *count,
+                               long long max_rows, double *z64c, cudaStream_t st) {
+    if (max_rows <= 0) return cudaSuccess;
+    const long long want = (max_rows * d + 255) / 256;
+    const int grid = (int)(want < 1184 ? want : 1184);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(z64, d, list, count, z64c);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_weighted_average(const long long *idx, const double *w, long long n_q, int k,

@@ -33,7 +33,12 @@ template <int KC>
 __global__ void __launch_bounds__(SEARCH_THREADS, 1)
 search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int dpad,
                    int n_rtiles, int nstage, long long n_q, int *__restrict__ cand_idx,
-                   float *__restrict__ cand_thr) {
+                   float *__restrict__ cand_thr, const int *__restrict__ n_rows_dev) {
+    if (n_rows_dev) {  // compacted launch: CTAs beyond the device-side row count have no work
+        const long long n_dev = *n_rows_dev;
+        if ((long long)blockIdx.x * QTILE >= n_dev) return;
+        n_q = min(n_q, n_dev);
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int rtile_floats = (dpad + 1) * RTILE;
     float *Qs = reinterpret_cast<float *>(smem_raw);
@@ -231,7 +236,8 @@ int search_simt_pick_stages(int dpad, int kc) {
 
 template <int KC>
 static cudaError_t launch_kc(const float *qimg, const float *rimg, int dpad, int n_rtiles,
-                             long long n_q, int *cand_idx, float *cand_thr, cudaStream_t st) {
+                             long long n_q, int *cand_idx, float *cand_thr, const int *n_rows_dev,
+                             cudaStream_t st) {
     const int nstage = search_simt_pick_stages(dpad, KC);
     if (nstage == 0) return cudaErrorInvalidValue;
     const size_t smem = search_simt_smem_bytes(dpad, KC, nstage);
@@ -240,17 +246,18 @@ static cudaError_t launch_kc(const float *qimg, const float *rimg, int dpad, int
     if (e != cudaSuccess) return e;
     const long long n_qtiles = (n_q + QTILE - 1) / QTILE;
     search_simt_kernel<KC><<<(unsigned)n_qtiles, SEARCH_THREADS, smem, st>>>(
-        qimg, rimg, dpad, n_rtiles, nstage, n_q, cand_idx, cand_thr);
+        qimg, rimg, dpad, n_rtiles, nstage, n_q, cand_idx, cand_thr, n_rows_dev);
     return cudaGetLastError();
 }
 
 cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, int n_rtiles,
                                long long n_q, int kc, int *cand_idx, float *cand_thr,
-                               cudaStream_t st) {
+                               const int *n_rows_dev, cudaStream_t st) {
+    if (n_q <= 0) return cudaSuccess;
     switch (kc) {
-        case 8: return launch_kc<8>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, st);
-        case 16: return launch_kc<16>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, st);
-        case 32: return launch_kc<32>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, st);
+        case 8: return launch_kc<8>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, st);
+        case 16: return launch_kc<16>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, st);
+        case 32: return launch_kc<32>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, st);
         default: return cudaErrorInvalidValue;
     }
 }

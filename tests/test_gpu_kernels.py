@@ -130,15 +130,38 @@ def test_mahalanobis_projection_and_engines_agree():
     d_o, i_o = orc.kneighbors(st, Q, k=7)
     d_g, i_g, _ = ix.query(Q, 7)
     orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=RTOL, atol=1e-7)
-    assert ix.stats()["engine"] == L.ENGINE_SIMT
-    L.set_option("engine", L.ENGINE_EXACT)
+    assert ix.stats()["engine"] == L.ENGINE_TENSOR      # default first stage: tcgen05 filter
+    # every engine is only a filter in front of the same float64 refine: identical results
+    for engine in (L.ENGINE_SIMT, L.ENGINE_EXACT, L.ENGINE_TENSOR):
+        L.set_option("engine", engine)
+        try:
+            d_e, i_e, _ = ix.query(Q, 7)
+            assert ix.stats()["engine"] == engine
+        finally:
+            L.set_option("engine", L.ENGINE_AUTO)
+        np.testing.assert_array_equal(i_e, i_g)
+        np.testing.assert_array_equal(d_e, d_g)
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_ill_conditioned_raw_features_cascade(engine):
+    """Raw, uncentred features with huge norms relative to neighbour distances: the TF32 filter
+    cannot certify most rows, the cascade hands them to the FP32 engine and the exact kernel,
+    and the answers still match the oracle."""
+    from sknnr_b200 import _lib as L
+
+    rng = np.random.default_rng(11)
+    R = rng.standard_normal((3000, 5)) * np.array([1.0, 50.0, 0.01, 3.0, 1000.0]) + np.array([5e5, 4e6, 10.0, 0.0, 2e4])
+    Q = R[rng.integers(0, 3000, 900)] + rng.standard_normal((900, 5)) * np.array([0.3, 20.0, 0.003, 1.0, 300.0])
+    st = orc.FittedState("euclidean", fit_Z=R, y=np.zeros((3000, 1)))
+    ix = _index(st)
+    L.set_option("engine", engine)
     try:
-        d_e, i_e, _ = ix.query(Q, 7)
-        assert ix.stats()["engine"] == L.ENGINE_EXACT
+        d_g, i_g, _ = ix.query(Q, 5, transformed=True)
     finally:
         L.set_option("engine", L.ENGINE_AUTO)
-    np.testing.assert_array_equal(i_e, i_g)
-    np.testing.assert_array_equal(d_e, d_g)
+    d_o, i_o = orc.kneighbors(st, Q, k=5, transformed=True)
+    orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=1e-5, atol=1e-3 * float(d_o.mean()))
 
 
 def test_adversarial_duplicates_offsets_and_self_queries():
