@@ -143,17 +143,23 @@ __device__ __forceinline__ void tc_compact(unsigned need, float *buf_s, int *buf
 template <int LD>
 __device__ __forceinline__ void tc_append8(const float *w, float thr, int idb, float *buf_s, int *buf_i,
                                            int tid, int &cnt) {
+    float *ps = buf_s + cnt * LD + tid;
+    int *pi = buf_i + cnt * LD + tid;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (w[j] < thr) {
-            buf_s[cnt * LD + tid] = w[j];
-            buf_i[cnt * LD + tid] = idb + j;
+            *ps = w[j];
+            *pi = idb + j;
+            ps += LD;
+            pi += LD;
             ++cnt;
         }
     }
 }
 
-// selection over 32 accumulator columns of this thread's query
+// selection over 32 accumulator columns of this thread's query.  Hits are rare (about one per
+// warp per call), so every level of the test is a warp-uniform vote + branch: the common path
+// is the min3 tree and one vote.
 template <int KC, int LD>
 __device__ __forceinline__ void tc_select32(const uint32_t (&r)[32], int idb, float *buf_s, int *buf_i,
                                             int tid, int warp, int lane, float &thr, int &cnt) {
@@ -168,11 +174,13 @@ __device__ __forceinline__ void tc_select32(const uint32_t (&r)[32], int idb, fl
                         fminf(fminf(w[4], w[5]), fminf(w[6], w[7])));
     }
     const float m = fminf(fminf(ms[0], ms[1]), fminf(ms[2], ms[3]));
+    if (!__any_sync(SK_FULL, m < thr)) return;
     unsigned pend = 0;
-    if (m < thr) {
 #pragma unroll
-        for (int sub = 0; sub < 4; ++sub) {
-            if (ms[sub] < thr) {
+    for (int sub = 0; sub < 4; ++sub) {
+        const bool hit = ms[sub] < thr;
+        if (__any_sync(SK_FULL, hit)) {
+            if (hit) {
                 if (cnt > TC_CAP - 8)
                     pend |= 1u << sub;   // no room for 8 more: compact first (warp-cooperative)
                 else
@@ -184,10 +192,11 @@ __device__ __forceinline__ void tc_select32(const uint32_t (&r)[32], int idb, fl
     unsigned need = __ballot_sync(SK_FULL, pend != 0);
     while (need) {
         tc_compact<KC, LD>(need, buf_s, buf_i, warp, lane, thr, cnt);
-        if (pend) {
 #pragma unroll
-            for (int sub = 0; sub < 4; ++sub) {
-                if (pend & (1u << sub)) {
+        for (int sub = 0; sub < 4; ++sub) {
+            const bool retry = (pend >> sub) & 1u;
+            if (__any_sync(SK_FULL, retry)) {
+                if (retry) {
                     if (!(ms[sub] < thr)) {
                         pend &= ~(1u << sub);
                     } else if (cnt <= TC_CAP - 8) {
