@@ -23,8 +23,13 @@ def run(n_ref, n_q, d, k, engine):
           f"fallback={stt['n_fallback']} used_engine={stt['engine']} launches={stt['kernel_launches']} {dt*1e3:.1f} ms", flush=True)
 
 if __name__ == "__main__":
-    for args in [(300, 200, 8, 3), (1000, 700, 32, 7), (5000, 3000, 32, 7), (20000, 4000, 64, 7), (777, 513, 17, 5), (4096, 1024, 40, 12)]:
+    for args in [(300, 200, 8, 3), (1000, 700, 32, 7), (5000, 3000, 32, 7), (20000, 4000, 64, 7), (777, 513, 17, 5), (4096, 1024, 40, 12),
+                 (50000, 3000, 32, 7), (9000, 2000, 24, 15)]:
         for engine in (2, 1):
             run(*args, engine)
+    for stride in (0, 2, 8):
+        L.set_option("tc_seed_stride", stride)
+        run(50000, 3000, 32, 7, 2)
+    L.set_option("tc_seed_stride", 4)
     L.set_option("engine", 0)
     print("tc_smoke done")

@@ -41,6 +41,7 @@ struct Options {
     int64_t chunk_rows = 1 << 20;
     int64_t timing = 0;
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
+    int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = off)
 } g_opt;
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -217,7 +218,7 @@ struct sknnr_index : IndexBase {
     int n_rtiles = 0;
     double r2max = 0.0;
     float *d_rimg_tc = nullptr;    // tensor-core engine reference image
-    int n_rtiles_tc = 0, kc_tot = 0, tc_mt = 0, tc_nstage = 0;
+    int n_rtiles_tc = 0, kc_tot = 0, tc_nstage = 0;
     bool tensor_ok = false;        // shape fits the tensor engine
     bool tensor_demoted = false;   // too many uncertified rows: fall back to the SIMT engine
 };
@@ -258,6 +259,9 @@ int sknnr_set_option(const char *name, int64_t value) {
         if (value != 0 && value != 8 && value != 16 && value != 32)
             return fail(SKNNR_EINVAL, "kc must be 0, 8, 16 or 32");
         g_opt.kc = value;
+    } else if (!strcmp(name, "tc_seed_stride")) {
+        if (value < 0 || value > 64) return fail(SKNNR_EINVAL, "tc_seed_stride must be 0..64");
+        g_opt.tc_seed_stride = value;
     } else {
         return fail(SKNNR_EINVAL, std::string("unknown option ") + name);
     }
@@ -342,13 +346,13 @@ int sknnr_index_create(const double *fit_z, int64_t n_ref, int32_t d_out, const 
     if (e == cudaSuccess)
         e = cudaMemcpy(ix->d_rimg, rimg.data(), rimg.size() * sizeof(float), cudaMemcpyHostToDevice);
 
-    // tensor-core engine image: tiles of 64 plots, [chunk][row][4] TF32 (round to nearest),
+    // tensor-core engine image: tiles of 128 plots, [chunk][row][4] TF32 (round to nearest),
     // K padded to dpad plus one extra block whose first chunk holds a 3-way TF32 split of |r|^2
     // (+inf for padding plots) and whose second chunk is zero
     ix->kc_tot = ix->dpad / 4 + 2;
     ix->n_rtiles_tc = (int)((n_ref + TC_N - 1) / TC_N);
-    search_tc_pick_shape(ix->kc_tot, &ix->tc_mt, &ix->tc_nstage);
-    ix->tensor_ok = ix->tc_mt != 0;
+    ix->tc_nstage = search_tc_pick_stages(ix->kc_tot);
+    ix->tensor_ok = ix->tc_nstage != 0;
     if (e == cudaSuccess && ix->tensor_ok) {
         auto tf32 = [](float x) -> float {
             uint32_t b;
@@ -462,7 +466,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     CK(launch_project(dX, x_f32, ldx, rows, transformed ? ix->d_out : ix->d_in, ix->d_out, ix->dpad,
                       transformed ? nullptr : ix->d_center, transformed ? nullptr : ix->d_scale,
                       transformed ? nullptr : ix->d_proj, ix->d_mu, s.z64.p,
-                      use_simt_first ? s.qimg.p : nullptr, use_tc ? s.qimg_tc.p : nullptr, ix->tc_mt, nullptr, st));
+                      use_simt_first ? s.qimg.p : nullptr, use_tc ? s.qimg_tc.p : nullptr, 2, nullptr, st));
     ix->stats.kernel_launches++;
 
     ExactArgs ea{};
@@ -511,8 +515,8 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     const int *stage2_count = nullptr;  // null: stage 2 covers every row of the chunk
     if (use_tc) {
         if (g_opt.timing) CK(s.mark(st));
-        CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, kc, ix->tc_mt,
-                            ix->tc_nstage, s.cand_idx.p, s.cand_thr.p, st));
+        CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, kc, ix->tc_nstage,
+                            (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, st));
         if (g_opt.timing) CK(s.mark(st));
         ra.z64 = s.z64.p;
         ra.n_q = rows;

@@ -17,9 +17,9 @@ constexpr int QTILE = 32 * NCOMPUTE_WARPS;  // queries per CTA tile (32 per comp
 constexpr int RTILE = 64;       // reference plots per staged tile
 constexpr int SEARCH_THREADS = NCOMPUTE_WARPS * 32;  // lane 0 of warp 0 also issues the TMA copies
 constexpr int MAXK = 32;        // entries handled by one warp-wide sort
-// tensor-core engine tile shape: M = 128 queries per MMA (2 or 3 M tiles per CTA), N = 64 plots
+// tensor-core engine tile shape: M = 128 queries per MMA (2 M tiles per CTA), N = 128 plots
 constexpr int TC_M = 128;
-constexpr int TC_N = 64;
+constexpr int TC_N = 128;
 
 // ---------------------------------------------------------------------------------------
 // mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP)

@@ -12,8 +12,8 @@ struct FinishParams;
 // ---- project.cu: Z = ((X - center) / scale) @ proj  (S2, a1-a4) -----------------------
 // Writes Z as float64 rows (exact re-rank operand) and as the search kernel's query tile
 // image [n_qtiles][dpad][256] f32 = -2 * (Z - mu).
-// Also (optionally) the tensor-core engine's image [n_tiles][tc_mt][dpad/4+2][128][4] TF32
-// (tc_mt = M tiles per CTA of the tensor kernel).
+// Also (optionally) the tensor-core engine's image [n_q/128][dpad/4+2][128][4] TF32 (two
+// consecutive 128-row operands form one CTA tile of the tensor kernel).
 // Both images are zero-padded to a multiple of 768 rows (padded_rows).  n_rows_dev != null makes
 // the launch "compacted": only the first *n_rows_dev rows exist (device-side count).
 inline long long padded_rows(long long n) { return (n + 767) / 768 * 768; }
@@ -33,10 +33,12 @@ cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, i
                                const int *n_rows_dev, cudaStream_t st);
 
 // ---- search_tc.cu (tcgen05 / TMEM engine) ------------------------------------------------
-size_t search_tc_smem_bytes(int kc_tot, int nstage, int mt);
-void search_tc_pick_shape(int kc_tot, int *mt, int *nstage);
+size_t search_tc_smem_bytes(int kc_tot, int nstage);
+int search_tc_pick_stages(int kc_tot);   // 0: the shape does not fit the engine
+int search_tc_seed_tiles(int n_rtiles, int seed_stride);
+// seed_stride: every seed_stride-th reference tile is pre-scanned to seed the thresholds (0 = off)
 cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int kc, int mt, int nstage, int *cand_idx,
+                             long long n_q, int kc, int nstage, int seed_stride, int *cand_idx,
                              float *cand_thr, cudaStream_t st);
 
 // ---- refine.cu -------------------------------------------------------------------------
