@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--kc", type=int, default=0)
+    ap.add_argument("--tc-seed-stride", type=int, default=-1)
+    ap.add_argument("--tc-mt", type=int, default=0)
+    ap.add_argument("--tc-debug", type=int, default=0)
     return ap.parse_args()
 
 
@@ -206,6 +209,12 @@ def run_ours(a, rank, world, local_rank):
         L.set_option("engine", a.engine)
     if a.kc:
         L.set_option("kc", a.kc)
+    if a.tc_mt:
+        L.set_option("tc_mt", a.tc_mt)
+    if a.tc_debug:
+        L.set_option("tc_debug", a.tc_debug)
+    if a.tc_seed_stride >= 0:
+        L.set_option("tc_seed_stride", a.tc_seed_stride)
 
     R, y, mean, scale = make_reference_set(a)
     index = KNNIndex((R - mean) / scale, mean, scale, None, y, device=local_rank)

@@ -1,4 +1,5 @@
 set -x
-timeout 300 python scripts/tc_smoke.py > gpurun_out/tc_smoke.log 2>&1; echo tc_smoke_exit=$?; tail -22 gpurun_out/tc_smoke.log
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$?; tail -5 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 2 --warmup 1 --n-queries 4194304 --no-cpu-baseline > gpurun_out/bench_tc.log 2>&1; echo bench_exit=$?; tail -c 2600 gpurun_out/bench_tc.log | head -c 1800
+timeout 300 python scripts/tc_smoke.py > gpurun_out/tc_smoke.log 2>&1; echo tc_smoke_exit=$?; grep -c OK gpurun_out/tc_smoke.log; grep -v OK gpurun_out/tc_smoke.log | tail -5
+B="python bench.py --steps 1 --warmup 1 --n-queries 1048576 --no-cpu-baseline --no-e2e"
+for m in 2 3 4; do timeout 300 $B --tc-mt $m > gpurun_out/bench_mt$m.log 2>&1; echo exit=$?; grep -o '"kernel_ms_per_step": [0-9.]*\|"ms_per_step": [0-9.]*' gpurun_out/bench_mt$m.log | tr '\n' ' '; echo; done
+for m in 2 3 4; do timeout 300 $B --tc-mt $m --tc-debug 1 > gpurun_out/bench_dbg$m.log 2>&1; echo exit=$?; grep -o '"kernel_ms_per_step": [0-9.]*\|"ms_per_step": [0-9.]*' gpurun_out/bench_dbg$m.log | tr '\n' ' '; echo; done

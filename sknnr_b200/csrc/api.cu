@@ -41,6 +41,7 @@ struct Options {
     int64_t chunk_rows = 1 << 20;
     int64_t timing = 0;
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
+    int64_t tc_mt = 0;          // tensor engine: M tiles per CTA (0 = automatic, else 2..4)
     int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = off)
 } g_opt;
 
@@ -218,7 +219,7 @@ struct sknnr_index : IndexBase {
     int n_rtiles = 0;
     double r2max = 0.0;
     float *d_rimg_tc = nullptr;    // tensor-core engine reference image
-    int n_rtiles_tc = 0, kc_tot = 0, tc_nstage = 0;
+    int n_rtiles_tc = 0, kc_tot = 0, tc_mt = 0, tc_nstage = 0;
     bool tensor_ok = false;        // shape fits the tensor engine
     bool tensor_demoted = false;   // too many uncertified rows: fall back to the SIMT engine
 };
@@ -259,6 +260,11 @@ int sknnr_set_option(const char *name, int64_t value) {
         if (value != 0 && value != 8 && value != 16 && value != 32)
             return fail(SKNNR_EINVAL, "kc must be 0, 8, 16 or 32");
         g_opt.kc = value;
+    } else if (!strcmp(name, "tc_debug")) {
+        g_tc_debug = (int)value;
+    } else if (!strcmp(name, "tc_mt")) {
+        if (value != 0 && (value < 2 || value > 4)) return fail(SKNNR_EINVAL, "tc_mt must be 0 or 2..4");
+        g_opt.tc_mt = value;
     } else if (!strcmp(name, "tc_seed_stride")) {
         if (value < 0 || value > 64) return fail(SKNNR_EINVAL, "tc_seed_stride must be 0..64");
         g_opt.tc_seed_stride = value;
@@ -351,8 +357,8 @@ int sknnr_index_create(const double *fit_z, int64_t n_ref, int32_t d_out, const 
     // (+inf for padding plots) and whose second chunk is zero
     ix->kc_tot = ix->dpad / 4 + 2;
     ix->n_rtiles_tc = (int)((n_ref + TC_N - 1) / TC_N);
-    ix->tc_nstage = search_tc_pick_stages(ix->kc_tot);
-    ix->tensor_ok = ix->tc_nstage != 0;
+    search_tc_pick_shape(ix->kc_tot, (int)g_opt.tc_mt, &ix->tc_mt, &ix->tc_nstage);
+    ix->tensor_ok = ix->tc_mt != 0;
     if (e == cudaSuccess && ix->tensor_ok) {
         auto tf32 = [](float x) -> float {
             uint32_t b;
@@ -515,7 +521,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     const int *stage2_count = nullptr;  // null: stage 2 covers every row of the chunk
     if (use_tc) {
         if (g_opt.timing) CK(s.mark(st));
-        CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, kc, ix->tc_nstage,
+        CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, kc, ix->tc_mt, ix->tc_nstage,
                             (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, st));
         if (g_opt.timing) CK(s.mark(st));
         ra.z64 = s.z64.p;

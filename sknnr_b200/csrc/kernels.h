@@ -14,9 +14,10 @@ struct FinishParams;
 // image [n_qtiles][dpad][256] f32 = -2 * (Z - mu).
 // Also (optionally) the tensor-core engine's image [n_q/128][dpad/4+2][128][4] TF32 (two
 // consecutive 128-row operands form one CTA tile of the tensor kernel).
-// Both images are zero-padded to a multiple of 768 rows (padded_rows).  n_rows_dev != null makes
+// Both images are zero-padded to a multiple of 1536 rows (padded_rows: every CTA tile size of
+// either engine - 256, 384, 512 - divides it).  n_rows_dev != null makes
 // the launch "compacted": only the first *n_rows_dev rows exist (device-side count).
-inline long long padded_rows(long long n) { return (n + 767) / 768 * 768; }
+inline long long padded_rows(long long n) { return (n + 1535) / 1536 * 1536; }
 cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long n_q, int d_in,
                            int d_out, int dpad, const double *center, const double *scale,
                            const double *proj, const double *mu, double *z64, float *qimg,
@@ -33,12 +34,14 @@ cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, i
                                const int *n_rows_dev, cudaStream_t st);
 
 // ---- search_tc.cu (tcgen05 / TMEM engine) ------------------------------------------------
-size_t search_tc_smem_bytes(int kc_tot, int nstage);
-int search_tc_pick_stages(int kc_tot);   // 0: the shape does not fit the engine
+size_t search_tc_smem_bytes(int kc_tot, int nstage, int mt);
+// (M tiles per CTA, ring stages); want_mt = 0: automatic; *mt = 0: the shape does not fit
+void search_tc_pick_shape(int kc_tot, int want_mt, int *mt, int *nstage);
 int search_tc_seed_tiles(int n_rtiles, int seed_stride);
+extern int g_tc_debug;  // timing experiments: bit 0 = skip the hit path (wrong results)
 // seed_stride: every seed_stride-th reference tile is pre-scanned to seed the thresholds (0 = off)
 cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int kc, int nstage, int seed_stride, int *cand_idx,
+                             long long n_q, int kc, int mt, int nstage, int seed_stride, int *cand_idx,
                              float *cand_thr, cudaStream_t st);
 
 // ---- refine.cu -------------------------------------------------------------------------

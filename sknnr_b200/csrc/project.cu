@@ -116,10 +116,9 @@ cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long
     const int xs_ld = d_in | 1;
     const size_t smem = ((size_t)PROJ_THREADS * xs_ld + (proj ? (size_t)d_in * d_out : 0)) * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    // cover whole query tiles so that padding columns of the last tile are zero-filled
-    // (QTILE = 384 and TC_QT = 256 are both multiples of PROJ_THREADS = 128; the image buffers
-    // are sized for the larger padding)
-    const long long padded = (n_q + QTILE * 2 - 1) / (QTILE * 2) * (QTILE * 2);
+    // cover whole query tiles so that padding columns of the last tile are zero-filled (every
+    // CTA tile size of the search engines divides padded_rows, a multiple of PROJ_THREADS)
+    const long long padded = padded_rows(n_q);
     const long long grid = (padded + PROJ_THREADS - 1) / PROJ_THREADS;
     cudaError_t e;
     if (x_is_f32) {

@@ -12,12 +12,16 @@
 // certify are re-searched by the FP32 SIMT engine and, failing that, by the exhaustive float64
 // kernel.
 //
-// One CTA = 256 queries = two M=128 MMA tiles that share every reference tile (N=128):
-//   warp 8, lane 0   driver: TMA bulk copies (cp.async.bulk + mbarrier) of the query image once
-//                    and of reference tiles through an NSTAGE ring, then K/8 x 2 tcgen05.mma
-//                    per tile, tcgen05.commit onto the "smem slot free" and "accumulator ready"
-//                    mbarriers;
-//   warps 0..7       epilogue: thread <-> query (TMEM lane).  The 128 accumulator columns of a
+// One CTA = MT x 128 queries = MT (2, 3 or 4) M=128 MMA tiles that share every reference tile
+// (N=128).  A "job" is one (reference tile, M tile) pair = K/8 tcgen05.mma into one of four
+// 128-column TMEM accumulator slots; jobs run in (tile, M tile) order and job j uses slot j % 4,
+// so the MMAs of up to 4 - MT later jobs overlap the epilogue of the current ones (MT = 2: two
+// full stages; MT = 4: each M tile's next job starts as soon as its own slot has been read).
+//   warp 4MT+1, lane 0  TMA producer: bulk copies (cp.async.bulk + mbarrier) of the query image
+//                    once and of reference tiles through an NSTAGE ring;
+//   warp 4MT, lane 0    MMA issuer: the tcgen05.mma of every job, tcgen05.commit onto the
+//                    "smem slot free" and "accumulator slot ready" mbarriers;
+//   warps 0..4MT-1   epilogue: thread <-> query (TMEM lane), four warps per M tile.  The 128 accumulator columns of a
 //                    tile are read 32 at a time with tcgen05.ld into two alternating register
 //                    buffers (the load of chunk c+1 is in flight while chunk c is reduced), a
 //                    min3 tree gives the chunk minimum, one vote tells whether any lane of the
@@ -27,8 +31,8 @@
 //                    in shared memory).  When a buffer overflows the whole warp compacts: every
 //                    thread sorts the scores of its own buffer in registers (bitonic network),
 //                    keeps the KC smallest and lowers its threshold to the KC-th.
-//   two TMEM accumulator stages (2 stages x 2 M tiles x 128 columns = all 512 columns) let the
-//   MMAs of tile t+1 overlap the epilogue of tile t.
+//   More M tiles = more epilogue warps per SM (the epilogue is latency-bound: dependent vote /
+//   shuffle / shared-memory chains), fewer = deeper MMA look-ahead and room for a larger K.
 //
 // Threshold seeding.  A streaming top-KC pays KC*ln(n_ref/KC) threshold hits per query, almost
 // all of them while the threshold is still loose.  The kernel therefore first runs every
@@ -52,15 +56,21 @@
 
 namespace sk {
 
-constexpr int TC_MT = 2;                        // M tiles (of 128 queries) per CTA
-constexpr int TC_QT = TC_MT * TC_M;             // queries per CTA
-constexpr int TC_EPI_WARPS = TC_MT * 4;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 1) * 32;
-constexpr int TC_CAP = 32;                      // candidate buffer slots per query
-constexpr int TC_LD = TC_QT + 1;                // slot stride (odd: a query's slots hit 32 banks)
+constexpr int TC_SLOTS = 4;                     // TMEM accumulator slots of TC_N columns
 constexpr int TC_GROUPS = 32;                   // seeding: group minima per query
+constexpr int TC_SORT = 32;                     // width of the register sorting network (>= CAP)
+template <int MT_, int CAP_> struct TcCfg {
+    static constexpr int MT = MT_;                    // M tiles (of 128 queries) per CTA
+    static constexpr int CAP = CAP_;                  // candidate buffer slots per query
+    static constexpr int QT = MT * TC_M;              // queries per CTA
+    static constexpr int EPI_WARPS = MT * 4;
+    static constexpr int THREADS = (EPI_WARPS + 2) * 32;  // + MMA issuer warp + TMA producer warp
+    static constexpr int LD = QT + 1;                 // slot stride (odd: a query's slots hit 32 banks)
+    static_assert(CAP <= TC_SORT && CAP % 2 == 0, "candidate buffer shape");
+};
 constexpr uint32_t TC_ROWB = 16;                // bytes of one row of one K chunk (4 TF32)
 static_assert(TC_N == 128, "epilogue assumes four 32-column chunks per tile");
+static_assert(TC_SLOTS * TC_N == 512, "the accumulator slots fill TMEM");
 
 // ---- tcgen05 wrappers -------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
@@ -73,6 +83,18 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                  : "memory");
+}
+// true in exactly one (converged) lane of the warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -187,13 +209,14 @@ struct ThrCnt {
 // KC-th smallest.  Entries equal to the new threshold are kept only up to KC entries in total;
 // the dropped ones are >= the threshold, which is all the certificate needs.  Called by all 32
 // lanes (data-independent network, no divergence).
-template <int KC>
+template <int KC, int CAP, int LD>
 __device__ __noinline__ ThrCnt tc_compact_all(float *col_s, int *col_i, float thr, int cnt) {
+    static_assert(KC < CAP, "the buffer needs slack above KC");
     __syncwarp();
-    float s[TC_CAP];
+    float s[TC_SORT];
 #pragma unroll
-    for (int j = 0; j < TC_CAP; ++j) s[j] = (j < cnt) ? col_s[j * TC_LD] : SK_INF_F;
-    sort_regs<TC_CAP>(s);
+    for (int j = 0; j < TC_SORT; ++j) s[j] = (j < CAP && j < cnt) ? col_s[j * LD] : SK_INF_F;
+    sort_regs<TC_SORT>(s);
     const float t = s[KC - 1];  // +inf while the buffer holds fewer than KC entries
     int n_less = 0;
 #pragma unroll
@@ -201,16 +224,16 @@ __device__ __noinline__ ThrCnt tc_compact_all(float *col_s, int *col_i, float th
     int quota = KC - n_less;    // entries equal to t that may stay
     int w = 0;
 #pragma unroll 4
-    for (int j = 0; j < TC_CAP; ++j) {
-        const float v = col_s[j * TC_LD];
-        const int id = col_i[j * TC_LD];
+    for (int j = 0; j < CAP; ++j) {
+        const float v = col_s[j * LD];
+        const int id = col_i[j * LD];
         const bool valid = j < cnt;
         const bool lt = valid && (v < t);
         const bool eq = valid && (v == t) && quota > 0;
         if (eq) --quota;
         if (lt || eq) {
-            col_s[w * TC_LD] = v;
-            col_i[w * TC_LD] = id;
+            col_s[w * LD] = v;
+            col_i[w * LD] = id;
             ++w;
         }
     }
@@ -224,12 +247,16 @@ __device__ __noinline__ ThrCnt tc_compact_all(float *col_s, int *col_i, float th
 // One 32-column chunk of the main pass.  `r` holds this thread's scores against references
 // idb .. idb+31; `inflight` is the other register buffer, whose tcgen05.ld may still be in
 // flight (it must land before a function call may spill it).
-template <int KC>
+template <int KC, int CAP, int LD>
 __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], uint32_t (&inflight)[32], int idb,
                                            float *buf_s, int *buf_i, float *scratch, int tid,
-                                           int lane, float &thr, int &cnt) {
+                                           int lane, float &thr, int &cnt, int dbg) {
     const float m = tc_min32(r);
     unsigned hits = __ballot_sync(SK_FULL, m < thr);
+    if (dbg & 1) {  // timing experiment: count the hits, skip the hit path (results are wrong)
+        cnt = (cnt + __popc(hits)) & 15;
+        return;
+    }
     while (hits) {  // warp-uniform: one iteration per lane whose chunk minimum beat its threshold
         const int L = __ffs(hits) - 1;
         hits &= hits - 1;
@@ -250,11 +277,11 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], uint32_t (&i
         int *ci = buf_i + (tid - lane + L);
         while (pending) {
             unsigned take = pending;
-            if (cntL + __popc(pending) > TC_CAP) {
+            if (cntL + __popc(pending) > CAP) {
                 if (cntL > KC) {
                     if (lane == L) cnt = cntL;  // entries appended earlier in this loop
                     tmem_ld_wait(inflight);
-                    const ThrCnt tc = tc_compact_all<KC>(buf_s + tid, buf_i + tid, thr, cnt);
+                    const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + tid, buf_i + tid, thr, cnt);
                     thr = tc.thr;
                     cnt = tc.cnt;
                     thrL = __shfl_sync(SK_FULL, thr, L);
@@ -262,14 +289,14 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], uint32_t (&i
                     pending &= __ballot_sync(SK_FULL, x < thrL);
                     continue;
                 }
-                // at most KC entries held, more than CAP - KC = 16 hits: half a warp at a time
-                take = pending & 0xffffu;
-                if (take == 0) take = pending;
+                // at most KC entries held but more hits than free slots: lowest hits first
+                const int room = CAP - cntL;
+                while (__popc(take) > room) take &= ~(0x80000000u >> __clz(take));
             }
             if ((take >> lane) & 1u) {
                 const int slot = cntL + __popc(take & ((1u << lane) - 1u));
-                cs[slot * TC_LD] = x;
-                ci[slot * TC_LD] = idb + lane;
+                cs[slot * LD] = x;
+                ci[slot * LD] = idb + lane;
             }
             cntL += __popc(take);
             pending &= ~take;
@@ -278,15 +305,15 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], uint32_t (&i
     }
 }
 
-// Epilogue of one reference tile: 4 chunks of 32 columns through the alternating register
-// buffers A / B.  On entry the load of chunk 0 into A has been issued; on exit the load of the
-// next tile's chunk 0 into A has been issued (if there is a next tile).
-template <class F>
-__device__ __forceinline__ void tc_epi_tile(uint32_t (&A)[32], uint32_t (&B)[32], uint32_t tbase,
-                                            int t, int n_seq, uint64_t *tfull, uint64_t *tempty,
-                                            int lane, F &&proc) {
-    const int a = t & 1;
-    const uint32_t tcol = tbase + (uint32_t)(a * TC_MT * TC_N);
+// Epilogue of one job (reference tile x this warp's M tile): 4 chunks of 32 columns through the
+// alternating register buffers A / B.  On entry the load of chunk 0 into A has been issued; on
+// exit the load of chunk 0 of this warp's next job (j + MT) into A has been issued, if any.
+template <int MT, class F>
+__device__ __forceinline__ void tc_epi_job(uint32_t (&A)[32], uint32_t (&B)[32], uint32_t tlane, int j,
+                                           bool has_next, uint64_t *afull, uint64_t *aempty, int lane,
+                                           F &&proc) {
+    const int sl = j & (TC_SLOTS - 1);
+    const uint32_t tcol = tlane + (uint32_t)(sl * TC_N);
     tmem_ld_wait(A);
     tmem_ld32_issue(tcol + 32, B, A[0]);
     proc(A, B, std::integral_constant<int, 0>{});
@@ -297,36 +324,39 @@ __device__ __forceinline__ void tc_epi_tile(uint32_t (&A)[32], uint32_t (&B)[32]
     tmem_ld32_issue(tcol + 96, B, A[0]);
     proc(A, B, std::integral_constant<int, 2>{});
     tmem_ld_wait(B);
-    // every TMEM read of this accumulator stage has landed: hand it back to the MMA issuer
+    // every TMEM read of this accumulator slot has landed: hand it back to the MMA issuer
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty[a]);
-    if (t + 1 < n_seq) {
-        mbar_wait(&tfull[a ^ 1], ((t + 1) >> 1) & 1);
+    if (lane == 0) mbar_arrive(&aempty[sl]);
+    if (has_next) {
+        const int jn = j + MT, sn = jn & (TC_SLOTS - 1);
+        mbar_wait(&afull[sn], (jn >> 2) & 1);
         tc_fence_after();
-        tmem_ld32_issue(tbase + (uint32_t)((a ^ 1) * TC_MT * TC_N), A, B[0]);
+        tmem_ld32_issue(tlane + (uint32_t)(sn * TC_N), A, B[0]);
     }
     proc(B, A, std::integral_constant<int, 3>{});
 }
 
-template <int KC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int KC, int MT, int CAP>
+__global__ void __launch_bounds__(TcCfg<MT, CAP>::THREADS, 1)
 search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int kc_tot,
                  int n_rtiles, int nstage, int n_seed, int seed_stride, long long n_q,
-                 int *__restrict__ cand_idx, float *__restrict__ cand_thr) {
+                 int *__restrict__ cand_idx, float *__restrict__ cand_thr, int dbg) {
+    using Cfg = TcCfg<MT, CAP>;
+    constexpr int LD = Cfg::LD, EPI_WARPS = Cfg::EPI_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t a_bytes = (uint32_t)kc_tot * TC_M * TC_ROWB;  // one 128-query operand image
     const uint32_t b_bytes = (uint32_t)kc_tot * TC_N * TC_ROWB;  // one 128-plot operand image
-    unsigned char *Qs = smem_raw;                                // TC_MT operand images
-    unsigned char *Rs = Qs + TC_MT * a_bytes;                    // nstage operand images
-    float *buf_s = reinterpret_cast<float *>(Rs + (size_t)nstage * b_bytes);
-    int *buf_i = reinterpret_cast<int *>(buf_s + TC_CAP * TC_LD);
-    float *scratch_all = reinterpret_cast<float *>(buf_i + TC_CAP * TC_LD);  // [warps][32], 16-B aligned
-    uint64_t *full = reinterpret_cast<uint64_t *>(scratch_all + TC_EPI_WARPS * 32);
+    unsigned char *Qs = smem_raw;                                // MT operand images
+    unsigned char *Rs = Qs + MT * a_bytes;                       // nstage operand images
+    float *scratch_all = reinterpret_cast<float *>(Rs + (size_t)nstage * b_bytes);  // [warps][32]
+    float *buf_s = scratch_all + EPI_WARPS * 32;
+    int *buf_i = reinterpret_cast<int *>(buf_s + CAP * LD);
+    uint64_t *full = reinterpret_cast<uint64_t *>(buf_i + CAP * LD);  // (CAP * LD * 4) % 8 == 0
     uint64_t *empty = full + nstage;
-    uint64_t *tfull = empty + nstage;   // [2] accumulator stage ready
-    uint64_t *tempty = tfull + 2;       // [2] accumulator stage drained
-    uint64_t *qbar = tempty + 2;
+    uint64_t *afull = empty + nstage;       // [4] accumulator slot ready
+    uint64_t *aempty = afull + TC_SLOTS;    // [4] accumulator slot drained
+    uint64_t *qbar = aempty + TC_SLOTS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qbar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -335,14 +365,14 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], TC_EPI_WARPS);
+        for (int a = 0; a < TC_SLOTS; ++a) {
+            mbar_init(&afull[a], 1);
+            mbar_init(&aempty[a], 4);   // the four epilogue warps of the M tile that used the slot
         }
         mbar_init(qbar, 1);
         fence_mbar_init();
     }
-    if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 512);
+    if (warp == EPI_WARPS) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -351,76 +381,117 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     const int ksteps = kc_tot >> 1;  // MMA K = 8 TF32 = two 16-byte chunks
     const int n_seq = n_seed + n_rtiles;  // sampled tiles (seeding), then every tile
 
-    if (warp == TC_EPI_WARPS) {
-        // ======================= driver: TMA producer + MMA issuer =======================
+    if (warp == EPI_WARPS + 1) {
+        // ======================= TMA producer (one thread) =======================
+        // No divisions, no descriptor rebuilds in these two single-thread loops: each of their
+        // instructions is on the critical path of the tensor pipe.
         if (lane == 0) {
-            auto issue_tile = [&](int tn) {
-                const int sn = tn % nstage;
-                if (tn >= nstage) mbar_wait(&empty[sn], ((tn / nstage) - 1) & 1);
+            mbar_expect_tx(qbar, MT * a_bytes);
+            bulk_g2s(Qs, (const unsigned char *)qimg + (size_t)qtile * MT * a_bytes, MT * a_bytes, qbar);
+            int sn = 0;
+            uint32_t wrap_par = 1;   // parity of (uses of the slot so far - 1); first pass: no wait
+            bool wrapped = false;
+            const unsigned char *rbase = (const unsigned char *)rimg;
+            for (int tn = 0; tn < n_seq; ++tn) {
+                if (wrapped) mbar_wait(&empty[sn], wrap_par);
                 const int tile = tn < n_seed ? tn * seed_stride : tn - n_seed;
                 mbar_expect_tx(&full[sn], b_bytes);
-                bulk_g2s(Rs + (size_t)sn * b_bytes, (const unsigned char *)rimg + (size_t)tile * b_bytes,
-                         b_bytes, &full[sn]);
-            };
-            mbar_expect_tx(qbar, TC_MT * a_bytes);
-            bulk_g2s(Qs, (const unsigned char *)qimg + (size_t)qtile * TC_MT * a_bytes, TC_MT * a_bytes, qbar);
-            for (int tn = 0; tn < nstage - 1 && tn < n_seq; ++tn) issue_tile(tn);
-            mbar_wait(qbar, 0);
-            const uint32_t q_addr = smem_u32(Qs), r_addr = smem_u32(Rs);
-            const uint32_t a_lbo = TC_M * TC_ROWB, b_lbo = TC_N * TC_ROWB;
-            for (int t = 0; t < n_seq; ++t) {
-                const int s = t % nstage, a = t & 1;
-                mbar_wait(&full[s], (t / nstage) & 1);
-                if (t >= 2) mbar_wait(&tempty[a], ((t >> 1) - 1) & 1);
-                tc_fence_after();
-#pragma unroll 1
-                for (int h = 0; h < TC_MT; ++h) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((a * TC_MT + h) * TC_N);
-                    for (int j = 0; j < ksteps; ++j) {
-                        const uint64_t adesc = tc_smem_desc(q_addr + h * a_bytes + j * 2 * a_lbo, a_lbo, 128);
-                        const uint64_t bdesc = tc_smem_desc(r_addr + s * b_bytes + j * 2 * b_lbo, b_lbo, 128);
-                        tc_mma_tf32(d_tmem, adesc, bdesc, TC_IDESC, j > 0 ? 1u : 0u);
-                    }
+                bulk_g2s(Rs + (size_t)sn * b_bytes, rbase + (size_t)tile * b_bytes, b_bytes, &full[sn]);
+                if (++sn == nstage) {
+                    sn = 0;
+                    wrap_par = wrapped ? (wrap_par ^ 1u) : 0u;
+                    wrapped = true;
                 }
-                tc_commit(&empty[s]);   // smem slot reusable once these MMAs have read it
-                tc_commit(&tfull[a]);   // accumulators of tile t complete
-                if (t + nstage - 1 < n_seq) issue_tile(t + nstage - 1);
             }
         }
         __syncwarp();
+    } else if (warp == EPI_WARPS) {
+        // ======================= MMA issuer =======================
+        // The whole warp runs this loop in lock step (uniform control flow keeps descriptors and
+        // counters in uniform registers); one elected lane issues the tcgen05 instructions.
+        mbar_wait(qbar, 0);
+        const uint32_t a_lbo = TC_M * TC_ROWB, b_lbo = TC_N * TC_ROWB;
+        // descriptor = {hi: SBO = 128 B, version 1; lo: start address >> 4 | LBO >> 4 << 16}; moving
+        // to the next K step (two 16-byte chunks) or operand image only adds to the address field
+        const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+        const uint32_t a_lo0 = ((smem_u32(Qs) >> 4) & 0x3fffu) | (((a_lbo >> 4) & 0x3fffu) << 16);
+        const uint32_t b_lo0 = ((smem_u32(Rs) >> 4) & 0x3fffu) | (((b_lbo >> 4) & 0x3fffu) << 16);
+        const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
+        const uint32_t a_img = a_bytes >> 4, b_img = b_bytes >> 4;
+        int s = 0;
+        uint32_t full_par = 0, b_lo_s = b_lo0;
+        int j = 0;               // job number = t * MT + h
+        uint32_t sl = 0;         // j % TC_SLOTS
+        uint32_t aempty_par = 0; // parity of (j / TC_SLOTS - 1), first used by jobs 4..7
+        for (int t = 0; t < n_seq; ++t) {
+            mbar_wait(&full[s], full_par);
+            uint32_t a_lo_h = a_lo0;
+#pragma unroll 1
+            for (int h = 0; h < MT; ++h, ++j) {
+                if (j >= TC_SLOTS) mbar_wait(&aempty[sl], aempty_par);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + sl * TC_N;
+                if (elect_one()) {
+                    uint32_t a_lo = a_lo_h, b_lo = b_lo_s;
+                    tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 0u);
+#pragma unroll 4
+                    for (int ks = 1; ks < ksteps; ++ks) {
+                        a_lo += a_kstep;
+                        b_lo += b_kstep;
+                        tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 1u);
+                    }
+                    tc_commit(&afull[sl]);   // accumulators of job j complete
+                    if (h == MT - 1) tc_commit(&empty[s]);  // smem slot reusable once read
+                }
+                __syncwarp();
+                a_lo_h += a_img;
+                if (++sl == TC_SLOTS) {
+                    sl = 0;
+                    if (j >= TC_SLOTS) aempty_par ^= 1u;
+                }
+            }
+            b_lo_s += b_img;
+            if (++s == nstage) {
+                s = 0;
+                full_par ^= 1u;
+                b_lo_s = b_lo0;
+            }
+        }
     } else {
         // ======================= epilogue: thread <-> query =======================
         const int tid = threadIdx.x;          // query slot; TMEM lane (tid & 127) of M tile (tid >> 7)
         const int h = warp >> 2;
-        const uint32_t tbase = tmem_base + (((uint32_t)((warp & 3) * 32)) << 16) + (uint32_t)(h * TC_N);
+        const uint32_t tlane = tmem_base + (((uint32_t)((warp & 3) * 32)) << 16);
         float *scratch = scratch_all + warp * 32;
         float thr = SK_INF_F;
         int cnt = 0;
         uint32_t A[32], B[32];
-        int t = 0;
-        mbar_wait(&tfull[0], 0);
+        int t = 0;                            // position in the tile sequence; this warp's job = t * MT + h
+        mbar_wait(&afull[h], 0);              // job h uses slot h (MT <= 4), first completion
         tc_fence_after();
         uint32_t dep0 = 0;
-        tmem_ld32_issue(tbase, A, dep0);
+        tmem_ld32_issue(tlane + (uint32_t)(h * TC_N), A, dep0);
 
         // ---- seeding pass: group minima over the sampled tiles ----
+        // (the 32 running minima of a query live in the still unused candidate buffer: slots of
+        // buf_s, then of buf_i; chunk c of the n-th sampled tile feeds group (4n + c) % 32)
         if (n_seed > 0) {
+            static_assert(2 * CAP >= TC_GROUPS, "group minima are parked in the candidate buffers");
+            float *gcol = buf_s + tid;
+#pragma unroll
+            for (int g = 0; g < TC_GROUPS; ++g) gcol[g * LD] = SK_INF_F;   // buf_i follows buf_s
+            for (; t < n_seed; ++t) {
+                const int g0 = (t * 4) & (TC_GROUPS - 1);
+                tc_epi_job<MT>(A, B, tlane, t * MT + h, t + 1 < n_seq, afull, aempty, lane,
+                               [&](const uint32_t (&r)[32], uint32_t (&)[32], auto ic) {
+                                   constexpr int c = decltype(ic)::value;
+                                   float *p = gcol + (g0 + c) * LD;
+                                   *p = fminf(*p, tc_min32(r));
+                               });
+            }
             float gm[TC_GROUPS];
 #pragma unroll
-            for (int g = 0; g < TC_GROUPS; ++g) gm[g] = SK_INF_F;
-            for (int tb = 0; tb < n_seed; tb += TC_GROUPS / 4) {
-#pragma unroll
-                for (int j = 0; j < TC_GROUPS / 4; ++j) {
-                    if (tb + j < n_seed) {
-                        tc_epi_tile(A, B, tbase, t, n_seq, tfull, tempty, lane,
-                                    [&](const uint32_t (&r)[32], uint32_t (&)[32], auto ic) {
-                                        constexpr int c = decltype(ic)::value;
-                                        gm[j * 4 + c] = fminf(gm[j * 4 + c], tc_min32(r));
-                                    });
-                        ++t;
-                    }
-                }
-            }
+            for (int g = 0; g < TC_GROUPS; ++g) gm[g] = gcol[g * LD];
             sort_regs<TC_GROUPS>(gm);
             thr = gm[KC - 1];
         }
@@ -428,31 +499,31 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         // ---- main pass ----
         for (int tile = 0; tile < n_rtiles; ++tile, ++t) {
             const int idb = tile * TC_N;
-            tc_epi_tile(A, B, tbase, t, n_seq, tfull, tempty, lane,
-                        [&](const uint32_t (&r)[32], uint32_t (&inflight)[32], auto ic) {
-                            constexpr int c = decltype(ic)::value;
-                            tc_process<KC>(r, inflight, idb + c * 32, buf_s, buf_i, scratch, tid, lane,
-                                           thr, cnt);
-                        });
+            tc_epi_job<MT>(A, B, tlane, t * MT + h, t + 1 < n_seq, afull, aempty, lane,
+                           [&](const uint32_t (&r)[32], uint32_t (&inflight)[32], auto ic) {
+                               constexpr int c = decltype(ic)::value;
+                               tc_process<KC, CAP, LD>(r, inflight, idb + c * 32, buf_s, buf_i, scratch,
+                                                       tid, lane, thr, cnt, dbg);
+                           });
         }
 
         // ---- final compaction, then every thread writes its own candidates ----
         {
-            const ThrCnt tc = tc_compact_all<KC>(buf_s + tid, buf_i + tid, thr, cnt);
+            const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + tid, buf_i + tid, thr, cnt);
             thr = tc.thr;
             cnt = tc.cnt;
         }
-        const long long q = qtile * TC_QT + tid;
+        const long long q = qtile * Cfg::QT + tid;
         if (q < n_q) {
             int4 *dst = reinterpret_cast<int4 *>(cand_idx + q * KC);
 #pragma unroll
-            for (int j = 0; j < KC; j += 4) {
+            for (int jj = 0; jj < KC; jj += 4) {
                 int4 v;
-                v.x = (j + 0 < cnt) ? buf_i[(j + 0) * TC_LD + tid] : -1;
-                v.y = (j + 1 < cnt) ? buf_i[(j + 1) * TC_LD + tid] : -1;
-                v.z = (j + 2 < cnt) ? buf_i[(j + 2) * TC_LD + tid] : -1;
-                v.w = (j + 3 < cnt) ? buf_i[(j + 3) * TC_LD + tid] : -1;
-                dst[j / 4] = v;
+                v.x = (jj + 0 < cnt) ? buf_i[(jj + 0) * LD + tid] : -1;
+                v.y = (jj + 1 < cnt) ? buf_i[(jj + 1) * LD + tid] : -1;
+                v.z = (jj + 2 < cnt) ? buf_i[(jj + 2) * LD + tid] : -1;
+                v.w = (jj + 3 < cnt) ? buf_i[(jj + 3) * LD + tid] : -1;
+                dst[jj / 4] = v;
             }
             cand_thr[q] = thr;  // +inf only when the list holds every reference
         }
@@ -461,20 +532,33 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == TC_EPI_WARPS) tmem_dealloc(tmem_base, 512);
+    if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
-size_t search_tc_smem_bytes(int kc_tot, int nstage) {
+static int tc_cap_for(int mt) { return mt == 4 ? 24 : 32; }
+
+int g_tc_debug = 0;  // timing experiments only (set through the "tc_debug" option)
+
+size_t search_tc_smem_bytes(int kc_tot, int nstage, int mt) {
     const size_t a = (size_t)kc_tot * TC_M * TC_ROWB, b = (size_t)kc_tot * TC_N * TC_ROWB;
-    return TC_MT * a + nstage * b + 2 * (size_t)TC_CAP * TC_LD * 4 + (size_t)TC_EPI_WARPS * 32 * 4 +
-           (size_t)(2 * nstage + 5) * 8 + 16;
+    const size_t ld = (size_t)mt * TC_M + 1;
+    return mt * a + nstage * b + (size_t)mt * 4 * 32 * 4 + 2 * (size_t)tc_cap_for(mt) * ld * 4 +
+           (size_t)(2 * nstage + 2 * TC_SLOTS + 1) * 8 + 16;
 }
 
-// ring stages that fit the 227 KB of shared memory (0 = the shape does not fit the engine)
-int search_tc_pick_stages(int kc_tot) {
-    for (int s = 4; s >= 2; --s)
-        if (search_tc_smem_bytes(kc_tot, s) <= 227 * 1024) return s;
-    return 0;
+// (M tiles per CTA, ring stages) for this contraction depth; want_mt = 0 picks the largest CTA
+// tile that keeps at least two ring stages.  mt = 0: the shape does not fit the engine.
+void search_tc_pick_shape(int kc_tot, int want_mt, int *mt, int *nstage) {
+    for (int m = (want_mt ? want_mt : 4); m >= 2; --m) {
+        for (int s = 4; s >= 2; --s)
+            if (search_tc_smem_bytes(kc_tot, s, m) <= 227 * 1024) {
+                *mt = m;
+                *nstage = s;
+                return;
+            }
+    }
+    *mt = 0;
+    *nstage = 0;
 }
 
 // sampled tiles of the seeding pass (0 = no seeding: too few references for it to pay)
@@ -483,27 +567,37 @@ int search_tc_seed_tiles(int n_rtiles, int seed_stride) {
     return (n_rtiles + seed_stride - 1) / seed_stride;
 }
 
-template <int KC>
+template <int KC, int MT, int CAP>
 static cudaError_t launch_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles, int nstage,
                              int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
                              cudaStream_t st) {
-    const size_t smem = search_tc_smem_bytes(kc_tot, nstage);
-    cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+    using Cfg = TcCfg<MT, CAP>;
+    const size_t smem = search_tc_smem_bytes(kc_tot, nstage, MT);
+    cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC, MT, CAP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    const long long n_qtiles = (n_q + TC_QT - 1) / TC_QT;
+    const long long n_qtiles = (n_q + Cfg::QT - 1) / Cfg::QT;
     const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride);
-    search_tc_kernel<KC><<<(unsigned)n_qtiles, TC_THREADS, smem, st>>>(
-        qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, seed_stride, n_q, cand_idx, cand_thr);
+    search_tc_kernel<KC, MT, CAP><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
+        qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, seed_stride, n_q, cand_idx, cand_thr, g_tc_debug);
     return cudaGetLastError();
 }
 
 cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int kc, int nstage, int seed_stride, int *cand_idx,
+                             long long n_q, int kc, int mt, int nstage, int seed_stride, int *cand_idx,
                              float *cand_thr, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
-    if (kc == 8) return launch_tc<8>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx, cand_thr, st);
-    if (kc == 16) return launch_tc<16>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx, cand_thr, st);
+#define SK_TC_CASE(KC_, MT_, CAP_)                                                              \
+    if (kc == KC_ && mt == MT_)                                                                 \
+        return launch_tc<KC_, MT_, CAP_>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, \
+                                         cand_idx, cand_thr, st);
+    SK_TC_CASE(8, 2, 32)
+    SK_TC_CASE(8, 3, 32)
+    SK_TC_CASE(8, 4, 24)
+    SK_TC_CASE(16, 2, 32)
+    SK_TC_CASE(16, 3, 32)
+    SK_TC_CASE(16, 4, 24)
+#undef SK_TC_CASE
     return cudaErrorInvalidValue;
 }
 
