@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--kc", type=int, default=0)
     ap.add_argument("--tc-seed-stride", type=int, default=-1)
-    ap.add_argument("--tc-mt", type=int, default=0)
+    ap.add_argument("--tc-streams", type=int, default=0)
     ap.add_argument("--tc-debug", type=int, default=0)
     return ap.parse_args()
 
@@ -209,8 +209,8 @@ def run_ours(a, rank, world, local_rank):
         L.set_option("engine", a.engine)
     if a.kc:
         L.set_option("kc", a.kc)
-    if a.tc_mt:
-        L.set_option("tc_mt", a.tc_mt)
+    if a.tc_streams:
+        L.set_option("tc_streams", a.tc_streams)
     if a.tc_debug:
         L.set_option("tc_debug", a.tc_debug)
     if a.tc_seed_stride >= 0:

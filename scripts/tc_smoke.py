@@ -27,11 +27,11 @@ if __name__ == "__main__":
                  (50000, 3000, 32, 7), (9000, 2000, 24, 15)]:
         for engine in (2, 1):
             run(*args, engine)
-    for mt in (2, 3, 4):
-        L.set_option("tc_mt", mt)
+    for ns in (1, 2):
+        L.set_option("tc_streams", ns)
         for args in [(300, 200, 8, 3), (5000, 3000, 32, 7), (50000, 3000, 32, 7), (20000, 1500, 24, 7), (9000, 2000, 24, 15)]:
             run(*args, 2)
-    L.set_option("tc_mt", 0)
+    L.set_option("tc_streams", 0)
     for stride in (0, 2, 8):
         L.set_option("tc_seed_stride", stride)
         run(50000, 3000, 32, 7, 2)

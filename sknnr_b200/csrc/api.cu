@@ -41,7 +41,7 @@ struct Options {
     int64_t chunk_rows = 1 << 20;
     int64_t timing = 0;
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
-    int64_t tc_mt = 0;          // tensor engine: M tiles per CTA (0 = automatic, else 2..4)
+    int64_t tc_streams = 0;     // tensor engine: candidate streams per query (0 = automatic, else 1 or 2)
     int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = off)
 } g_opt;
 
@@ -219,7 +219,7 @@ struct sknnr_index : IndexBase {
     int n_rtiles = 0;
     double r2max = 0.0;
     float *d_rimg_tc = nullptr;    // tensor-core engine reference image
-    int n_rtiles_tc = 0, kc_tot = 0, tc_mt = 0, tc_nstage = 0;
+    int n_rtiles_tc = 0, kc_tot = 0, tc_nstage = 0;
     bool tensor_ok = false;        // shape fits the tensor engine
     bool tensor_demoted = false;   // too many uncertified rows: fall back to the SIMT engine
 };
@@ -262,9 +262,9 @@ int sknnr_set_option(const char *name, int64_t value) {
         g_opt.kc = value;
     } else if (!strcmp(name, "tc_debug")) {
         g_tc_debug = (int)value;
-    } else if (!strcmp(name, "tc_mt")) {
-        if (value != 0 && (value < 2 || value > 4)) return fail(SKNNR_EINVAL, "tc_mt must be 0 or 2..4");
-        g_opt.tc_mt = value;
+    } else if (!strcmp(name, "tc_streams")) {
+        if (value < 0 || value > 2) return fail(SKNNR_EINVAL, "tc_streams must be 0, 1 or 2");
+        g_opt.tc_streams = value;
     } else if (!strcmp(name, "tc_seed_stride")) {
         if (value < 0 || value > 64) return fail(SKNNR_EINVAL, "tc_seed_stride must be 0..64");
         g_opt.tc_seed_stride = value;
@@ -357,8 +357,8 @@ int sknnr_index_create(const double *fit_z, int64_t n_ref, int32_t d_out, const 
     // (+inf for padding plots) and whose second chunk is zero
     ix->kc_tot = ix->dpad / 4 + 2;
     ix->n_rtiles_tc = (int)((n_ref + TC_N - 1) / TC_N);
-    search_tc_pick_shape(ix->kc_tot, (int)g_opt.tc_mt, &ix->tc_mt, &ix->tc_nstage);
-    ix->tensor_ok = ix->tc_mt != 0;
+    ix->tc_nstage = search_tc_pick_stages(ix->kc_tot);
+    ix->tensor_ok = ix->tc_nstage != 0;
     if (e == cudaSuccess && ix->tensor_ok) {
         auto tf32 = [](float x) -> float {
             uint32_t b;
@@ -496,8 +496,8 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
         return SKNNR_OK;
     }
 
-    CK(s.cand_idx.reserve((size_t)rows * kc));
-    CK(s.cand_thr.reserve((size_t)rows));
+    CK(s.cand_idx.reserve((size_t)rows * std::max(kc, 16)));
+    CK(s.cand_thr.reserve((size_t)rows * 2));
     CK(s.fb.reserve((size_t)rows + 1));
     CK(s.fb2.reserve((size_t)rows + 1));
     CK(cudaMemsetAsync(s.fb.p, 0, sizeof(int), st));
@@ -521,9 +521,14 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     const int *stage2_count = nullptr;  // null: stage 2 covers every row of the chunk
     if (use_tc) {
         if (g_opt.timing) CK(s.mark(st));
-        CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, kc, ix->tc_mt, ix->tc_nstage,
+        // two candidate streams of 8 per query while k (+1) <= 8 (twice the scanner warps), else one of 16
+        int ns = kk <= 8 ? 2 : 1;
+        if (g_opt.tc_streams == 1) ns = 1;
+        CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, ns, ix->tc_nstage,
                             (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, st));
         if (g_opt.timing) CK(s.mark(st));
+        ra.kc = 16;
+        ra.n_thr = ns;
         ra.z64 = s.z64.p;
         ra.n_q = rows;
         ra.eps_s = eps_tc;
@@ -548,6 +553,8 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     if (g_opt.timing && !use_tc) CK(s.mark(st));
     FinishParams fp2 = fp;
     fp2.row_map = use_tc ? s.fb.p + 1 : nullptr;
+    ra.kc = kc;
+    ra.n_thr = 1;
     ra.z64 = use_tc ? s.z64c.p : s.z64.p;
     ra.n_q = rows;
     ra.eps_s = eps_simt;

@@ -34,14 +34,16 @@ cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, i
                                const int *n_rows_dev, cudaStream_t st);
 
 // ---- search_tc.cu (tcgen05 / TMEM engine) ------------------------------------------------
-size_t search_tc_smem_bytes(int kc_tot, int nstage, int mt);
-// (M tiles per CTA, ring stages); want_mt = 0: automatic; *mt = 0: the shape does not fit
-void search_tc_pick_shape(int kc_tot, int want_mt, int *mt, int *nstage);
-int search_tc_seed_tiles(int n_rtiles, int seed_stride);
+// Two candidate-stream layouts: ns = 2 (two lists of 8 per query, k (+1) <= 8) and ns = 1 (one
+// list of 16).  cand_idx is [n_q][16], cand_thr [n_q][ns]; every reference outside a query's
+// lists has an approximate score >= the minimum of its ns thresholds.
+size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns);
+int search_tc_pick_stages(int kc_tot);   // 0: the shape does not fit the engine
+int search_tc_seed_tiles(int n_rtiles, int seed_stride, int ns);
 extern int g_tc_debug;  // timing experiments: bit 0 = skip the hit path (wrong results)
-// seed_stride: every seed_stride-th reference tile is pre-scanned to seed the thresholds (0 = off)
+// seed_stride: one reference tile in seed_stride is pre-scanned to seed the thresholds (0 = off)
 cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int kc, int mt, int nstage, int seed_stride, int *cand_idx,
+                             long long n_q, int ns, int nstage, int seed_stride, int *cand_idx,
                              float *cand_thr, cudaStream_t st);
 
 // ---- refine.cu -------------------------------------------------------------------------
@@ -50,7 +52,8 @@ struct RefineArgs {
     const double *ref64;    // [n_ref, d]
     const double *mu;       // [d] centroid used by the search images
     const int *cand_idx;    // [n_q, kc]
-    const float *cand_thr;  // [n_q]
+    const float *cand_thr;  // [n_q, n_thr]: a query's filter threshold is the minimum of its n_thr entries
+    int n_thr;
     int kc;
     int d;
     long long n_q;

@@ -54,7 +54,8 @@ refine_kernel(RefineArgs a, FinishParams fp) {
 
     const int kk = fp.k + (fp.exclude_self ? 1 : 0);
     const double kth = __shfl_sync(SK_FULL, d2, kk - 1);
-    const float thr = a.cand_thr[q];
+    float thr = a.cand_thr[q * a.n_thr];
+    for (int i = 1; i < a.n_thr; ++i) thr = fminf(thr, a.cand_thr[q * a.n_thr + i]);
     // every reference outside the list has approximate score >= thr, hence true squared
     // distance >= thr + |q|^2 - E with E = eps_s * (|q|^2 + max|r|^2)
     bool ok;

@@ -58,15 +58,18 @@ namespace sk {
 
 constexpr int TC_SLOTS = 4;                     // TMEM accumulator slots of TC_N columns
 constexpr int TC_GROUPS = 32;                   // seeding: group minima per query
-constexpr int TC_SORT = 32;                     // width of the register sorting network (>= CAP)
-template <int MT_, int CAP_> struct TcCfg {
-    static constexpr int MT = MT_;                    // M tiles (of 128 queries) per CTA
-    static constexpr int CAP = CAP_;                  // candidate buffer slots per query
-    static constexpr int QT = MT * TC_M;              // queries per CTA
-    static constexpr int EPI_WARPS = MT * 4;
+// MT M tiles (of 128 queries) per CTA; NS independent candidate streams per query (stream p sees
+// the reference tiles at positions p, p + NS, ... of the tile sequence and has its own scanner
+// warps, buffer and threshold); KCS candidates kept per stream, CAP buffer slots per stream.
+template <int MT_, int NS_, int CAP_> struct TcCfg {
+    static constexpr int MT = MT_, NS = NS_, CAP = CAP_;
+    static constexpr int QT = MT * TC_M;                  // queries per CTA
+    static constexpr int EPI_WARPS = MT * 4 * NS;         // scanner warps: (stream, M tile, lane quarter)
     static constexpr int THREADS = (EPI_WARPS + 2) * 32;  // + MMA issuer warp + TMA producer warp
-    static constexpr int LD = QT + 1;                 // slot stride (odd: a query's slots hit 32 banks)
-    static_assert(CAP <= TC_SORT && CAP % 2 == 0, "candidate buffer shape");
+    static constexpr int LD = QT * NS + 1;                // slot stride (odd: a column's slots hit 32 banks)
+    static constexpr int SORT = CAP <= 16 ? 16 : 32;      // width of the register sorting network
+    static_assert(CAP <= SORT && CAP % 2 == 0, "candidate buffer shape");
+    static_assert(TC_SLOTS % MT == 0 || NS == 1, "a stream's jobs must map to fixed accumulator slots");
 };
 constexpr uint32_t TC_ROWB = 16;                // bytes of one row of one K chunk (4 TF32)
 static_assert(TC_N == 128, "epilogue assumes four 32-column chunks per tile");
@@ -212,11 +215,12 @@ struct ThrCnt {
 template <int KC, int CAP, int LD>
 __device__ __noinline__ ThrCnt tc_compact_all(float *col_s, int *col_i, float thr, int cnt) {
     static_assert(KC < CAP, "the buffer needs slack above KC");
+    constexpr int SORT = CAP <= 16 ? 16 : 32;
     __syncwarp();
-    float s[TC_SORT];
+    float s[SORT];
 #pragma unroll
-    for (int j = 0; j < TC_SORT; ++j) s[j] = (j < CAP && j < cnt) ? col_s[j * LD] : SK_INF_F;
-    sort_regs<TC_SORT>(s);
+    for (int j = 0; j < SORT; ++j) s[j] = (j < CAP && j < cnt) ? col_s[j * LD] : SK_INF_F;
+    sort_regs<SORT>(s);
     const float t = s[KC - 1];  // +inf while the buffer holds fewer than KC entries
     int n_less = 0;
 #pragma unroll
@@ -307,8 +311,8 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], uint32_t (&i
 
 // Epilogue of one job (reference tile x this warp's M tile): 4 chunks of 32 columns through the
 // alternating register buffers A / B.  On entry the load of chunk 0 into A has been issued; on
-// exit the load of chunk 0 of this warp's next job (j + MT) into A has been issued, if any.
-template <int MT, class F>
+// exit the load of chunk 0 of this warp's next job (j + STEP) into A has been issued, if any.
+template <int STEP, class F>
 __device__ __forceinline__ void tc_epi_job(uint32_t (&A)[32], uint32_t (&B)[32], uint32_t tlane, int j,
                                            bool has_next, uint64_t *afull, uint64_t *aempty, int lane,
                                            F &&proc) {
@@ -329,7 +333,7 @@ __device__ __forceinline__ void tc_epi_job(uint32_t (&A)[32], uint32_t (&B)[32],
     __syncwarp();
     if (lane == 0) mbar_arrive(&aempty[sl]);
     if (has_next) {
-        const int jn = j + MT, sn = jn & (TC_SLOTS - 1);
+        const int jn = j + STEP, sn = jn & (TC_SLOTS - 1);
         mbar_wait(&afull[sn], (jn >> 2) & 1);
         tc_fence_after();
         tmem_ld32_issue(tlane + (uint32_t)(sn * TC_N), A, B[0]);
@@ -337,12 +341,12 @@ __device__ __forceinline__ void tc_epi_job(uint32_t (&A)[32], uint32_t (&B)[32],
     proc(B, A, std::integral_constant<int, 3>{});
 }
 
-template <int KC, int MT, int CAP>
-__global__ void __launch_bounds__(TcCfg<MT, CAP>::THREADS, 1)
+template <int KC, int MT, int NS, int CAP>
+__global__ void __launch_bounds__(TcCfg<MT, NS, CAP>::THREADS, 1)
 search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int kc_tot,
                  int n_rtiles, int nstage, int n_seed, int seed_stride, long long n_q,
                  int *__restrict__ cand_idx, float *__restrict__ cand_thr, int dbg) {
-    using Cfg = TcCfg<MT, CAP>;
+    using Cfg = TcCfg<MT, NS, CAP>;
     constexpr int LD = Cfg::LD, EPI_WARPS = Cfg::EPI_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t a_bytes = (uint32_t)kc_tot * TC_M * TC_ROWB;  // one 128-query operand image
@@ -394,7 +398,9 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             const unsigned char *rbase = (const unsigned char *)rimg;
             for (int tn = 0; tn < n_seq; ++tn) {
                 if (wrapped) mbar_wait(&empty[sn], wrap_par);
-                const int tile = tn < n_seed ? tn * seed_stride : tn - n_seed;
+                // sampled tiles: NS consecutive tiles out of every NS * seed_stride, so that sequence
+                // position and tile number agree modulo NS (n_seed is a multiple of NS)
+                const int tile = tn < n_seed ? (tn / NS) * (NS * seed_stride) + (tn % NS) : tn - n_seed;
                 mbar_expect_tx(&full[sn], b_bytes);
                 bulk_g2s(Rs + (size_t)sn * b_bytes, rbase + (size_t)tile * b_bytes, b_bytes, &full[sn]);
                 if (++sn == nstage) {
@@ -458,36 +464,43 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             }
         }
     } else {
-        // ======================= epilogue: thread <-> query =======================
-        const int tid = threadIdx.x;          // query slot; TMEM lane (tid & 127) of M tile (tid >> 7)
-        const int h = warp >> 2;
+        // ======================= epilogue: thread <-> (query, stream) =======================
+        // warp = (stream p, M tile h, lane quarter); stream p handles positions p, p + NS, ... of
+        // the tile sequence, i.e. jobs (p + NS * i) * MT + h
+        const int col = threadIdx.x;          // candidate buffer column of this (query, stream)
+        const int p = warp / (MT * 4);
+        const int h = (warp >> 2) % MT;
+        const int qslot = h * TC_M + (warp & 3) * 32 + lane;   // query within the CTA = TMEM lane of M tile h
         const uint32_t tlane = tmem_base + (((uint32_t)((warp & 3) * 32)) << 16);
         float *scratch = scratch_all + warp * 32;
         float thr = SK_INF_F;
         int cnt = 0;
         uint32_t A[32], B[32];
-        int t = 0;                            // position in the tile sequence; this warp's job = t * MT + h
-        mbar_wait(&afull[h], 0);              // job h uses slot h (MT <= 4), first completion
-        tc_fence_after();
-        uint32_t dep0 = 0;
-        tmem_ld32_issue(tlane + (uint32_t)(h * TC_N), A, dep0);
+        int t = p;                            // position in the tile sequence; this warp's job = t * MT + h
+        if (t < n_seq) {
+            const int j0 = t * MT + h;
+            mbar_wait(&afull[j0 & (TC_SLOTS - 1)], (j0 >> 2) & 1);
+            tc_fence_after();
+            uint32_t dep0 = 0;
+            tmem_ld32_issue(tlane + (uint32_t)((j0 & (TC_SLOTS - 1)) * TC_N), A, dep0);
+        }
 
-        // ---- seeding pass: group minima over the sampled tiles ----
-        // (the 32 running minima of a query live in the still unused candidate buffer: slots of
-        // buf_s, then of buf_i; chunk c of the n-th sampled tile feeds group (4n + c) % 32)
+        // ---- seeding pass: group minima over the sampled tiles of this stream ----
+        // (the 32 running minima live in the still unused candidate buffer column: slots of
+        // buf_s, then of buf_i; chunk c of the stream's n-th sampled tile feeds group (4n + c) % 32)
         if (n_seed > 0) {
             static_assert(2 * CAP >= TC_GROUPS, "group minima are parked in the candidate buffers");
-            float *gcol = buf_s + tid;
+            float *gcol = buf_s + col;
 #pragma unroll
             for (int g = 0; g < TC_GROUPS; ++g) gcol[g * LD] = SK_INF_F;   // buf_i follows buf_s
-            for (; t < n_seed; ++t) {
-                const int g0 = (t * 4) & (TC_GROUPS - 1);
-                tc_epi_job<MT>(A, B, tlane, t * MT + h, t + 1 < n_seq, afull, aempty, lane,
-                               [&](const uint32_t (&r)[32], uint32_t (&)[32], auto ic) {
-                                   constexpr int c = decltype(ic)::value;
-                                   float *p = gcol + (g0 + c) * LD;
-                                   *p = fminf(*p, tc_min32(r));
-                               });
+            for (; t < n_seed; t += NS) {
+                const int g0 = ((t / NS) * 4) & (TC_GROUPS - 1);
+                tc_epi_job<NS * MT>(A, B, tlane, t * MT + h, t + NS < n_seq, afull, aempty, lane,
+                                    [&](const uint32_t (&r)[32], uint32_t (&)[32], auto ic) {
+                                        constexpr int c = decltype(ic)::value;
+                                        float *g = gcol + (g0 + c) * LD;
+                                        *g = fminf(*g, tc_min32(r));
+                                    });
             }
             float gm[TC_GROUPS];
 #pragma unroll
@@ -496,36 +509,36 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             thr = gm[KC - 1];
         }
 
-        // ---- main pass ----
-        for (int tile = 0; tile < n_rtiles; ++tile, ++t) {
-            const int idb = tile * TC_N;
-            tc_epi_job<MT>(A, B, tlane, t * MT + h, t + 1 < n_seq, afull, aempty, lane,
-                           [&](const uint32_t (&r)[32], uint32_t (&inflight)[32], auto ic) {
-                               constexpr int c = decltype(ic)::value;
-                               tc_process<KC, CAP, LD>(r, inflight, idb + c * 32, buf_s, buf_i, scratch,
-                                                       tid, lane, thr, cnt, dbg);
-                           });
+        // ---- main pass over the stream's tiles ----
+        for (; t < n_seq; t += NS) {
+            const int idb = (t - n_seed) * TC_N;
+            tc_epi_job<NS * MT>(A, B, tlane, t * MT + h, t + NS < n_seq, afull, aempty, lane,
+                                [&](const uint32_t (&r)[32], uint32_t (&inflight)[32], auto ic) {
+                                    constexpr int c = decltype(ic)::value;
+                                    tc_process<KC, CAP, LD>(r, inflight, idb + c * 32, buf_s, buf_i, scratch,
+                                                            col, lane, thr, cnt, dbg);
+                                });
         }
 
-        // ---- final compaction, then every thread writes its own candidates ----
+        // ---- final compaction, then every thread writes the candidates of its (query, stream) ----
         {
-            const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + tid, buf_i + tid, thr, cnt);
+            const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + col, buf_i + col, thr, cnt);
             thr = tc.thr;
             cnt = tc.cnt;
         }
-        const long long q = qtile * Cfg::QT + tid;
+        const long long q = qtile * Cfg::QT + qslot;
         if (q < n_q) {
-            int4 *dst = reinterpret_cast<int4 *>(cand_idx + q * KC);
+            int4 *dst = reinterpret_cast<int4 *>(cand_idx + (q * NS + p) * KC);
 #pragma unroll
             for (int jj = 0; jj < KC; jj += 4) {
                 int4 v;
-                v.x = (jj + 0 < cnt) ? buf_i[(jj + 0) * LD + tid] : -1;
-                v.y = (jj + 1 < cnt) ? buf_i[(jj + 1) * LD + tid] : -1;
-                v.z = (jj + 2 < cnt) ? buf_i[(jj + 2) * LD + tid] : -1;
-                v.w = (jj + 3 < cnt) ? buf_i[(jj + 3) * LD + tid] : -1;
+                v.x = (jj + 0 < cnt) ? buf_i[(jj + 0) * LD + col] : -1;
+                v.y = (jj + 1 < cnt) ? buf_i[(jj + 1) * LD + col] : -1;
+                v.z = (jj + 2 < cnt) ? buf_i[(jj + 2) * LD + col] : -1;
+                v.w = (jj + 3 < cnt) ? buf_i[(jj + 3) * LD + col] : -1;
                 dst[jj / 4] = v;
             }
-            cand_thr[q] = thr;  // +inf only when the list holds every reference
+            cand_thr[q * NS + p] = thr;  // +inf only when the list holds every reference of the stream
         }
     }
 
@@ -535,69 +548,62 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
-static int tc_cap_for(int mt) { return mt == 4 ? 24 : 32; }
-
 int g_tc_debug = 0;  // timing experiments only (set through the "tc_debug" option)
 
-size_t search_tc_smem_bytes(int kc_tot, int nstage, int mt) {
+// Two configurations:
+//   ns = 2: two streams of KCS = 8 candidates (CAP 16) per query, 16 scanner warps -- k (+1) <= 8
+//   ns = 1: one stream of 16 candidates (CAP 32), 8 scanner warps              -- k (+1) <= 14
+static constexpr int TC_MT = 2;
+
+size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns) {
     const size_t a = (size_t)kc_tot * TC_M * TC_ROWB, b = (size_t)kc_tot * TC_N * TC_ROWB;
-    const size_t ld = (size_t)mt * TC_M + 1;
-    return mt * a + nstage * b + (size_t)mt * 4 * 32 * 4 + 2 * (size_t)tc_cap_for(mt) * ld * 4 +
+    const size_t ld = (size_t)TC_MT * TC_M * ns + 1, cap = ns == 2 ? 16 : 32;
+    return TC_MT * a + nstage * b + (size_t)TC_MT * 4 * ns * 32 * 4 + 2 * cap * ld * 4 +
            (size_t)(2 * nstage + 2 * TC_SLOTS + 1) * 8 + 16;
 }
 
-// (M tiles per CTA, ring stages) for this contraction depth; want_mt = 0 picks the largest CTA
-// tile that keeps at least two ring stages.  mt = 0: the shape does not fit the engine.
-void search_tc_pick_shape(int kc_tot, int want_mt, int *mt, int *nstage) {
-    for (int m = (want_mt ? want_mt : 4); m >= 2; --m) {
-        for (int s = 4; s >= 2; --s)
-            if (search_tc_smem_bytes(kc_tot, s, m) <= 227 * 1024) {
-                *mt = m;
-                *nstage = s;
-                return;
-            }
-    }
-    *mt = 0;
-    *nstage = 0;
+// ring stages for this contraction depth (0: the shape does not fit the engine)
+int search_tc_pick_stages(int kc_tot) {
+    for (int s = 4; s >= 2; --s)
+        if (search_tc_smem_bytes(kc_tot, s, 2) <= 227 * 1024 && search_tc_smem_bytes(kc_tot, s, 1) <= 227 * 1024)
+            return s;
+    return 0;
 }
 
-// sampled tiles of the seeding pass (0 = no seeding: too few references for it to pay)
-int search_tc_seed_tiles(int n_rtiles, int seed_stride) {
+// sampled tiles of the seeding pass (0 = no seeding: too few references for it to pay); a
+// multiple of ns: ns consecutive tiles out of every ns * seed_stride
+int search_tc_seed_tiles(int n_rtiles, int seed_stride, int ns) {
     if (seed_stride <= 0 || n_rtiles < 64) return 0;
-    return (n_rtiles + seed_stride - 1) / seed_stride;
+    return n_rtiles / (ns * seed_stride) * ns;
 }
 
-template <int KC, int MT, int CAP>
+template <int KC, int MT, int NS, int CAP>
 static cudaError_t launch_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles, int nstage,
                              int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
                              cudaStream_t st) {
-    using Cfg = TcCfg<MT, CAP>;
-    const size_t smem = search_tc_smem_bytes(kc_tot, nstage, MT);
-    cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC, MT, CAP>,
+    using Cfg = TcCfg<MT, NS, CAP>;
+    const size_t smem = search_tc_smem_bytes(kc_tot, nstage, NS);
+    cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC, MT, NS, CAP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const long long n_qtiles = (n_q + Cfg::QT - 1) / Cfg::QT;
-    const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride);
-    search_tc_kernel<KC, MT, CAP><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
+    const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride, NS);
+    search_tc_kernel<KC, MT, NS, CAP><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
         qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, seed_stride, n_q, cand_idx, cand_thr, g_tc_debug);
     return cudaGetLastError();
 }
 
+// cand_idx [n_q][16] (ns lists of 16 / ns entries), cand_thr [n_q][ns]
 cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int kc, int mt, int nstage, int seed_stride, int *cand_idx,
+                             long long n_q, int ns, int nstage, int seed_stride, int *cand_idx,
                              float *cand_thr, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
-#define SK_TC_CASE(KC_, MT_, CAP_)                                                              \
-    if (kc == KC_ && mt == MT_)                                                                 \
-        return launch_tc<KC_, MT_, CAP_>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, \
-                                         cand_idx, cand_thr, st);
-    SK_TC_CASE(8, 2, 32)
-    SK_TC_CASE(8, 3, 32)
-    SK_TC_CASE(8, 4, 24)
-    SK_TC_CASE(16, 2, 32)
-    SK_TC_CASE(16, 3, 32)
-    SK_TC_CASE(16, 4, 24)
-#undef SK_TC_CASE
+    if (ns == 2)
+        return launch_tc<8, TC_MT, 2, 16>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx,
+                                          cand_thr, st);
+    if (ns == 1)
+        return launch_tc<16, TC_MT, 1, 32>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx,
+                                           cand_thr, st);
     return cudaErrorInvalidValue;
 }
 
