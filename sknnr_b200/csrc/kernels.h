@@ -39,7 +39,7 @@ cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, i
 // lists has an approximate score >= the minimum of its ns thresholds.
 size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns);
 int search_tc_pick_stages(int kc_tot);   // 0: the shape does not fit the engine
-int search_tc_seed_tiles(int n_rtiles, int seed_stride, int ns);
+int search_tc_seed_tiles(int n_rtiles, int seed_stride);
 extern int g_tc_debug;  // timing experiments: bit 0 = skip the hit path (wrong results)
 // seed_stride: one reference tile in seed_stride is pre-scanned to seed the thresholds (0 = off)
 cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,

@@ -58,9 +58,9 @@ namespace sk {
 
 constexpr int TC_SLOTS = 4;                     // TMEM accumulator slots of TC_N columns
 constexpr int TC_GROUPS = 32;                   // seeding: group minima per query
-// MT M tiles (of 128 queries) per CTA; NS independent candidate streams per query (stream p sees
-// the reference tiles at positions p, p + NS, ... of the tile sequence and has its own scanner
-// warps, buffer and threshold); KCS candidates kept per stream, CAP buffer slots per stream.
+// MT M tiles (of 128 queries) per CTA; NS independent candidate streams per query: stream p owns
+// columns [p * 128 / NS, (p + 1) * 128 / NS) of every reference tile and has its own scanner
+// warps, candidate buffer and threshold; KCS candidates kept per stream, CAP buffer slots.
 template <int MT_, int NS_, int CAP_> struct TcCfg {
     static constexpr int MT = MT_, NS = NS_, CAP = CAP_;
     static constexpr int QT = MT * TC_M;                  // queries per CTA
@@ -69,7 +69,7 @@ template <int MT_, int NS_, int CAP_> struct TcCfg {
     static constexpr int LD = QT * NS + 1;                // slot stride (odd: a column's slots hit 32 banks)
     static constexpr int SORT = CAP <= 16 ? 16 : 32;      // width of the register sorting network
     static_assert(CAP <= SORT && CAP % 2 == 0, "candidate buffer shape");
-    static_assert(TC_SLOTS % MT == 0 || NS == 1, "a stream's jobs must map to fixed accumulator slots");
+    static constexpr int CH = 4 / NS;                     // 32-column chunks a scanner warp reads per job
 };
 constexpr uint32_t TC_ROWB = 16;                // bytes of one row of one K chunk (4 TF32)
 static_assert(TC_N == 128, "epilogue assumes four 32-column chunks per tile");
@@ -248,99 +248,159 @@ __device__ __noinline__ ThrCnt tc_compact_all(float *col_s, int *col_i, float th
     return out;
 }
 
-// One 32-column chunk of the main pass.  `r` holds this thread's scores against references
-// idb .. idb+31; `inflight` is the other register buffer, whose tcgen05.ld may still be in
-// flight (it must land before a function call may spill it).
+// Cooperative (slow, always safe) hit path for ONE lane L whose 32 scores (references idb ..
+// idb+31) have been published to the warp's scratch line: the warp re-tests them one score per
+// lane and appends the survivors to lane L's candidate buffer, compacting the warp's buffers
+// whenever it would overflow.  Used when the in-lane path below ran out of buffer slots.
 template <int KC, int CAP, int LD>
-__device__ __forceinline__ void tc_process(const uint32_t (&r)[32], uint32_t (&inflight)[32], int idb,
-                                           float *buf_s, int *buf_i, float *scratch, int tid,
-                                           int lane, float &thr, int &cnt, int dbg) {
-    const float m = tc_min32(r);
-    unsigned hits = __ballot_sync(SK_FULL, m < thr);
+__device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, float *buf_s, int *buf_i, const float *scratch,
+                                               int col, int lane, float thr, int cnt) {
+    const float x = scratch[lane];                 // score of lane L's query vs reference idb+lane
+    float thrL = __shfl_sync(SK_FULL, thr, L);
+    int cntL = __shfl_sync(SK_FULL, cnt, L);
+    unsigned pending = __ballot_sync(SK_FULL, x < thrL);
+    float *cs = buf_s + (col - lane + L);
+    int *ci = buf_i + (col - lane + L);
+    while (pending) {
+        unsigned take = pending;
+        if (cntL + __popc(pending) > CAP) {
+            if (cntL > KC) {
+                if (lane == L) cnt = cntL;  // entries appended earlier in this loop
+                const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + col, buf_i + col, thr, cnt);
+                thr = tc.thr;
+                cnt = tc.cnt;
+                thrL = __shfl_sync(SK_FULL, thr, L);
+                cntL = __shfl_sync(SK_FULL, cnt, L);
+                pending &= __ballot_sync(SK_FULL, x < thrL);
+                continue;
+            }
+            // at most KC entries held but more hits than free slots: lowest hits first
+            const int room = CAP - cntL;
+            while (__popc(take) > room) take &= ~(0x80000000u >> __clz(take));
+        }
+        if ((take >> lane) & 1u) {
+            const int slot = cntL + __popc(take & ((1u << lane) - 1u));
+            cs[slot * LD] = x;
+            ci[slot * LD] = idb + lane;
+        }
+        cntL += __popc(take);
+        pending &= ~take;
+    }
+    if (lane == L) cnt = cntL;
+    ThrCnt out;
+    out.thr = thr;
+    out.cnt = cnt;
+    return out;
+}
+
+// in-lane append of the values of v[0..N) below thr (references id0 ..): stores are suppressed
+// once the buffer is full but cnt keeps counting, so cnt > CAP afterwards flags the overflow
+template <int N, int CAP, int LD>
+__device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, float *&ps, int *&pi, int &cnt) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (v[j] < thr) {
+            if (cnt < CAP) {
+                *ps = v[j];
+                *pi = id0 + j;
+                ps += LD;
+                pi += LD;
+            }
+            ++cnt;
+        }
+    }
+}
+
+// One 32-column chunk of the main pass.  `r` holds this thread's scores against references
+// idb .. idb+31.  Fast path: min3 tree + one vote.  Hit path, in the hit lanes only and without
+// any cross-lane traffic: the tree's intermediate minima (four groups of <= 9 values) locate the
+// values below the threshold, which the lane appends to its own candidate buffer column.
+template <int KC, int CAP, int LD>
+__device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, float *buf_s, int *buf_i,
+                                           float *scratch, int col, int lane, float &thr, int &cnt,
+                                           int dbg) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    float a[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = fminf(fminf(v[3 * i], v[3 * i + 1]), v[3 * i + 2]);
+    a[10] = fminf(v[30], v[31]);
+    const float b0 = fminf(fminf(a[0], a[1]), a[2]);     // v[0..9)
+    const float b1 = fminf(fminf(a[3], a[4]), a[5]);     // v[9..18)
+    const float b2 = fminf(fminf(a[6], a[7]), a[8]);     // v[18..27)
+    const float b3 = fminf(a[9], a[10]);                 // v[27..32)
+    const float m = fminf(fminf(b0, b1), fminf(b2, b3));
+    bool hit = m < thr;
+    const unsigned hits = __ballot_sync(SK_FULL, hit);
+    if (hits == 0u) return;
     if (dbg & 1) {  // timing experiment: count the hits, skip the hit path (results are wrong)
-        cnt = (cnt + __popc(hits)) & 15;
+        cnt = (cnt + __popc(hits)) & 7;
         return;
     }
-    while (hits) {  // warp-uniform: one iteration per lane whose chunk minimum beat its threshold
-        const int L = __ffs(hits) - 1;
-        hits &= hits - 1;
-        __syncwarp();
-        if (lane == L) {
-            float4 *sc = reinterpret_cast<float4 *>(scratch);
+    // keep room for the usual one or two appends; compaction also refreshes the thresholds
+    if (__any_sync(SK_FULL, hit && cnt > CAP - 3)) {
+        const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + col, buf_i + col, thr, cnt);
+        thr = tc.thr;
+        cnt = tc.cnt;
+        hit = m < thr;
+    }
+    const int cnt0 = cnt;
+    if (hit) {
+        float *ps = buf_s + col + cnt * LD;
+        int *pi = buf_i + col + cnt * LD;
+        if (b0 < thr) tc_leaf<9, CAP, LD>(v, idb, thr, ps, pi, cnt);
+        if (b1 < thr) tc_leaf<9, CAP, LD>(v + 9, idb + 9, thr, ps, pi, cnt);
+        if (b2 < thr) tc_leaf<9, CAP, LD>(v + 18, idb + 18, thr, ps, pi, cnt);
+        if (b3 < thr) tc_leaf<5, CAP, LD>(v + 27, idb + 27, thr, ps, pi, cnt);
+    }
+    // rare: a lane found more values than it had free slots -> undo its appends and redo the
+    // chunk for it through the cooperative path (which compacts as often as needed)
+    unsigned ovf = __ballot_sync(SK_FULL, cnt > CAP);
+    if (ovf) {
+        if (cnt > CAP) cnt = cnt0;
+        while (ovf) {  // warp-uniform
+            const int L = __ffs(ovf) - 1;
+            ovf &= ovf - 1;
+            __syncwarp();
+            if (lane == L) {
+                float4 *sc = reinterpret_cast<float4 *>(scratch);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                sc[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                    __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-        }
-        __syncwarp();
-        const float x = scratch[lane];                 // score of lane L's query vs reference idb+lane
-        float thrL = __shfl_sync(SK_FULL, thr, L);
-        int cntL = __shfl_sync(SK_FULL, cnt, L);
-        unsigned pending = __ballot_sync(SK_FULL, x < thrL);
-        float *cs = buf_s + (tid - lane + L);
-        int *ci = buf_i + (tid - lane + L);
-        while (pending) {
-            unsigned take = pending;
-            if (cntL + __popc(pending) > CAP) {
-                if (cntL > KC) {
-                    if (lane == L) cnt = cntL;  // entries appended earlier in this loop
-                    tmem_ld_wait(inflight);
-                    const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + tid, buf_i + tid, thr, cnt);
-                    thr = tc.thr;
-                    cnt = tc.cnt;
-                    thrL = __shfl_sync(SK_FULL, thr, L);
-                    cntL = __shfl_sync(SK_FULL, cnt, L);
-                    pending &= __ballot_sync(SK_FULL, x < thrL);
-                    continue;
-                }
-                // at most KC entries held but more hits than free slots: lowest hits first
-                const int room = CAP - cntL;
-                while (__popc(take) > room) take &= ~(0x80000000u >> __clz(take));
+                for (int i = 0; i < 8; ++i) sc[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
-            if ((take >> lane) & 1u) {
-                const int slot = cntL + __popc(take & ((1u << lane) - 1u));
-                cs[slot * LD] = x;
-                ci[slot * LD] = idb + lane;
-            }
-            cntL += __popc(take);
-            pending &= ~take;
+            __syncwarp();
+            const ThrCnt tc = tc_process_coop<KC, CAP, LD>(L, idb, buf_s, buf_i, scratch, col, lane, thr, cnt);
+            thr = tc.thr;
+            cnt = tc.cnt;
         }
-        if (lane == L) cnt = cntL;
     }
 }
 
-// Epilogue of one job (reference tile x this warp's M tile): 4 chunks of 32 columns through the
-// alternating register buffers A / B.  On entry the load of chunk 0 into A has been issued; on
-// exit the load of chunk 0 of this warp's next job (j + STEP) into A has been issued, if any.
-template <int STEP, class F>
-__device__ __forceinline__ void tc_epi_job(uint32_t (&A)[32], uint32_t (&B)[32], uint32_t tlane, int j,
-                                           bool has_next, uint64_t *afull, uint64_t *aempty, int lane,
-                                           F &&proc) {
-    const int sl = j & (TC_SLOTS - 1);
-    const uint32_t tcol = tlane + (uint32_t)(sl * TC_N);
-    tmem_ld_wait(A);
-    tmem_ld32_issue(tcol + 32, B, A[0]);
-    proc(A, B, std::integral_constant<int, 0>{});
-    tmem_ld_wait(B);
-    tmem_ld32_issue(tcol + 64, A, B[0]);
-    proc(B, A, std::integral_constant<int, 1>{});
-    tmem_ld_wait(A);
-    tmem_ld32_issue(tcol + 96, B, A[0]);
-    proc(A, B, std::integral_constant<int, 2>{});
-    tmem_ld_wait(B);
-    // every TMEM read of this accumulator slot has landed: hand it back to the MMA issuer
+// Epilogue of one job (reference tile x this warp's M tile): the warp's CH chunks of 32 columns
+// are all read into registers first and the accumulator slot is handed back to the MMA issuer
+// BEFORE any of them is reduced, so the MMAs of the slot's next job overlap the reduction and a
+// slow hit path never holds TMEM.
+template <int CH, class F>
+__device__ __forceinline__ void tc_epi_job(uint32_t (&R)[CH][32], uint32_t tcol, uint64_t *afull_bar,
+                                           uint32_t parity, uint64_t *aempty_bar, int lane, F &&proc) {
+    mbar_wait(afull_bar, parity);
+    tc_fence_after();
+    uint32_t dep = 0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) tmem_ld32_issue(tcol + 32 * c, R[c], dep);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) tmem_ld_wait(R[c]);
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&aempty[sl]);
-    if (has_next) {
-        const int jn = j + STEP, sn = jn & (TC_SLOTS - 1);
-        mbar_wait(&afull[sn], (jn >> 2) & 1);
-        tc_fence_after();
-        tmem_ld32_issue(tlane + (uint32_t)(sn * TC_N), A, B[0]);
-    }
-    proc(B, A, std::integral_constant<int, 3>{});
+    if (lane == 0) mbar_arrive(aempty_bar);
+    if constexpr (CH >= 1) proc(R[0], std::integral_constant<int, 0>{});
+    if constexpr (CH >= 2) proc(R[1], std::integral_constant<int, 1>{});
+    if constexpr (CH >= 3) proc(R[2], std::integral_constant<int, 2>{});
+    if constexpr (CH >= 4) proc(R[3], std::integral_constant<int, 3>{});
 }
 
+// (register budget: the register file is allocated per 4 warps, so the 18-warp dual-stream CTA
+// gets 65536 / (20 * 32) = 102 -> 96 registers per thread and the 10-warp one 168)
 template <int KC, int MT, int NS, int CAP>
 __global__ void __launch_bounds__(TcCfg<MT, NS, CAP>::THREADS, 1)
 search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int kc_tot,
@@ -371,7 +431,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         }
         for (int a = 0; a < TC_SLOTS; ++a) {
             mbar_init(&afull[a], 1);
-            mbar_init(&aempty[a], 4);   // the four epilogue warps of the M tile that used the slot
+            mbar_init(&aempty[a], 4 * NS);  // the scanner warps of the M tile that used the slot
         }
         mbar_init(qbar, 1);
         fence_mbar_init();
@@ -398,9 +458,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             const unsigned char *rbase = (const unsigned char *)rimg;
             for (int tn = 0; tn < n_seq; ++tn) {
                 if (wrapped) mbar_wait(&empty[sn], wrap_par);
-                // sampled tiles: NS consecutive tiles out of every NS * seed_stride, so that sequence
-                // position and tile number agree modulo NS (n_seed is a multiple of NS)
-                const int tile = tn < n_seed ? (tn / NS) * (NS * seed_stride) + (tn % NS) : tn - n_seed;
+                const int tile = tn < n_seed ? tn * seed_stride : tn - n_seed;
                 mbar_expect_tx(&full[sn], b_bytes);
                 bulk_g2s(Rs + (size_t)sn * b_bytes, rbase + (size_t)tile * b_bytes, b_bytes, &full[sn]);
                 if (++sn == nstage) {
@@ -465,42 +523,37 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         }
     } else {
         // ======================= epilogue: thread <-> (query, stream) =======================
-        // warp = (stream p, M tile h, lane quarter); stream p handles positions p, p + NS, ... of
-        // the tile sequence, i.e. jobs (p + NS * i) * MT + h
+        // warp = (stream p, M tile h, lane quarter); every warp takes part in every job of its M
+        // tile and reads the stream's CH chunks of the 128 accumulator columns
+        constexpr int CH = Cfg::CH;
         const int col = threadIdx.x;          // candidate buffer column of this (query, stream)
         const int p = warp / (MT * 4);
         const int h = (warp >> 2) % MT;
         const int qslot = h * TC_M + (warp & 3) * 32 + lane;   // query within the CTA = TMEM lane of M tile h
-        const uint32_t tlane = tmem_base + (((uint32_t)((warp & 3) * 32)) << 16);
+        const uint32_t tlane = tmem_base + (((uint32_t)((warp & 3) * 32)) << 16) + (uint32_t)(p * CH * 32);
         float *scratch = scratch_all + warp * 32;
         float thr = SK_INF_F;
         int cnt = 0;
-        uint32_t A[32], B[32];
-        int t = p;                            // position in the tile sequence; this warp's job = t * MT + h
-        if (t < n_seq) {
-            const int j0 = t * MT + h;
-            mbar_wait(&afull[j0 & (TC_SLOTS - 1)], (j0 >> 2) & 1);
-            tc_fence_after();
-            uint32_t dep0 = 0;
-            tmem_ld32_issue(tlane + (uint32_t)((j0 & (TC_SLOTS - 1)) * TC_N), A, dep0);
-        }
+        uint32_t R[CH][32];
+        int t = 0;                            // position in the tile sequence; this warp's job = t * MT + h
 
-        // ---- seeding pass: group minima over the sampled tiles of this stream ----
+        // ---- seeding pass: group minima over the sampled tiles ----
         // (the 32 running minima live in the still unused candidate buffer column: slots of
-        // buf_s, then of buf_i; chunk c of the stream's n-th sampled tile feeds group (4n + c) % 32)
+        // buf_s, then of buf_i; chunk c of the n-th sampled tile feeds group (CH * n + c) % 32)
         if (n_seed > 0) {
             static_assert(2 * CAP >= TC_GROUPS, "group minima are parked in the candidate buffers");
             float *gcol = buf_s + col;
 #pragma unroll
             for (int g = 0; g < TC_GROUPS; ++g) gcol[g * LD] = SK_INF_F;   // buf_i follows buf_s
-            for (; t < n_seed; t += NS) {
-                const int g0 = ((t / NS) * 4) & (TC_GROUPS - 1);
-                tc_epi_job<NS * MT>(A, B, tlane, t * MT + h, t + NS < n_seq, afull, aempty, lane,
-                                    [&](const uint32_t (&r)[32], uint32_t (&)[32], auto ic) {
-                                        constexpr int c = decltype(ic)::value;
-                                        float *g = gcol + (g0 + c) * LD;
-                                        *g = fminf(*g, tc_min32(r));
-                                    });
+            for (; t < n_seed; ++t) {
+                const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
+                const int g0 = (t * CH) & (TC_GROUPS - 1);
+                tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), &afull[sl], (j >> 2) & 1, &aempty[sl], lane,
+                               [&](const uint32_t (&r)[32], auto ic) {
+                                   constexpr int c = decltype(ic)::value;
+                                   float *g = gcol + (g0 + c) * LD;
+                                   *g = fminf(*g, tc_min32(r));
+                               });
             }
             float gm[TC_GROUPS];
 #pragma unroll
@@ -509,15 +562,16 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             thr = gm[KC - 1];
         }
 
-        // ---- main pass over the stream's tiles ----
-        for (; t < n_seq; t += NS) {
-            const int idb = (t - n_seed) * TC_N;
-            tc_epi_job<NS * MT>(A, B, tlane, t * MT + h, t + NS < n_seq, afull, aempty, lane,
-                                [&](const uint32_t (&r)[32], uint32_t (&inflight)[32], auto ic) {
-                                    constexpr int c = decltype(ic)::value;
-                                    tc_process<KC, CAP, LD>(r, inflight, idb + c * 32, buf_s, buf_i, scratch,
-                                                            col, lane, thr, cnt, dbg);
-                                });
+        // ---- main pass ----
+        for (; t < n_seq; ++t) {
+            const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
+            const int idb = (t - n_seed) * TC_N + p * CH * 32;
+            tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), &afull[sl], (j >> 2) & 1, &aempty[sl], lane,
+                           [&](const uint32_t (&r)[32], auto ic) {
+                               constexpr int c = decltype(ic)::value;
+                               tc_process<KC, CAP, LD>(r, idb + c * 32, buf_s, buf_i, scratch, col, lane, thr,
+                                                       cnt, dbg);
+                           });
         }
 
         // ---- final compaction, then every thread writes the candidates of its (query, stream) ----
@@ -570,11 +624,10 @@ int search_tc_pick_stages(int kc_tot) {
     return 0;
 }
 
-// sampled tiles of the seeding pass (0 = no seeding: too few references for it to pay); a
-// multiple of ns: ns consecutive tiles out of every ns * seed_stride
-int search_tc_seed_tiles(int n_rtiles, int seed_stride, int ns) {
+// sampled tiles of the seeding pass (0 = no seeding: too few references for it to pay)
+int search_tc_seed_tiles(int n_rtiles, int seed_stride) {
     if (seed_stride <= 0 || n_rtiles < 64) return 0;
-    return n_rtiles / (ns * seed_stride) * ns;
+    return (n_rtiles + seed_stride - 1) / seed_stride;
 }
 
 template <int KC, int MT, int NS, int CAP>
@@ -587,7 +640,7 @@ static cudaError_t launch_tc(const float *qimg, const float *rimg, int kc_tot, i
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const long long n_qtiles = (n_q + Cfg::QT - 1) / Cfg::QT;
-    const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride, NS);
+    const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride);
     search_tc_kernel<KC, MT, NS, CAP><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
         qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, seed_stride, n_q, cand_idx, cand_thr, g_tc_debug);
     return cudaGetLastError();
