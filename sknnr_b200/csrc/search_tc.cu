@@ -52,6 +52,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdio>
 #include <type_traits>
 
 namespace sk {
@@ -65,7 +66,7 @@ template <int MT_, int NS_, int CAP_> struct TcCfg {
     static constexpr int MT = MT_, NS = NS_, CAP = CAP_;
     static constexpr int QT = MT * TC_M;                  // queries per CTA
     static constexpr int EPI_WARPS = MT * 4 * NS;         // scanner warps: (stream, M tile, lane quarter)
-    static constexpr int THREADS = (EPI_WARPS + 2) * 32;  // + MMA issuer warp + TMA producer warp
+    static constexpr int THREADS = (EPI_WARPS + MT + 1) * 32;  // + MT MMA issuer warps + TMA producer warp
     static constexpr int LD = QT * NS + 1;                // slot stride (odd: a column's slots hit 32 banks)
     static constexpr int SORT = CAP <= 16 ? 16 : 32;      // width of the register sorting network
     static_assert(CAP <= SORT && CAP % 2 == 0, "candidate buffer shape");
@@ -200,6 +201,15 @@ __device__ __forceinline__ float tc_min32(const uint32_t (&r)[32]) {
     const float b2 = fminf(fminf(a[6], a[7]), a[8]);
     const float b3 = fminf(a[9], a[10]);
     return fminf(fminf(b0, b1), fminf(b2, b3));
+}
+
+// timing experiment (dbg bit 3): per-job timestamps of CTA 0, M tile 0
+#define TC_TS_J0 100
+#define TC_TS_N 8
+__device__ unsigned long long g_tc_ts[8][TC_TS_N];
+__device__ __forceinline__ void tc_stamp(int dbg, int which, int t) {
+    if ((dbg & 8) && blockIdx.x == 0 && t >= TC_TS_J0 && t < TC_TS_J0 + TC_TS_N && (threadIdx.x & 31) == 0)
+        g_tc_ts[which][t - TC_TS_J0] = clock64();
 }
 
 struct ThrCnt {
@@ -382,21 +392,27 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
 // slow hit path never holds TMEM.
 template <int CH, class F>
 __device__ __forceinline__ void tc_epi_job(uint32_t (&R)[CH][32], uint32_t tcol, uint64_t *afull_bar,
-                                           uint32_t parity, uint64_t *aempty_bar, int lane, F &&proc) {
+                                           uint32_t parity, uint64_t *aempty_bar, int lane, F &&proc,
+                                           int dbg = 0, int ts_t = -1) {
+    tc_stamp(dbg, 0, ts_t);
     mbar_wait(afull_bar, parity);
+    tc_stamp(dbg, 1, ts_t);
     tc_fence_after();
     uint32_t dep = 0;
 #pragma unroll
     for (int c = 0; c < CH; ++c) tmem_ld32_issue(tcol + 32 * c, R[c], dep);
 #pragma unroll
     for (int c = 0; c < CH; ++c) tmem_ld_wait(R[c]);
+    tc_stamp(dbg, 2, ts_t);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(aempty_bar);
+    tc_stamp(dbg, 3, ts_t);
     if constexpr (CH >= 1) proc(R[0], std::integral_constant<int, 0>{});
     if constexpr (CH >= 2) proc(R[1], std::integral_constant<int, 1>{});
     if constexpr (CH >= 3) proc(R[2], std::integral_constant<int, 2>{});
     if constexpr (CH >= 4) proc(R[3], std::integral_constant<int, 3>{});
+    tc_stamp(dbg, 4, ts_t);
 }
 
 // (register budget: the register file is allocated per 4 warps, so the 18-warp dual-stream CTA
@@ -427,7 +443,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], MT);   // one tcgen05.commit per MMA issuer
         }
         for (int a = 0; a < TC_SLOTS; ++a) {
             mbar_init(&afull[a], 1);
@@ -445,7 +461,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     const int ksteps = kc_tot >> 1;  // MMA K = 8 TF32 = two 16-byte chunks
     const int n_seq = n_seed + n_rtiles;  // sampled tiles (seeding), then every tile
 
-    if (warp == EPI_WARPS + 1) {
+    if (warp == EPI_WARPS + MT) {
         // ======================= TMA producer (one thread) =======================
         // No divisions, no descriptor rebuilds in these two single-thread loops: each of their
         // instructions is on the critical path of the tensor pipe.
@@ -459,8 +475,12 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             for (int tn = 0; tn < n_seq; ++tn) {
                 if (wrapped) mbar_wait(&empty[sn], wrap_par);
                 const int tile = tn < n_seed ? tn * seed_stride : tn - n_seed;
-                mbar_expect_tx(&full[sn], b_bytes);
-                bulk_g2s(Rs + (size_t)sn * b_bytes, rbase + (size_t)tile * b_bytes, b_bytes, &full[sn]);
+                if ((dbg & 4) && wrapped) {
+                    mbar_arrive(&full[sn]);   // timing experiment: reuse the stale tile, no L2 traffic
+                } else {
+                    mbar_expect_tx(&full[sn], b_bytes);
+                    bulk_g2s(Rs + (size_t)sn * b_bytes, rbase + (size_t)tile * b_bytes, b_bytes, &full[sn]);
+                }
                 if (++sn == nstage) {
                     sn = 0;
                     wrap_par = wrapped ? (wrap_par ^ 1u) : 0u;
@@ -469,51 +489,50 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             }
         }
         __syncwarp();
-    } else if (warp == EPI_WARPS) {
-        // ======================= MMA issuer =======================
-        // The whole warp runs this loop in lock step (uniform control flow keeps descriptors and
+    } else if (warp >= EPI_WARPS) {
+        // ======================= MMA issuers: one warp per M tile =======================
+        // Issuing is effectively synchronous (the thread gets the next tcgen05.mma out at the
+        // rate the tensor pipe retires them), and barrier waits + bookkeeping cost a lone warp
+        // another ~300 cycles per job during which ITS MMAs are not being queued; with one issuer
+        // per M tile the other issuer's MMAs fill that gap.
+        // The whole warp runs the loop in lock step (uniform control flow keeps descriptors and
         // counters in uniform registers); one elected lane issues the tcgen05 instructions.
+        const int h = warp - EPI_WARPS;
         mbar_wait(qbar, 0);
         const uint32_t a_lbo = TC_M * TC_ROWB, b_lbo = TC_N * TC_ROWB;
         // descriptor = {hi: SBO = 128 B, version 1; lo: start address >> 4 | LBO >> 4 << 16}; moving
         // to the next K step (two 16-byte chunks) or operand image only adds to the address field
         const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
-        const uint32_t a_lo0 = ((smem_u32(Qs) >> 4) & 0x3fffu) | (((a_lbo >> 4) & 0x3fffu) << 16);
+        const uint32_t a_lo0 = (((smem_u32(Qs) + h * a_bytes) >> 4) & 0x3fffu) | (((a_lbo >> 4) & 0x3fffu) << 16);
         const uint32_t b_lo0 = ((smem_u32(Rs) >> 4) & 0x3fffu) | (((b_lbo >> 4) & 0x3fffu) << 16);
         const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
-        const uint32_t a_img = a_bytes >> 4, b_img = b_bytes >> 4;
+        const uint32_t b_img = b_bytes >> 4;
         int s = 0;
         uint32_t full_par = 0, b_lo_s = b_lo0;
-        int j = 0;               // job number = t * MT + h
-        uint32_t sl = 0;         // j % TC_SLOTS
-        uint32_t aempty_par = 0; // parity of (j / TC_SLOTS - 1), first used by jobs 4..7
         for (int t = 0; t < n_seq; ++t) {
+            const int j = t * MT + h;                    // this issuer's job on tile t
+            const uint32_t sl = (uint32_t)j & (TC_SLOTS - 1);
             mbar_wait(&full[s], full_par);
-            uint32_t a_lo_h = a_lo0;
-#pragma unroll 1
-            for (int h = 0; h < MT; ++h, ++j) {
-                if (j >= TC_SLOTS) mbar_wait(&aempty[sl], aempty_par);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + sl * TC_N;
-                if (elect_one()) {
-                    uint32_t a_lo = a_lo_h, b_lo = b_lo_s;
-                    tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 0u);
+            if (h == 0) tc_stamp(dbg, 5, t);
+            if (j >= TC_SLOTS) mbar_wait(&aempty[sl], (uint32_t)(((j >> 2) - 1) & 1));
+            if (h == 0) tc_stamp(dbg, 6, t);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + sl * TC_N;
+            if (elect_one()) {
+                uint32_t a_lo = a_lo0, b_lo = b_lo_s;
+                tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 0u);
 #pragma unroll 4
-                    for (int ks = 1; ks < ksteps; ++ks) {
-                        a_lo += a_kstep;
-                        b_lo += b_kstep;
-                        tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 1u);
-                    }
-                    tc_commit(&afull[sl]);   // accumulators of job j complete
-                    if (h == MT - 1) tc_commit(&empty[s]);  // smem slot reusable once read
+                for (int ks = 1; ks < ksteps; ++ks) {
+                    a_lo += a_kstep;
+                    b_lo += b_kstep;
+                    tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 1u);
                 }
-                __syncwarp();
-                a_lo_h += a_img;
-                if (++sl == TC_SLOTS) {
-                    sl = 0;
-                    if (j >= TC_SLOTS) aempty_par ^= 1u;
-                }
+                tc_commit(&afull[sl]);   // accumulators of job j complete
+                if (h == 0 && (dbg & 8) && blockIdx.x == 0 && t >= TC_TS_J0 && t < TC_TS_J0 + TC_TS_N)
+                    g_tc_ts[7][t - TC_TS_J0] = clock64();
+                tc_commit(&empty[s]);    // one of the MT arrivals that free the smem slot
             }
+            __syncwarp();
             b_lo_s += b_img;
             if (++s == nstage) {
                 s = 0;
@@ -571,7 +590,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
                                constexpr int c = decltype(ic)::value;
                                tc_process<KC, CAP, LD>(r, idb + c * 32, buf_s, buf_i, scratch, col, lane, thr,
                                                        cnt, dbg);
-                           });
+                           }, warp == 0 ? dbg : 0, t);
         }
 
         // ---- final compaction, then every thread writes the candidates of its (query, stream) ----
@@ -600,6 +619,15 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     __syncthreads();
     tc_fence_after();
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
+    if ((dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long t0 = g_tc_ts[5][0];
+        for (int i = 0; i < TC_TS_N; ++i)
+            printf("tile %d: issuer want %6lld slotfree %6lld committed %6lld | scanner want %6lld afull %6lld "
+                   "loaded %6lld released %6lld processed %6lld\n",
+                   TC_TS_J0 + i, (long long)(g_tc_ts[5][i] - t0), (long long)(g_tc_ts[6][i] - t0),
+                   (long long)(g_tc_ts[7][i] - t0), (long long)(g_tc_ts[0][i] - t0), (long long)(g_tc_ts[1][i] - t0),
+                   (long long)(g_tc_ts[2][i] - t0), (long long)(g_tc_ts[3][i] - t0), (long long)(g_tc_ts[4][i] - t0));
+    }
 }
 
 int g_tc_debug = 0;  // timing experiments only (set through the "tc_debug" option)
