@@ -79,6 +79,11 @@ struct DevBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // the cascade's tail (SIMT re-search + exhaustive search of uncertified rows) runs on its own
+    // stream so that a handful of slow CTAs overlap the next chunk's first stage
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t ev_stage1 = nullptr, ev_tail = nullptr;
+    bool tail_pending = false;
     DevBuf<unsigned char> x;       // staged query rows (host callers)
     DevBuf<double> z64;
     DevBuf<float> qimg;
@@ -109,6 +114,10 @@ struct Slot {
         ev_used = 0;
         if (h_fb) cudaFreeHost(h_fb);
         if (own_stream && stream) cudaStreamDestroy(stream);
+        if (tail_stream) cudaStreamDestroy(tail_stream);
+        if (ev_stage1) cudaEventDestroy(ev_stage1);
+        if (ev_tail) cudaEventDestroy(ev_tail);
+        tail_stream = nullptr; ev_stage1 = ev_tail = nullptr; tail_pending = false;
         h_fb = nullptr; stream = nullptr;
     }
     // record a timing event on `st` (pairs: even = start, odd = stop)
@@ -158,6 +167,9 @@ struct IndexBase {
         for (auto &s : slots) {
             CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             s.own_stream = true;
+            CK(cudaStreamCreateWithFlags(&s.tail_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s.ev_stage1, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
             CK(cudaHostAlloc((void **)&s.h_fb, 2 * sizeof(int), cudaHostAllocDefault));
             s.h_fb[0] = s.h_fb[1] = 0;
         }
@@ -537,6 +549,10 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
         ra.n_rows_dev = nullptr;
         ra.row_map = nullptr;
         CK(launch_refine(ra, fp, st));
+        // everything below only concerns the uncertified rows: continue on the slot's tail stream
+        CK(cudaEventRecord(s.ev_stage1, st));
+        CK(cudaStreamWaitEvent(s.tail_stream, s.ev_stage1, 0));
+        st = s.tail_stream;
         // stage 2 input: gather the uncertified rows and rebuild their FP32 query image
         CK(s.z64c.reserve((size_t)rows * ix->d_out));
         CK(launch_gather_rows(s.z64.p, ix->d_out, s.fb.p + 1, s.fb.p, rows, s.z64c.p, st));
@@ -574,6 +590,10 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     CK(cudaMemcpyAsync(&s.h_fb[1], s.fb2.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     s.fb_pending = true;
     s.rows_in_flight = use_tc ? rows : 0;
+    if (use_tc) {
+        CK(cudaEventRecord(s.ev_tail, st));
+        s.tail_pending = true;
+    }
     return SKNNR_OK;
 }
 
@@ -615,12 +635,19 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     int ci = 0;
     for (int64_t r0 = 0; r0 < n_q; r0 += chunk, ++ci) {
         const int64_t rows = std::min(chunk, n_q - r0);
-        Slot &s = dev_ptrs ? ix->slots[0] : ix->slots[ci & 1];
+        // two slots alternate: the tail of chunk c (on its slot's tail stream) overlaps the first
+        // stage of chunk c + 1 (other slot's buffers)
+        Slot &s = ix->slots[ci & 1];
         cudaStream_t saved = s.stream;
         if (dev_ptrs) {
             s.stream = user_stream;
+            if (s.tail_pending) {   // the slot's buffers are free once its previous tail is done
+                CK(cudaStreamWaitEvent(user_stream, s.ev_tail, 0));
+                s.tail_pending = false;
+            }
         } else {
             CK(cudaStreamSynchronize(s.stream));  // previous chunk on this slot is done
+            s.tail_pending = false;
             ix->harvest(s);
             // adaptive engine choice: if the TF32 filter cannot certify > 5 % of the rows
             // (ill-conditioned features: huge norms relative to neighbour distances) the FP32
@@ -656,6 +683,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
                        flags, decimals, weights, o_dist, o_idx, o_pred);
         if (rc != SKNNR_OK) { s.stream = saved; return rc; }
         if (!dev_ptrs) {
+            if (s.tail_pending) CK(cudaStreamWaitEvent(s.stream, s.ev_tail, 0));  // results complete
             if (out_dist) {
                 CK(cudaMemcpyAsync(out_dist + r0 * k, o_dist, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, s.stream));
                 ix->stats.d2h_bytes += rows * k * 8;
@@ -674,8 +702,16 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     if (!dev_ptrs) {
         for (auto &s : ix->slots) {
             CK(cudaStreamSynchronize(s.stream));
+            s.tail_pending = false;
             ix->harvest(s);
         }
+    } else {
+        // results are complete on the caller's stream once both tails have joined it
+        for (auto &s : ix->slots)
+            if (s.tail_pending) {
+                CK(cudaStreamWaitEvent(user_stream, s.ev_tail, 0));
+                s.tail_pending = false;
+            }
     }
     // a device-pointer call is not synchronised: its counters are harvested by the stats query
     return SKNNR_OK;

@@ -19,6 +19,51 @@ namespace sk {
 
 constexpr int REFINE_WARPS = 8;
 
+// Exact squared distance by direct float64 differences, summed in ONE fixed order shared by every
+// kernel of this library (so all engines agree bit for bit): sixteen strided partial sums
+//     p[h] = sum_j (zq[h + 16 j] - r[h + 16 j])^2,   j ascending,
+// combined by the butterfly tree of a 16-lane shuffle reduction (xor 8, 4, 2, 1).
+// dist2_lane is the partial of lane h of a half warp (coalesced: the half warp reads 128
+// consecutive bytes of the reference row per load); dist2_serial replays the same tree in one
+// thread.
+__device__ __forceinline__ double dist2_lane(const double *__restrict__ zq, const double *__restrict__ r,
+                                             int d, int h) {
+    double acc = 0.0;
+    for (int k = h; k < d; k += 16) {
+        const double df = zq[k] - __ldg(r + k);
+        acc += df * df;
+    }
+    return acc;
+}
+__device__ __forceinline__ double dist2_reduce16(double acc) {
+    acc += __shfl_xor_sync(SK_FULL, acc, 8);
+    acc += __shfl_xor_sync(SK_FULL, acc, 4);
+    acc += __shfl_xor_sync(SK_FULL, acc, 2);
+    acc += __shfl_xor_sync(SK_FULL, acc, 1);
+    return acc;
+}
+__device__ __forceinline__ double dist2_serial(const double *__restrict__ zq, const double *__restrict__ r,
+                                               int d) {
+    double p[16];
+#pragma unroll
+    for (int h = 0; h < 16; ++h) p[h] = 0.0;
+    for (int k0 = 0; k0 < d; k0 += 16) {
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            if (k0 + h < d) {
+                const double df = zq[k0 + h] - r[k0 + h];
+                p[h] += df * df;
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int h = 0; h < m; ++h) p[h] = p[h] + p[h + m];   // == lane h after the xor-m shuffle step
+    }
+    return p[0];
+}
+
 __global__ void __launch_bounds__(REFINE_WARPS * 32)
 refine_kernel(RefineArgs a, FinishParams fp) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -26,18 +71,21 @@ refine_kernel(RefineArgs a, FinishParams fp) {
     if (q >= a.n_q || (a.n_rows_dev && q >= *a.n_rows_dev)) return;
     const double *zq = a.z64 + q * a.d;
 
+    // Exact squared distances of the candidates: each half warp takes one candidate per pass (its
+    // 16 lanes read consecutive features, so a pass touches two lines of L2 instead of 32) and
+    // reduces with a 16-lane butterfly; lane (i & 15) of the half warp keeps the result of pass i.
+    const int half = lane >> 4, hl = lane & 15;
     int id = 0x7fffffff;
     double d2 = SK_INF_D;
-    if (lane < a.kc) {
-        const int c = a.cand_idx[q * a.kc + lane];
-        if (c >= 0 && c < a.n_ref) {
+    for (int i = 0; 2 * i < a.kc; ++i) {
+        const int ci = 2 * i + half;
+        const int c = ci < a.kc ? a.cand_idx[q * a.kc + ci] : -1;
+        const bool have = c >= 0 && c < a.n_ref;
+        double acc = 0.0;
+        if (have) acc = dist2_lane(zq, a.ref64 + (long long)c * a.d, a.d, hl);
+        acc = dist2_reduce16(acc);
+        if (have && hl == (i & 15)) {
             id = c;
-            const double *r = a.ref64 + (long long)c * a.d;
-            double acc = 0.0;
-            for (int k = 0; k < a.d; ++k) {
-                const double df = zq[k] - r[k];
-                acc += df * df;
-            }
             d2 = acc;
         }
     }
@@ -89,12 +137,7 @@ __device__ __forceinline__ double exact_pair(const ExactArgs &a, long long q, in
     if (a.metric == 0) {
         const double *zq = a.z64 + q * a.d;
         const double *r = a.ref64 + (long long)j * a.d;
-        double acc = 0.0;
-        for (int k = 0; k < a.d; ++k) {
-            const double df = zq[k] - r[k];
-            acc += df * df;
-        }
-        return acc;
+        return dist2_serial(zq, r, a.d);
     }
     // weighted Hamming: left-to-right float64 sum of w_t over mismatching trees / sum(w)
     // ($SP/scipy/spatial/distance.py:1718-1723 -> cdist_hamming)

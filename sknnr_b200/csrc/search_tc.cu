@@ -52,7 +52,6 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#include <cstdio>
 #include <type_traits>
 
 namespace sk {
@@ -201,15 +200,6 @@ __device__ __forceinline__ float tc_min32(const uint32_t (&r)[32]) {
     const float b2 = fminf(fminf(a[6], a[7]), a[8]);
     const float b3 = fminf(a[9], a[10]);
     return fminf(fminf(b0, b1), fminf(b2, b3));
-}
-
-// timing experiment (dbg bit 3): per-job timestamps of CTA 0, M tile 0
-#define TC_TS_J0 100
-#define TC_TS_N 8
-__device__ unsigned long long g_tc_ts[8][TC_TS_N];
-__device__ __forceinline__ void tc_stamp(int dbg, int which, int t) {
-    if ((dbg & 8) && blockIdx.x == 0 && t >= TC_TS_J0 && t < TC_TS_J0 + TC_TS_N && (threadIdx.x & 31) == 0)
-        g_tc_ts[which][t - TC_TS_J0] = clock64();
 }
 
 struct ThrCnt {
@@ -392,27 +382,21 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
 // slow hit path never holds TMEM.
 template <int CH, class F>
 __device__ __forceinline__ void tc_epi_job(uint32_t (&R)[CH][32], uint32_t tcol, uint64_t *afull_bar,
-                                           uint32_t parity, uint64_t *aempty_bar, int lane, F &&proc,
-                                           int dbg = 0, int ts_t = -1) {
-    tc_stamp(dbg, 0, ts_t);
+                                           uint32_t parity, uint64_t *aempty_bar, int lane, F &&proc) {
     mbar_wait(afull_bar, parity);
-    tc_stamp(dbg, 1, ts_t);
     tc_fence_after();
     uint32_t dep = 0;
 #pragma unroll
     for (int c = 0; c < CH; ++c) tmem_ld32_issue(tcol + 32 * c, R[c], dep);
 #pragma unroll
     for (int c = 0; c < CH; ++c) tmem_ld_wait(R[c]);
-    tc_stamp(dbg, 2, ts_t);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(aempty_bar);
-    tc_stamp(dbg, 3, ts_t);
     if constexpr (CH >= 1) proc(R[0], std::integral_constant<int, 0>{});
     if constexpr (CH >= 2) proc(R[1], std::integral_constant<int, 1>{});
     if constexpr (CH >= 3) proc(R[2], std::integral_constant<int, 2>{});
     if constexpr (CH >= 4) proc(R[3], std::integral_constant<int, 3>{});
-    tc_stamp(dbg, 4, ts_t);
 }
 
 // (register budget: the register file is allocated per 4 warps, so the 18-warp dual-stream CTA
@@ -513,9 +497,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             const int j = t * MT + h;                    // this issuer's job on tile t
             const uint32_t sl = (uint32_t)j & (TC_SLOTS - 1);
             mbar_wait(&full[s], full_par);
-            if (h == 0) tc_stamp(dbg, 5, t);
             if (j >= TC_SLOTS) mbar_wait(&aempty[sl], (uint32_t)(((j >> 2) - 1) & 1));
-            if (h == 0) tc_stamp(dbg, 6, t);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + sl * TC_N;
             if (elect_one()) {
@@ -528,8 +510,6 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
                     tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 1u);
                 }
                 tc_commit(&afull[sl]);   // accumulators of job j complete
-                if (h == 0 && (dbg & 8) && blockIdx.x == 0 && t >= TC_TS_J0 && t < TC_TS_J0 + TC_TS_N)
-                    g_tc_ts[7][t - TC_TS_J0] = clock64();
                 tc_commit(&empty[s]);    // one of the MT arrivals that free the smem slot
             }
             __syncwarp();
@@ -590,7 +570,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
                                constexpr int c = decltype(ic)::value;
                                tc_process<KC, CAP, LD>(r, idb + c * 32, buf_s, buf_i, scratch, col, lane, thr,
                                                        cnt, dbg);
-                           }, warp == 0 ? dbg : 0, t);
+                           });
         }
 
         // ---- final compaction, then every thread writes the candidates of its (query, stream) ----
@@ -619,15 +599,6 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     __syncthreads();
     tc_fence_after();
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
-    if ((dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
-        const unsigned long long t0 = g_tc_ts[5][0];
-        for (int i = 0; i < TC_TS_N; ++i)
-            printf("tile %d: issuer want %6lld slotfree %6lld committed %6lld | scanner want %6lld afull %6lld "
-                   "loaded %6lld released %6lld processed %6lld\n",
-                   TC_TS_J0 + i, (long long)(g_tc_ts[5][i] - t0), (long long)(g_tc_ts[6][i] - t0),
-                   (long long)(g_tc_ts[7][i] - t0), (long long)(g_tc_ts[0][i] - t0), (long long)(g_tc_ts[1][i] - t0),
-                   (long long)(g_tc_ts[2][i] - t0), (long long)(g_tc_ts[3][i] - t0), (long long)(g_tc_ts[4][i] - t0));
-    }
 }
 
 int g_tc_debug = 0;  // timing experiments only (set through the "tc_debug" option)
