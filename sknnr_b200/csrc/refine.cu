@@ -77,9 +77,10 @@ refine_kernel(RefineArgs a, FinishParams fp) {
     const int half = lane >> 4, hl = lane & 15;
     int id = 0x7fffffff;
     double d2 = SK_INF_D;
+    const int my_c = lane < a.kc ? a.cand_idx[q * a.kc + lane] : -1;   // kc <= 32: one coalesced load
+#pragma unroll 4
     for (int i = 0; 2 * i < a.kc; ++i) {
-        const int ci = 2 * i + half;
-        const int c = ci < a.kc ? a.cand_idx[q * a.kc + ci] : -1;
+        const int c = __shfl_sync(SK_FULL, my_c, (2 * i + half) & 31);
         const bool have = c >= 0 && c < a.n_ref;
         double acc = 0.0;
         if (have) acc = dist2_lane(zq, a.ref64 + (long long)c * a.d, a.d, hl);

@@ -293,19 +293,18 @@ __device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, float *buf_s, int
     return out;
 }
 
-// in-lane append of the values of v[0..N) below thr (references id0 ..): stores are suppressed
-// once the buffer is full but cnt keeps counting, so cnt > CAP afterwards flags the overflow
-template <int N, int CAP, int LD>
+// in-lane append of the values of v[0..N) below thr (references id0 ..), N <= 3: every value is
+// stored at the lane's next free slot and the slot only advances for the values that qualify, so
+// there is no branch per value.  The caller guarantees N free slots.
+template <int N, int LD>
 __device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, float *&ps, int *&pi, int &cnt) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
+        *ps = v[j];
+        *pi = id0 + j;
         if (v[j] < thr) {
-            if (cnt < CAP) {
-                *ps = v[j];
-                *pi = id0 + j;
-                ps += LD;
-                pi += LD;
-            }
+            ps += LD;
+            pi += LD;
             ++cnt;
         }
     }
@@ -346,19 +345,27 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
         hit = m < thr;
     }
     const int cnt0 = cnt;
+    bool over = false;
     if (hit) {
         float *ps = buf_s + col + cnt * LD;
         int *pi = buf_i + col + cnt * LD;
-        if (b0 < thr) tc_leaf<9, CAP, LD>(v, idb, thr, ps, pi, cnt);
-        if (b1 < thr) tc_leaf<9, CAP, LD>(v + 9, idb + 9, thr, ps, pi, cnt);
-        if (b2 < thr) tc_leaf<9, CAP, LD>(v + 18, idb + 18, thr, ps, pi, cnt);
-        if (b3 < thr) tc_leaf<5, CAP, LD>(v + 27, idb + 27, thr, ps, pi, cnt);
+        // descend the tree: group of <= 9 values -> triple -> values; every triple needs 3 free slots
+#define SK_TC_TRIPLE(I, N)                                                      \
+        if (a[I] < thr) {                                                       \
+            if (cnt > CAP - 3) over = true;                                     \
+            else tc_leaf<N, LD>(v + 3 * (I), idb + 3 * (I), thr, ps, pi, cnt);  \
+        }
+        if (b0 < thr) { SK_TC_TRIPLE(0, 3) SK_TC_TRIPLE(1, 3) SK_TC_TRIPLE(2, 3) }
+        if (b1 < thr) { SK_TC_TRIPLE(3, 3) SK_TC_TRIPLE(4, 3) SK_TC_TRIPLE(5, 3) }
+        if (b2 < thr) { SK_TC_TRIPLE(6, 3) SK_TC_TRIPLE(7, 3) SK_TC_TRIPLE(8, 3) }
+        if (b3 < thr) { SK_TC_TRIPLE(9, 3) SK_TC_TRIPLE(10, 2) }
+#undef SK_TC_TRIPLE
     }
     // rare: a lane found more values than it had free slots -> undo its appends and redo the
     // chunk for it through the cooperative path (which compacts as often as needed)
-    unsigned ovf = __ballot_sync(SK_FULL, cnt > CAP);
+    unsigned ovf = __ballot_sync(SK_FULL, over);
     if (ovf) {
-        if (cnt > CAP) cnt = cnt0;
+        if (over) cnt = cnt0;
         while (ovf) {  // warp-uniform
             const int L = __ffs(ovf) - 1;
             ovf &= ovf - 1;
