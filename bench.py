@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=32)
     ap.add_argument("--n-out", type=int, default=8)
     ap.add_argument("--k", type=int, default=7)
-    ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--engine", type=int, default=0)
@@ -298,9 +298,14 @@ def run_ours(a, rank, world, local_rank):
         ms_total = float(t.item())
     value = world * n_q * a.steps / (ms_total * 1e-3)
 
-    # dominant-kernel timing: one more step on the library's own stream with CUDA events
-    # around the search kernel launches (device-pointer calls do not harvest events)
-    d1, i1, p1 = None, None, None
+    # dominant-kernel timing: one more device-resident step; the library brackets every search
+    # kernel launch with CUDA events on the launching stream (option "timing") and the stats
+    # query sums them.  (The host-buffer call below overlaps chunks on several streams, so its
+    # per-kernel brackets would include waiting for the other streams' kernels.)
+    step_device()
+    barrier()
+    dev_stats = index.stats()
+    search_ms_dev = dev_stats["search_ms"]
 
     # e2e through the host-buffer call (pinned host in/out, copies inside the timed region)
     e2e = None
@@ -332,7 +337,7 @@ def run_ours(a, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         stats = index.stats()
-        search_ms, launches, fallbacks = stats["search_ms"], stats["kernel_launches"], stats["n_fallback"]
+        search_ms, launches, fallbacks = search_ms_dev, stats["kernel_launches"], stats["n_fallback"]
         e2e = {"value": world * n_q * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": int(stats["d2h_bytes"]),
                "steps": e2e_steps, "timer": "host wall clock around the synchronous C-ABI call"}
@@ -340,10 +345,8 @@ def run_ours(a, rank, world, local_rank):
         assert torch.equal(h_idx.to(dev), o_idx), "device and host paths disagree"
     else:
         # still need the search-kernel time: run the host path on a slice
-        rows = min(n_q, 1 << 20)
-        index.query(xh[:rows], k, weights="distance", with_pred=True, row_offset=rank * n_q)
-        stats = index.stats()
-        search_ms = stats["search_ms"] * (n_q / rows)
+        stats = dev_stats
+        search_ms = search_ms_dev
         launches, fallbacks = stats["kernel_launches"], stats["n_fallback"]
 
     if rank != 0:

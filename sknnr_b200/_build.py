@@ -20,7 +20,7 @@ SOURCES = ["api.cu", "search_simt.cu", "search_tc.cu", "refine.cu", "project.cu"
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "sknnr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xptxas=-v",
+    "-Xcompiler", "-fPIC", "-Xptxas=-v", *os.environ.get("SK_NVCC_EXTRA", "").split(),
 ]
 
 

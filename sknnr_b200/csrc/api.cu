@@ -138,7 +138,10 @@ struct IndexBase {
     int n_out = 0;
     double *d_y = nullptr;
     std::mutex lock;
-    Slot slots[2];
+    // chunks rotate through the slots (own stream + buffers each): H2D of one chunk, kernels of
+    // another and D2H of a third overlap; a device-pointer call alternates the first two
+    static constexpr int kSlots = 4;
+    Slot slots[kSlots];
     int exact_grid = 0;
     sknnr_stats stats{};
     int n_sm = 148;
@@ -637,7 +640,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
         const int64_t rows = std::min(chunk, n_q - r0);
         // two slots alternate: the tail of chunk c (on its slot's tail stream) overlaps the first
         // stage of chunk c + 1 (other slot's buffers)
-        Slot &s = ix->slots[ci & 1];
+        Slot &s = ix->slots[dev_ptrs ? (ci & 1) : (ci % IndexBase::kSlots)];
         cudaStream_t saved = s.stream;
         if (dev_ptrs) {
             s.stream = user_stream;
@@ -661,9 +664,13 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             dX = (const unsigned char *)X + (size_t)r0 * ldx * esz;
         } else {
             CK(s.x.reserve((size_t)rows * cols * esz));
-            CK(cudaMemcpy2DAsync(s.x.p, (size_t)cols * esz,
-                                 (const unsigned char *)X + (size_t)r0 * ldx * esz, (size_t)ldx * esz,
-                                 (size_t)cols * esz, (size_t)rows, cudaMemcpyHostToDevice, s.stream));
+            if (ldx == cols)
+                CK(cudaMemcpyAsync(s.x.p, (const unsigned char *)X + (size_t)r0 * ldx * esz,
+                                   (size_t)rows * cols * esz, cudaMemcpyHostToDevice, s.stream));
+            else
+                CK(cudaMemcpy2DAsync(s.x.p, (size_t)cols * esz,
+                                     (const unsigned char *)X + (size_t)r0 * ldx * esz, (size_t)ldx * esz,
+                                     (size_t)cols * esz, (size_t)rows, cudaMemcpyHostToDevice, s.stream));
             ix->stats.h2d_bytes += rows * cols * (int64_t)esz;
             dX = s.x.p;
             dld = cols;
@@ -926,7 +933,7 @@ int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, i
     int ci = 0;
     for (int64_t r0 = 0; r0 < n_q; r0 += chunk, ++ci) {
         const int64_t rows = std::min(chunk, n_q - r0);
-        Slot &s = dev_ptrs ? ix->slots[0] : ix->slots[ci & 1];
+        Slot &s = dev_ptrs ? ix->slots[0] : ix->slots[ci % IndexBase::kSlots];
         cudaStream_t saved = s.stream;
         if (dev_ptrs) {
             s.stream = user_stream;

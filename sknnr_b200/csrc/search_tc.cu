@@ -588,9 +588,10 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         }
         const long long q = qtile * Cfg::QT + qslot;
         if (q < n_q) {
-            int4 *dst = reinterpret_cast<int4 *>(cand_idx + (q * NS + p) * KC);
+            constexpr int KOUT = 16 / NS;   // list slots per stream in the output (unused ones hold -1)
+            int4 *dst = reinterpret_cast<int4 *>(cand_idx + (q * NS + p) * KOUT);
 #pragma unroll
-            for (int jj = 0; jj < KC; jj += 4) {
+            for (int jj = 0; jj < KOUT; jj += 4) {
                 int4 v;
                 v.x = (jj + 0 < cnt) ? buf_i[(jj + 0) * LD + col] : -1;
                 v.y = (jj + 1 < cnt) ? buf_i[(jj + 1) * LD + col] : -1;
@@ -614,6 +615,9 @@ int g_tc_debug = 0;  // timing experiments only (set through the "tc_debug" opti
 //   ns = 2: two streams of KCS = 8 candidates (CAP 16) per query, 16 scanner warps -- k (+1) <= 8
 //   ns = 1: one stream of 16 candidates (CAP 32), 8 scanner warps              -- k (+1) <= 14
 static constexpr int TC_MT = 2;
+#ifndef SK_TC_KCS
+#define SK_TC_KCS 8   // candidates kept per stream of the dual-stream layout (<= 8)
+#endif
 
 size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns) {
     const size_t a = (size_t)kc_tot * TC_M * TC_ROWB, b = (size_t)kc_tot * TC_N * TC_ROWB;
@@ -658,7 +662,7 @@ cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, i
                              float *cand_thr, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
     if (ns == 2)
-        return launch_tc<8, TC_MT, 2, 16>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx,
+        return launch_tc<SK_TC_KCS, TC_MT, 2, 16>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx,
                                           cand_thr, st);
     if (ns == 1)
         return launch_tc<16, TC_MT, 1, 32>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx,
