@@ -321,14 +321,19 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    float a[11];
+    // group minima b0..b3 over v[0..9), v[9..18), v[18..27), v[27..32).  The fast path reduces each
+    // group through STRIDED triples (v[g], v[g+3], v[g+6]); the hit path below re-derives the
+    // minima of the CONTIGUOUS triples it descends into, so that those eleven values are not kept
+    // live (and spilled) across the fast path.
+    float b[4];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) a[i] = fminf(fminf(v[3 * i], v[3 * i + 1]), v[3 * i + 2]);
-    a[10] = fminf(v[30], v[31]);
-    const float b0 = fminf(fminf(a[0], a[1]), a[2]);     // v[0..9)
-    const float b1 = fminf(fminf(a[3], a[4]), a[5]);     // v[9..18)
-    const float b2 = fminf(fminf(a[6], a[7]), a[8]);     // v[18..27)
-    const float b3 = fminf(a[9], a[10]);                 // v[27..32)
+    for (int g = 0; g < 3; ++g) {
+        const float *w = v + 9 * g;
+        b[g] = fminf(fminf(fminf(fminf(w[0], w[3]), w[6]), fminf(fminf(w[1], w[4]), w[7])),
+                     fminf(fminf(w[2], w[5]), w[8]));
+    }
+    b[3] = fminf(fminf(fminf(v[27], v[29]), v[31]), fminf(v[28], v[30]));
+    const float b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3];
     const float m = fminf(fminf(b0, b1), fminf(b2, b3));
     bool hit = m < thr;
     const unsigned hits = __ballot_sync(SK_FULL, hit);
@@ -351,7 +356,7 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
         int *pi = buf_i + col + cnt * LD;
         // descend the tree: group of <= 9 values -> triple -> values; every triple needs 3 free slots
 #define SK_TC_TRIPLE(I, N)                                                      \
-        if (a[I] < thr) {                                                       \
+        if (fminf(fminf(v[3 * (I)], v[3 * (I) + 1]), v[3 * (I) + ((N) == 3 ? 2 : 1)]) < thr) { \
             if (cnt > CAP - 3) over = true;                                     \
             else tc_leaf<N, LD>(v + 3 * (I), idb + 3 * (I), thr, ps, pi, cnt);  \
         }
