@@ -102,10 +102,12 @@ __device__ __forceinline__ long long shfl_xor_any<long long>(long long v, int m)
     return __shfl_xor_sync(SK_FULL, v, m);
 }
 
-template <typename K>
+// SIZE < 32 sorts every aligned group of SIZE lanes on its own (fewer network stages when only the
+// first SIZE lanes hold entries)
+template <typename K, int SIZE = 32>
 __device__ __forceinline__ void warp_sort_pairs(K &key, int &id, int lane) {
 #pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
+    for (int size = 2; size <= SIZE; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             K ok = shfl_xor_any<K>(key, stride);
@@ -290,6 +292,29 @@ struct FinishParams {
     double *out_pred;   // [n_q, n_out]
 };
 
+template <int SIZE>
+__device__ __forceinline__ void det_sort(double &key, long long &sec, double &dist, int lane) {
+#pragma unroll
+    for (int size = 2; size <= SIZE; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            double ok = __shfl_xor_sync(SK_FULL, key, stride);
+            long long os = __shfl_xor_sync(SK_FULL, sec, stride);
+            double od = __shfl_xor_sync(SK_FULL, dist, stride);
+            bool lower = (lane & stride) == 0;
+            bool asc = (lane & size) == 0;
+            bool other_less = (ok < key) || (ok == key && os < sec);
+            bool same = (ok == key && os == sec);
+            bool take = (lower == asc) ? other_less : (!other_less && !same);
+            if (take) {
+                key = ok;
+                sec = os;
+                dist = od;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void finish_query(const FinishParams &p, long long q, double dist,
                                              int id, int lane) {
     if (p.row_map) q = p.row_map[q];
@@ -323,26 +348,14 @@ __device__ __forceinline__ void finish_query(const FinishParams &p, long long q,
         // sort by (key, diff, id): fold (diff, id) into one 64-bit secondary key.  ids and
         // diffs are < 2^31 for any index this library accepts.
         long long sec = (lane < p.k) ? ((diff << 31) | (long long)id) : 0x7fffffffffffffffLL;
-        // bitonic network on (key, sec) carrying dist
-#pragma unroll
-        for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                double ok = __shfl_xor_sync(SK_FULL, key, stride);
-                long long os = __shfl_xor_sync(SK_FULL, sec, stride);
-                double od = __shfl_xor_sync(SK_FULL, dist, stride);
-                bool lower = (lane & stride) == 0;
-                bool asc = (lane & size) == 0;
-                bool other_less = (ok < key) || (ok == key && os < sec);
-                bool same = (ok == key && os == sec);
-                bool take = (lower == asc) ? other_less : (!other_less && !same);
-                if (take) {
-                    key = ok;
-                    sec = os;
-                    dist = od;
-                }
-            }
-        }
+        // bitonic network on (key, sec) carrying dist; only the first k lanes hold entries, so the
+        // network spans the next power of two >= k
+        if (p.k <= 8)
+            det_sort<8>(key, sec, dist, lane);
+        else if (p.k <= 16)
+            det_sort<16>(key, sec, dist, lane);
+        else
+            det_sort<32>(key, sec, dist, lane);
         id = (int)(sec & 0x7fffffffLL);
     }
     if (lane < p.k) {

@@ -75,6 +75,7 @@ refine_kernel(RefineArgs a, FinishParams fp) {
     // 16 lanes read consecutive features, so a pass touches two lines of L2 instead of 32) and
     // reduces with a 16-lane butterfly; lane (i & 15) of the half warp keeps the result of pass i.
     const int half = lane >> 4, hl = lane & 15;
+    const bool small = a.kc <= 16;      // lists of <= 16: candidate l ends up in lane l (16-lane sort)
     int id = 0x7fffffff;
     double d2 = SK_INF_D;
     const int my_c = lane < a.kc ? a.cand_idx[q * a.kc + lane] : -1;   // kc <= 32: one coalesced load
@@ -85,7 +86,13 @@ refine_kernel(RefineArgs a, FinishParams fp) {
         double acc = 0.0;
         if (have) acc = dist2_lane(zq, a.ref64 + (long long)c * a.d, a.d, hl);
         acc = dist2_reduce16(acc);
-        if (have && hl == (i & 15)) {
+        if (small) {
+            const double other = __shfl_xor_sync(SK_FULL, acc, 16);   // the other half warp's candidate
+            if ((lane >> 1) == i && lane < 16 && my_c >= 0 && my_c < a.n_ref) {
+                id = my_c;
+                d2 = (lane & 1) == half ? acc : other;
+            }
+        } else if (have && hl == (i & 15)) {
             id = c;
             d2 = acc;
         }
@@ -99,7 +106,10 @@ refine_kernel(RefineArgs a, FinishParams fp) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(SK_FULL, qn, o);
 
-    warp_sort_pairs<double>(d2, id, lane);
+    if (small)
+        warp_sort_pairs<double, 16>(d2, id, lane);
+    else
+        warp_sort_pairs<double, 32>(d2, id, lane);
 
     const int kk = fp.k + (fp.exclude_self ? 1 : 0);
     const double kth = __shfl_sync(SK_FULL, d2, kk - 1);
