@@ -367,20 +367,26 @@ def run_ours(a, rank, world, local_rank):
     hbm = {"algorithmic_bytes_per_step": n_q * (8 * d + k * 16 + 8 * n_out) + 4 * a.n_ref * dpad,
            "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"}
     if engine == L.ENGINE_TENSOR:
-        # tcgen05 kind::tf32 runs at half the bf16 rate: peak = measured cuBLAS bf16 burst / 2
-        bf16 = peaks.get("bf16_tflops", 1590.0)
+        # tcgen05 kind::tf32 runs at half the bf16 rate; the launches are timed inside a long,
+        # power-capped step, so the denominator is the SUSTAINED cuBLAS bf16 figure / 2
+        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
         tf32_peak = bf16 / 2.0
         roofline = {
             "kernel": "search_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": tf32_peak,
             "unit": "TFLOP/s", "frac": (achieved / tf32_peak) if achieved else None,
-            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst) / 2 = dense TF32" if peaks
-                            else "fallback 1590 bf16 / 2 (B200_PROFILING.md)"),
-            "traffic": None, "algorithmic_flops_per_launch": flops / n_chunks,
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 = dense TF32, of measured" if peaks
+                            else "fallback 1400 bf16 sustained / 2 (B200_PROFILING.md), of fallback"),
+            # dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-row launch, ncu --set full
+            # (profiles/r01_search_tc_v9.md); scaled to this run's rows per launch
+            "traffic": 237.3e6 * (n_q / n_chunks) / float(1 << 20) if d == 32 else None,
+            "algorithmic_flops_per_launch": flops / n_chunks,
             "launches_per_step": n_chunks, "kernel_ms_per_step": search_ms,
             "fp32_simt_peak_measured": fp32_peak,
-            "note": "algorithmic FLOPs 2*d'*n_q*n_ref; the kernel also spends 8 extra K per pair "
-                    "folding |r|^2 into the MMA and is paced by its TMEM epilogue (one compare "
-                    "per pair), not by the tensor pipe", "hbm": hbm,
+            "note": "algorithmic FLOPs 2*d'*n_q*n_ref over the CUDA-event time of the search kernel "
+                    "launches of one device-resident step; the kernel executes (d'+8)/d' of them (|r|^2 "
+                    "folded into the MMA) plus a 25 % threshold-seeding pre-pass, and is paced by its "
+                    "TMEM epilogue (thread <-> query min tree + hit path), see DESIGN.md section 4",
+            "hbm": hbm,
         }
     else:
         roofline = {

@@ -85,9 +85,15 @@ int sknnr_device_count(int *count);
  *   "engine"      SKNNR_ENGINE_*           (default AUTO)
  *   "chunk_rows"  rows per internal chunk  (default 1<<20)
  *   "timing"      0/1 record search_ms     (default 0)
- *   "kc"          0/8/16/32 minimum length of the float search's candidate list (default 16); 0 picks
- *                 the smallest list that holds k+1 (longer lists = fewer certificate
- *                 failures, more insertions)                                          */
+ *   "kc"          0/8/16/32 minimum length of the FP32 (SIMT) search's candidate list (default 16);
+ *                 0 picks the smallest list that holds k+1 (longer lists = fewer certificate
+ *                 failures, more insertions)
+ *   "tc_streams"  0/1/2 candidate streams per query of the tensor engine (default 0 = two
+ *                 streams of 8 while k (+1) <= 8, else one of 16)
+ *   "tc_seed_stride" 0..64: the tensor engine pre-scans one reference tile in n to seed its
+ *                 thresholds (default 4; 0 = off)
+ *   "tc_debug"    timing experiments only (bit 0 skips the hit path, bit 2 skips the tile
+ *                 loads: results are wrong)                                             */
 int sknnr_set_option(const char *name, int64_t value);
 
 /* ---- Euclidean-space index: Raw / Euclidean / Mahalanobis / MSN / GNN ------------------

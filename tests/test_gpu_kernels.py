@@ -273,3 +273,65 @@ def test_hamming_synthetic_bit_exact(n_ref, n_q, T, k, n_codes):
     d_g, i_g, _ = ix.query(Q.astype(np.uint16), k)
     np.testing.assert_array_equal(i_g, i_o)
     assert np.array_equal(d_g, d_o)
+
+
+@pytest.mark.parametrize(("streams", "seed_stride", "k", "exclude_self"), [
+    (2, 4, 7, False), (2, 0, 7, False), (2, 2, 5, True), (1, 4, 7, False), (1, 8, 12, False),
+    (2, 4, 7, True),
+])
+def test_tensor_engine_configurations_match_oracle(streams, seed_stride, k, exclude_self):
+    """The tensor engine's knobs (candidate streams per query, threshold-seeding stride) only change
+    how the filter works, never the result: every configuration equals the oracle and the
+    exhaustive float64 engine bit for bit.  12k plots = 94 reference tiles, enough for seeding."""
+    from sknnr_b200 import _lib as L
+
+    R, Q, y = _synthetic(12000, 1300, 32, seed=5)
+    st = orc.FittedState("euclidean", fit_Z=R, y=y)
+    ix = _index(st)
+    Qx = None if exclude_self else Q
+    d_o, i_o = orc.kneighbors(st, Qx, k=k, transformed=True)
+    L.set_option("tc_streams", streams)
+    L.set_option("tc_seed_stride", seed_stride)
+    L.set_option("engine", L.ENGINE_TENSOR)
+    try:
+        d_g, i_g, _ = ix.query(Qx, k, transformed=True, exclude_self=exclude_self)
+        assert ix.stats()["engine"] == L.ENGINE_TENSOR
+        L.set_option("engine", L.ENGINE_EXACT)
+        d_e, i_e, _ = ix.query(Qx, k, transformed=True, exclude_self=exclude_self)
+    finally:
+        L.set_option("engine", L.ENGINE_AUTO)
+        L.set_option("tc_streams", 0)
+        L.set_option("tc_seed_stride", 4)
+    orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=RTOL, atol=1e-7)
+    np.testing.assert_array_equal(i_g, i_e)
+    np.testing.assert_array_equal(d_g, d_e)
+
+
+def test_tensor_engine_duplicates_and_queries_on_plots():
+    """Adversarial parity set of SURVEY.md section 8(d): duplicated reference rows (exact ties ->
+    lowest index), queries equal to references (zero distances -> indicator weights) and a
+    constant-offset feature; the tie rows must come out of the cascade's exact stage identical
+    to the oracle."""
+    rng = np.random.default_rng(9)
+    R = rng.standard_normal((9000, 16))
+    R[:, 3] += 500.0
+    R[4000:4500] = R[:500]                       # 500 duplicated plots
+    off = np.zeros(16)
+    off[3] = 500.0
+    Q = np.vstack([R[rng.integers(0, 9000, 400)], rng.standard_normal((400, 16)) + off])
+    y = rng.standard_normal((9000, 3))
+    st = orc.FittedState("euclidean", fit_Z=R, y=y)
+    ix = _index(st)
+    d_o, i_o = orc.kneighbors(st, Q, k=7, transformed=True)
+    d_g, i_g, p_g = ix.query(Q, 7, transformed=True, weights="distance", with_pred=True)
+    # (the reference's float64 expansion returns ~1e-5 instead of 0 for a query that IS a plot with
+    # a feature offset of 500; ours is exactly 0 -> absolute floor from the operand norms)
+    orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=RTOL, atol=_atol(st))
+    assert (d_g[:400, 0] == 0.0).all()
+    same = (i_g == i_o).all(axis=1) & (d_o[:, 0] > 1e-3)
+    p_o = orc.weighted_average(y, i_o, orc.get_weights(d_o, "distance"))
+    np.testing.assert_allclose(p_g[same], p_o[same], rtol=RTOL, atol=1e-8)
+    # zero-distance rows: indicator weights on the coincident plot(s), $SP/sklearn/neighbors/_base.py:107-114
+    assert np.isfinite(p_g).all()
+    w = (d_g[:400] == 0.0).astype(float)
+    np.testing.assert_allclose(p_g[:400], orc.weighted_average(y, i_g[:400], w), rtol=1e-12, atol=1e-12)
