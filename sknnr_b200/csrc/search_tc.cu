@@ -393,9 +393,9 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
 // BEFORE any of them is reduced, so the MMAs of the slot's next job overlap the reduction and a
 // slow hit path never holds TMEM.
 template <int CH, class F>
-__device__ __forceinline__ void tc_epi_job(uint32_t (&R)[CH][32], uint32_t tcol, uint64_t *afull_bar,
-                                           uint32_t parity, uint64_t *aempty_bar, int lane, F &&proc) {
-    mbar_wait(afull_bar, parity);
+__device__ __forceinline__ void tc_epi_job(uint32_t (&R)[CH][32], uint32_t tcol, uint32_t afull_addr,
+                                           uint32_t parity, uint32_t aempty_addr, int lane, F &&proc) {
+    mbar_wait_addr(afull_addr, parity);
     tc_fence_after();
     uint32_t dep = 0;
 #pragma unroll
@@ -404,7 +404,7 @@ __device__ __forceinline__ void tc_epi_job(uint32_t (&R)[CH][32], uint32_t tcol,
     for (int c = 0; c < CH; ++c) tmem_ld_wait(R[c]);
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(aempty_bar);
+    if (lane == 0) mbar_arrive_addr(aempty_addr);
     if constexpr (CH >= 1) proc(R[0], std::integral_constant<int, 0>{});
     if constexpr (CH >= 2) proc(R[1], std::integral_constant<int, 1>{});
     if constexpr (CH >= 3) proc(R[2], std::integral_constant<int, 2>{});
@@ -547,6 +547,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         int cnt = 0;
         uint32_t R[CH][32];
         int t = 0;                            // position in the tile sequence; this warp's job = t * MT + h
+        const uint32_t afull_a0 = smem_u32(afull), aempty_a0 = smem_u32(aempty);
 
         // ---- seeding pass: group minima over the sampled tiles ----
         // (the 32 running minima live in the still unused candidate buffer column: slots of
@@ -559,7 +560,8 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             for (; t < n_seed; ++t) {
                 const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
                 const int g0 = (t * CH) & (TC_GROUPS - 1);
-                tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), &afull[sl], (j >> 2) & 1, &aempty[sl], lane,
+                tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), afull_a0 + 8u * sl, (uint32_t)((j >> 2) & 1),
+                               aempty_a0 + 8u * sl, lane,
                                [&](const uint32_t (&r)[32], auto ic) {
                                    constexpr int c = decltype(ic)::value;
                                    float *g = gcol + (g0 + c) * LD;
@@ -577,7 +579,8 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         for (; t < n_seq; ++t) {
             const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
             const int idb = (t - n_seed) * TC_N + p * CH * 32;
-            tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), &afull[sl], (j >> 2) & 1, &aempty[sl], lane,
+            tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), afull_a0 + 8u * sl, (uint32_t)((j >> 2) & 1),
+                               aempty_a0 + 8u * sl, lane,
                            [&](const uint32_t (&r)[32], auto ic) {
                                constexpr int c = decltype(ic)::value;
                                tc_process<KC, CAP, LD>(r, idb + c * 32, buf_s, buf_i, scratch, col, lane, thr,
