@@ -296,15 +296,19 @@ __device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, float *buf_s, int
 // in-lane append of the values of v[0..N) below thr (references id0 ..), N <= 3: every value is
 // stored at the lane's next free slot and the slot only advances for the values that qualify, so
 // there is no branch per value.  The caller guarantees N free slots.
-template <int N, int LD>
-__device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, float *&ps, int *&pi, int &cnt) {
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// `ps` = shared-memory address of the lane's next free score slot (the index slot lies IOFF bytes
+// further); see the comment above for the protocol
+template <int N, int LD, int IOFF>
+__device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, uint32_t &ps, int &cnt) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        *ps = v[j];
-        *pi = id0 + j;
+        st_shared_b32(ps, __float_as_uint(v[j]));
+        st_shared_b32(ps + IOFF, (uint32_t)(id0 + j));
         if (v[j] < thr) {
-            ps += LD;
-            pi += LD;
+            ps += LD * 4;
             ++cnt;
         }
     }
@@ -314,9 +318,10 @@ __device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, floa
 // idb .. idb+31.  Fast path: min3 tree + one vote.  Hit path, in the hit lanes only and without
 // any cross-lane traffic: the tree's intermediate minima (four groups of <= 9 values) locate the
 // values below the threshold, which the lane appends to its own candidate buffer column.
-template <int KC, int CAP, int LD>
+// `cs0` = shared-memory address of slot 0 of this thread's candidate column.
+template <int KC, int CAP, int LD, bool DBG>
 __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, float *buf_s, int *buf_i,
-                                           float *scratch, int col, int lane, float &thr, int &cnt,
+                                           float *scratch, uint32_t cs0, int lane, float &thr, int &cnt,
                                            int dbg) {
     float v[32];
 #pragma unroll
@@ -338,12 +343,13 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
     bool hit = m < thr;
     const unsigned hits = __ballot_sync(SK_FULL, hit);
     if (hits == 0u) return;
-    if (dbg & 1) {  // timing experiment: count the hits, skip the hit path (results are wrong)
+    if (DBG && (dbg & 1)) {  // timing experiment: count the hits, skip the hit path (results are wrong)
         cnt = (cnt + __popc(hits)) & 7;
         return;
     }
     // keep room for the usual one or two appends; compaction also refreshes the thresholds
     if (__any_sync(SK_FULL, hit && cnt > CAP - 3)) {
+        const int col = threadIdx.x;
         const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + col, buf_i + col, thr, cnt);
         thr = tc.thr;
         cnt = tc.cnt;
@@ -352,13 +358,12 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
     const int cnt0 = cnt;
     bool over = false;
     if (hit) {
-        float *ps = buf_s + col + cnt * LD;
-        int *pi = buf_i + col + cnt * LD;
+        uint32_t ps = cs0 + (uint32_t)(cnt * LD * 4);
         // descend the tree: group of <= 9 values -> triple -> values; every triple needs 3 free slots
 #define SK_TC_TRIPLE(I, N)                                                      \
         if (fminf(fminf(v[3 * (I)], v[3 * (I) + 1]), v[3 * (I) + ((N) == 3 ? 2 : 1)]) < thr) { \
             if (cnt > CAP - 3) over = true;                                     \
-            else tc_leaf<N, LD>(v + 3 * (I), idb + 3 * (I), thr, ps, pi, cnt);  \
+            else tc_leaf<N, LD, CAP * LD * 4>(v + 3 * (I), idb + 3 * (I), thr, ps, cnt);  \
         }
         if (b0 < thr) { SK_TC_TRIPLE(0, 3) SK_TC_TRIPLE(1, 3) SK_TC_TRIPLE(2, 3) }
         if (b1 < thr) { SK_TC_TRIPLE(3, 3) SK_TC_TRIPLE(4, 3) SK_TC_TRIPLE(5, 3) }
@@ -381,7 +386,8 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
                 for (int i = 0; i < 8; ++i) sc[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
             __syncwarp();
-            const ThrCnt tc = tc_process_coop<KC, CAP, LD>(L, idb, buf_s, buf_i, scratch, col, lane, thr, cnt);
+            const ThrCnt tc = tc_process_coop<KC, CAP, LD>(L, idb, buf_s, buf_i, scratch, (int)threadIdx.x, lane,
+                                                           thr, cnt);
             thr = tc.thr;
             cnt = tc.cnt;
         }
@@ -413,7 +419,7 @@ __device__ __forceinline__ void tc_epi_job(uint32_t (&R)[CH][32], uint32_t tcol,
 
 // (register budget: the register file is allocated per 4 warps, so the 18-warp dual-stream CTA
 // gets 65536 / (20 * 32) = 102 -> 96 registers per thread and the 10-warp one 168)
-template <int KC, int MT, int NS, int CAP>
+template <int KC, int MT, int NS, int CAP, bool DBG>
 __global__ void __launch_bounds__(TcCfg<MT, NS, CAP>::THREADS, 1)
 search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int kc_tot,
                  int n_rtiles, int nstage, int n_seed, int seed_stride, long long n_q,
@@ -471,7 +477,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             for (int tn = 0; tn < n_seq; ++tn) {
                 if (wrapped) mbar_wait(&empty[sn], wrap_par);
                 const int tile = tn < n_seed ? tn * seed_stride : tn - n_seed;
-                if ((dbg & 4) && wrapped) {
+                if (DBG && (dbg & 4) && wrapped) {
                     mbar_arrive(&full[sn]);   // timing experiment: reuse the stale tile, no L2 traffic
                 } else {
                     mbar_expect_tx(&full[sn], b_bytes);
@@ -548,6 +554,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         uint32_t R[CH][32];
         int t = 0;                            // position in the tile sequence; this warp's job = t * MT + h
         const uint32_t afull_a0 = smem_u32(afull), aempty_a0 = smem_u32(aempty);
+        const uint32_t cs0 = smem_u32(buf_s + col);
 
         // ---- seeding pass: group minima over the sampled tiles ----
         // (the 32 running minima live in the still unused candidate buffer column: slots of
@@ -583,7 +590,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
                                aempty_a0 + 8u * sl, lane,
                            [&](const uint32_t (&r)[32], auto ic) {
                                constexpr int c = decltype(ic)::value;
-                               tc_process<KC, CAP, LD>(r, idb + c * 32, buf_s, buf_i, scratch, col, lane, thr,
+                               tc_process<KC, CAP, LD, DBG>(r, idb + c * 32, buf_s, buf_i, scratch, cs0, lane, thr,
                                                        cnt, dbg);
                            });
         }
@@ -648,20 +655,33 @@ int search_tc_seed_tiles(int n_rtiles, int seed_stride) {
     return (n_rtiles + seed_stride - 1) / seed_stride;
 }
 
-template <int KC, int MT, int NS, int CAP>
-static cudaError_t launch_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles, int nstage,
-                             int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
-                             cudaStream_t st) {
+template <int KC, int MT, int NS, int CAP, bool DBG>
+static cudaError_t launch_tc_dbg(const float *qimg, const float *rimg, int kc_tot, int n_rtiles, int nstage,
+                                 int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
+                                 cudaStream_t st) {
     using Cfg = TcCfg<MT, NS, CAP>;
     const size_t smem = search_tc_smem_bytes(kc_tot, nstage, NS);
-    cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC, MT, NS, CAP>,
+    cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC, MT, NS, CAP, DBG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const long long n_qtiles = (n_q + Cfg::QT - 1) / Cfg::QT;
     const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride);
-    search_tc_kernel<KC, MT, NS, CAP><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
+    search_tc_kernel<KC, MT, NS, CAP, DBG><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
         qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, seed_stride, n_q, cand_idx, cand_thr, g_tc_debug);
     return cudaGetLastError();
+}
+
+template <int KC, int MT, int NS, int CAP>
+static cudaError_t launch_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles, int nstage,
+                             int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
+                             cudaStream_t st) {
+    // the timing-experiment hooks ("tc_debug") live in a separate instantiation: none of their
+    // tests is compiled into the product kernel
+    if (g_tc_debug)
+        return launch_tc_dbg<KC, MT, NS, CAP, true>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
+                                                    cand_idx, cand_thr, st);
+    return launch_tc_dbg<KC, MT, NS, CAP, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
+                                                 cand_idx, cand_thr, st);
 }
 
 // cand_idx [n_q][16] (ns lists of 16 / ns entries), cand_thr [n_q][ns]
