@@ -1,5 +1,3 @@
 set -x
-timeout 300 python scripts/tc_smoke.py > gpurun_out/tc_smoke.log 2>&1; echo tc_smoke_exit=$?; grep -c OK gpurun_out/tc_smoke.log; grep -v OK gpurun_out/tc_smoke.log | tail -5
-B="python bench.py --steps 1 --warmup 1 --n-queries 1048576 --no-cpu-baseline --no-e2e"
-timeout 300 $B > gpurun_out/bench_ns2.log 2>&1; grep -o '"kernel_ms_per_step": [0-9.]*\|"ms_per_step": [0-9.]*\|"fallback_rows_per_step": [0-9]*' gpurun_out/bench_ns2.log | tr '\n' ' '; echo
-timeout 300 $B --tc-debug 1 > gpurun_out/bench_dbg.log 2>&1; grep -o '"kernel_ms_per_step": [0-9.]*' gpurun_out/bench_dbg.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$?; tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --no-cpu-baseline --steps 2 > gpurun_out/bench_default.log 2>&1; echo bench_exit=$?; grep -o '"value": [0-9.]*\|"kernel_ms_per_step": [0-9.]*\|"ms_per_step": [0-9.]*\|"fallback_rows_per_step": [0-9]*\|"frac": [0-9.]*' gpurun_out/bench_default.log | tr '\n' ' '; echo

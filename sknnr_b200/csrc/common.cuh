@@ -368,9 +368,16 @@ __device__ __forceinline__ void finish_query(const FinishParams &p, long long q,
         // sort by (key, diff, id): fold (diff, id) into one 64-bit secondary key.  ids and
         // diffs are < 2^31 for any index this library accepts.
         long long sec = (lane < p.k) ? ((diff << 31) | (long long)id) : 0x7fffffffffffffffLL;
+        // The lanes arrive sorted by (dist, id) and the key is monotone in dist, so the order can
+        // only change inside a group of equal rounded keys: skip the network unless some
+        // neighbouring pair is out of (key, sec) order (rare: ties to `decimals` digits).
+        const double pk = __shfl_up_sync(SK_FULL, key, 1);
+        const long long ps = __shfl_up_sync(SK_FULL, sec, 1);
+        const bool out_of_order = lane > 0 && lane < p.k && (key < pk || (key == pk && sec < ps));
         // bitonic network on (key, sec) carrying dist; only the first k lanes hold entries, so the
         // network spans the next power of two >= k
-        if (p.k <= 8)
+        if (!__any_sync(SK_FULL, out_of_order)) {
+        } else if (p.k <= 8)
             det_sort<8>(key, sec, dist, lane);
         else if (p.k <= 16)
             det_sort<16>(key, sec, dist, lane);
