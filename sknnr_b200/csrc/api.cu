@@ -140,7 +140,7 @@ struct IndexBase {
     std::mutex lock;
     // chunks rotate through the slots (own stream + buffers each): H2D of one chunk, kernels of
     // another and D2H of a third overlap; a device-pointer call alternates the first two
-    static constexpr int kSlots = 4;
+    static constexpr int kSlots = 8;
     Slot slots[kSlots];
     int exact_grid = 0;
     sknnr_stats stats{};
@@ -635,9 +635,22 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
 
     cudaStream_t user_stream = (cudaStream_t)stream;
     const int64_t chunk = std::min<int64_t>(g_opt.chunk_rows, (n_q + 255) / 256 * 256);
+    // Host buffers: the first chunk's H2D copy and the last chunk's D2H copy cannot overlap any
+    // kernel, so the stream of chunks ramps up (1/4, 1/2, 1, ...) and down (..., 1/2, 1/4).
+    const bool ramp = !dev_ptrs && n_q >= 4 * chunk && chunk % 1024 == 0;
     int ci = 0;
-    for (int64_t r0 = 0; r0 < n_q; r0 += chunk, ++ci) {
-        const int64_t rows = std::min(chunk, n_q - r0);
+    int64_t rows = 0;
+    for (int64_t r0 = 0; r0 < n_q; r0 += rows, ++ci) {
+        rows = std::min(chunk, n_q - r0);
+        if (ramp) {
+            const int64_t left = n_q - r0, q4 = chunk / 4;
+            if (ci == 0) rows = q4;
+            else if (ci == 1) rows = 2 * q4;
+            else if (left > chunk + 3 * q4) rows = chunk;
+            else if (left > 3 * q4) rows = left - 3 * q4;   // leaves 1/2 + 1/4 for the last two
+            else if (left > q4) rows = left - q4;
+            else rows = left;
+        }
         // two slots alternate: the tail of chunk c (on its slot's tail stream) overlaps the first
         // stage of chunk c + 1 (other slot's buffers)
         Slot &s = ix->slots[dev_ptrs ? (ci & 1) : (ci % IndexBase::kSlots)];
