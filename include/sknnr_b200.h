@@ -64,6 +64,7 @@ extern "C" {
 
 typedef struct sknnr_index sknnr_index;           /* Euclidean-space estimators */
 typedef struct sknnr_hamming_index sknnr_hamming_index; /* RFNN node-ID estimators    */
+typedef struct sknnr_forest sknnr_forest;               /* fitted forests of an RFNodeTransformer */
 
 /* counters of the last query call on a handle (all int64) */
 typedef struct sknnr_stats {
@@ -174,6 +175,37 @@ int sknnr_hamming_weighted_average(sknnr_hamming_index *index, const int64_t *id
                                    const double *w, int64_t n_q, int32_t k,
                                    double *out_pred);
 int sknnr_hamming_index_stats(sknnr_hamming_index *index, sknnr_stats *out);
+
+/* ---- Forests: RFNodeTransformer.transform on the device (scope row f1) -------------------
+ * Replaces ref:src/sknnr/transformers/_tree_node_transformer.py:177-201 (est.apply per forest,
+ * hstack) -> $SP/sklearn/tree/_tree.pyx:977-994 (Tree._apply_dense): X is cast to float32, an
+ * internal node sends a row left iff (double)x[feature] <= threshold, NaN follows
+ * missing_go_to_left, a node with children_left == -1 is a leaf.
+ *
+ * All trees of all forests are concatenated in transform's column order:
+ *   tree_offsets [n_trees + 1] first node of every tree in the arrays below
+ *   children_left / children_right / feature / threshold / missing_go_to_left [n_nodes]:
+ *             scikit-learn's tree_ arrays (child indices local to their tree, -1 = leaf;
+ *             missing_go_to_left may be NULL)
+ *   node_code [n_nodes] u16 or NULL: the node code the Hamming index uses for each (leaf)
+ *             node, 31743 = "matches nothing"; NULL = the node ID itself                    */
+int sknnr_forest_create(const int32_t *tree_offsets, const int32_t *children_left,
+                        const int32_t *children_right, const int32_t *feature,
+                        const double *threshold, const uint8_t *missing_go_to_left,
+                        const uint16_t *node_code, int32_t n_trees, int32_t n_features,
+                        int32_t device, sknnr_forest **out);
+int sknnr_forest_destroy(sknnr_forest *forest);
+/* Node IDs (per tree, as est.apply returns them) of host rows X [n_q, >= n_features]. */
+int sknnr_forest_apply(sknnr_forest *forest, const void *X, int32_t x_dtype, int64_t n_q,
+                       int64_t ldx, int32_t *out_ids);
+/* sknnr_hamming_kneighbors on raw feature rows: forest walk -> node codes -> Hamming search
+ * without leaving the device.  X [n_q, ldx] of x_dtype (host, or device with
+ * SKNNR_DEVICE_PTRS); every other argument as in sknnr_hamming_kneighbors.                  */
+int sknnr_hamming_kneighbors_forest(sknnr_hamming_index *index, sknnr_forest *forest,
+                                    const void *X, int32_t x_dtype, int64_t n_q, int64_t ldx,
+                                    int64_t row_offset, int32_t k, uint32_t flags,
+                                    int32_t decimals, double *out_dist, int64_t *out_idx,
+                                    int32_t weights, double *out_pred, void *stream);
 
 /* Pinned host memory for callers that stream large rasters (cudaHostAlloc / cudaFreeHost). */
 int sknnr_host_alloc(void **ptr, int64_t bytes);

@@ -23,5 +23,29 @@ def main(n_ref=20000, n_q=500000, T=500, k=7):
     print(f"hamming n_ref={n_ref} T={T} n_q={n_q} k={k}: e2e {n_q/dt/1e6:.3f} M queries/s ({dt*1e3:.1f} ms), "
           f"search kernel {st['search_ms']:.1f} ms = {n_q*n_ref*T/st['search_ms']/1e9:.1f} T id-compares/s, stats {st}")
 
+def forest_main(n_ref=20000, n_q=1000000, d=16, n_targets=10, n_estimators=50, k=7):
+    """BASELINE.md C4 recipe at reduced query count: RFNNRegressor(n_estimators=50) on 10 targets
+    (T = 500 trees), raw feature rows in, neighbours out: forest walk + Hamming search fused."""
+    import sknnr_b200 as S
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((n_ref, d))
+    y = X[:, :n_targets] * 2 + np.random.default_rng(1).standard_normal((n_ref, n_targets))
+    Q = np.random.default_rng(2).standard_normal((n_q, d))
+    t0 = time.perf_counter()
+    est = S.RFNNRegressor(n_estimators=n_estimators, n_neighbors=k, random_state=0, n_jobs=-1).fit(X, y)
+    print(f"fit (scikit-learn forest training + device self-query): {time.perf_counter()-t0:.1f} s", flush=True)
+    tr = est.transformer_
+    tr.transform(Q[:20000])
+    t0 = time.perf_counter(); ids = tr.transform(Q[:200000]); dt = time.perf_counter() - t0
+    print(f"device forest walk (transform, ids to host): {200000/dt/1e6:.2f} M rows/s x {ids.shape[1]} trees")
+    t0 = time.perf_counter(); want = np.hstack([e.apply(Q[:20000]) for e in tr.estimators_]); dt_cpu = time.perf_counter() - t0
+    print(f"scikit-learn est.apply on the host: {20000/dt_cpu/1e3:.1f} k rows/s; bit-equal: {np.array_equal(want, ids[:20000])}")
+    est.kneighbors(Q[:50000])
+    t0 = time.perf_counter(); dist, idx = est.kneighbors(Q); dt = time.perf_counter() - t0
+    print(f"RFNN kneighbors, raw rows in (fused forest walk + Hamming, n_ref={n_ref}, T={ids.shape[1]}): "
+          f"{n_q/dt/1e6:.3f} M queries/s, stats {est.regressor_._get_index().stats()}")
+
+
 if __name__ == "__main__":
     main()
+    forest_main()

@@ -151,9 +151,11 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
         return int(n_neighbors)
 
     def _search(self, X, n_neighbors, deterministic, *, raw=False, weights=None, with_pred=False,
-                return_distance=True):
+                return_distance=True, forest=None):
         """One device call.  ``raw=True``: X holds untransformed features and the projection is
-        fused in front (S2+S1[+S3]); otherwise X is already in the estimator's space."""
+        fused in front (S2+S1[+S3]); ``forest`` (a fitted tree-node transformer): X holds validated
+        raw features and the forest walk is fused in front of the Hamming search; otherwise X is
+        already in the estimator's space."""
         check_is_fitted(self)
         ix = self._get_index()
         query_is_train = X is None
@@ -162,6 +164,9 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
         if query_is_train:
             k = self._check_k(n_neighbors, True, self.n_samples_fit_)
             return ix.query(None, k, exclude_self=True, **kw)
+        if forest is not None:
+            k = self._check_k(n_neighbors, False, X.shape[0])
+            return ix.query_forest(forest._forest_index(self.__dict__.get("_node_tables")), X, k, **kw)
         if not raw:
             X = validate_data(self, X, ensure_all_finite=True, accept_sparse=False, reset=False, order="C")
         else:
@@ -189,13 +194,13 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
         return (dist, idx) if return_distance else idx
 
     # -- predict -----------------------------------------------------------------------
-    def _predict_impl(self, X, raw):
+    def _predict_impl(self, X, raw, forest=None):
         w = self.weights
         if w in (None, "uniform", "distance"):
             _, _, pred = self._search(X, None, True, raw=raw, weights=w, with_pred=True,
-                                      return_distance=False)
+                                      return_distance=False, forest=forest)
         else:  # callable: evaluated by Python on the distances, averaged on the device
-            dist, idx, _ = self._search(X, None, True, raw=raw)
+            dist, idx, _ = self._search(X, None, True, raw=raw, forest=forest)
             pred = self._get_index().weighted_average(idx, np.asarray(w(dist), dtype=np.float64))
         if self._y.ndim == 1:
             pred = pred.ravel()
@@ -243,6 +248,11 @@ class TransformedKNeighborsRegressor(BaseEstimator, ABC):
         """True when the transformer is an affine map the device fuses in front of the search."""
         return hasattr(self.transformer_, "_affine")
 
+    def _forest_fusable(self) -> bool:
+        """True when the transformer is a fitted forest the device walks in front of the Hamming
+        search (raw features -> node codes -> neighbours in one call)."""
+        return hasattr(self.transformer_, "_forest_index") and self.regressor_._metric_kind() == "hamming"
+
     def fit(self, X, y):
         validate_data(self, X=X, y=y, ensure_all_finite=True, multi_output=True)
         self._set_fitted_transformer(X, y)
@@ -277,6 +287,10 @@ class TransformedKNeighborsRegressor(BaseEstimator, ABC):
         """Same contract as ref:src/sknnr/_base.py:285-344."""
         check_is_fitted(self, "transformer_")
         reg = self.regressor_
+        if X is not None and self._forest_fusable():
+            dist, idx, _ = reg._search(self._validated_raw(X), n_neighbors, use_deterministic_ordering,
+                                       forest=self.transformer_, return_distance=return_distance)
+            return reg._finish_kneighbors(dist, idx, return_distance, return_dataframe_index)
         if X is None or not self._fusable():
             return reg.kneighbors(
                 X=self._transform_X(X), n_neighbors=n_neighbors, return_distance=return_distance,
@@ -288,6 +302,8 @@ class TransformedKNeighborsRegressor(BaseEstimator, ABC):
 
     def predict(self, X):
         check_is_fitted(self, "transformer_")
+        if X is not None and self._forest_fusable():
+            return self.regressor_._predict_impl(self._validated_raw(X), raw=False, forest=self.transformer_)
         if X is None or not self._fusable():
             return self.regressor_.predict(self._transform_X(X))
         return self.regressor_._predict_impl(self._validated_raw(X), raw=True)

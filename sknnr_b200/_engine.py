@@ -220,6 +220,28 @@ class HammingIndex(_IndexBase):
             _ptr(pred), None))
         return dist, idx, pred
 
+    def query_forest(self, forest, X, k, *, deterministic=True, decimals=10, row_offset=0,
+                     weights=None, with_pred=False, return_distance=True, return_index=True):
+        """kneighbors (+ predict) on RAW feature rows: forest walk -> node codes -> Hamming
+        search in one device call (sknnr_hamming_kneighbors_forest)."""
+        X = np.asarray(X)
+        if X.dtype != np.float32:
+            X = np.asarray(X, dtype=np.float64)
+        X = np.ascontiguousarray(X)
+        if X.ndim != 2 or X.shape[1] != forest.n_features:
+            raise ValueError(f"X has {X.shape[1] if X.ndim == 2 else '?'} features, but "
+                             f"{forest.n_features} are expected")
+        n_q = X.shape[0]
+        mode = _weights_mode(weights, with_pred)
+        dist = np.empty((n_q, k), dtype=np.float64) if return_distance else None
+        idx = np.empty((n_q, k), dtype=np.int64) if return_index else None
+        pred = np.empty((n_q, self.n_out), dtype=np.float64) if mode != L.W_NONE else None
+        L.check(self._lib.sknnr_hamming_kneighbors_forest(
+            self._h, forest._h, _ptr(X), L.F32 if X.dtype == np.float32 else L.F64, n_q, X.shape[1],
+            int(row_offset), int(k), self._flags(False, deterministic), int(decimals), _ptr(dist),
+            _ptr(idx), mode, _ptr(pred), None))
+        return dist, idx, pred
+
     def query_device(self, q_ptr, n_q, ldq, k, *, dist_ptr=0, idx_ptr=0, pred_ptr=0, weights=None,
                      deterministic=True, decimals=10, row_offset=0, stream=0):
         mode = _weights_mode(weights, bool(pred_ptr))
@@ -236,3 +258,66 @@ class HammingIndex(_IndexBase):
         L.check(self._lib.sknnr_hamming_weighted_average(self._h, _ptr(idx), _ptr(w), idx.shape[0],
                                                          idx.shape[1], _ptr(out)))
         return out
+
+
+class ForestIndex:
+    """Device copy of the fitted trees of an ``RFNodeTransformer`` (all forests, concatenated in
+    ``transform``'s column order): scikit-learn's ``tree_`` arrays flattened, plus the 16-bit
+    node code the Hamming index uses for every node.  Serves ``transform`` (node IDs) and the
+    fused raw-features -> neighbours call of :class:`HammingIndex`."""
+
+    def __init__(self, trees, n_features, node_code_tables=None, device=None):
+        """``trees``: scikit-learn ``Tree`` objects (``est.tree_``) in column order;
+        ``node_code_tables``: per tree, the sorted node IDs that map to codes 0, 1, ... (None =
+        the node ID is its own code)."""
+        self._h = C.c_void_p(None)
+        self._lib = L.load()
+        self.n_trees = len(trees)
+        self.n_features = int(n_features)
+        offs = np.zeros(self.n_trees + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([t.node_count for t in trees])
+        cat = lambda name, dt: np.ascontiguousarray(np.concatenate([np.asarray(getattr(t, name)) for t in trees]), dtype=dt)
+        left, right = cat("children_left", np.int32), cat("children_right", np.int32)
+        feat = np.maximum(cat("feature", np.int32), 0)         # leaves carry -2
+        thr = cat("threshold", np.float64)
+        if all(hasattr(t, "missing_go_to_left") for t in trees):
+            mgl = cat("missing_go_to_left", np.uint8)
+        else:
+            mgl = None
+        code = np.empty(int(offs[-1]), dtype=np.uint16)
+        for t in range(self.n_trees):
+            ids = np.arange(trees[t].node_count, dtype=np.int64)
+            if node_code_tables is None:
+                c = np.where(ids < L.MAX_CODE, ids, L.MAX_CODE)
+            else:
+                u = node_code_tables[t]
+                pos = np.searchsorted(u, ids)
+                posc = np.minimum(pos, len(u) - 1)
+                c = np.where(u[posc] == ids, pos, L.MAX_CODE)
+            code[offs[t]:offs[t + 1]] = c.astype(np.uint16)
+        self.device = default_device() if device is None else int(device)
+        L.check(self._lib.sknnr_forest_create(
+            _ptr(offs), _ptr(left), _ptr(right), _ptr(feat), _ptr(thr), _ptr(mgl), _ptr(code),
+            self.n_trees, self.n_features, self.device, C.byref(self._h)))
+
+    def apply(self, X) -> np.ndarray:
+        """Node ID of every tree for every row, int64 ``[n, n_trees]`` (== hstack of est.apply)."""
+        X = np.asarray(X)
+        if X.dtype != np.float32:
+            X = np.asarray(X, dtype=np.float64)
+        X = np.ascontiguousarray(X)
+        out = np.empty((X.shape[0], self.n_trees), dtype=np.int32)
+        L.check(self._lib.sknnr_forest_apply(self._h, _ptr(X), L.F32 if X.dtype == np.float32 else L.F64,
+                                             X.shape[0], X.shape[1], _ptr(out)))
+        return out.astype(np.int64)
+
+    def close(self):
+        h, self._h = self._h, C.c_void_p(None)
+        if h and h.value:
+            self._lib.sknnr_forest_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -26,7 +26,8 @@ EXPORTS = [
     "sknnr_weighted_average", "sknnr_index_stats", "sknnr_hamming_index_create",
     "sknnr_hamming_index_destroy", "sknnr_hamming_kneighbors",
     "sknnr_hamming_weighted_average", "sknnr_hamming_index_stats", "sknnr_host_alloc",
-    "sknnr_host_free", "sknnr_measure_fp32_peak",
+    "sknnr_host_free", "sknnr_measure_fp32_peak", "sknnr_forest_create", "sknnr_forest_destroy",
+    "sknnr_forest_apply", "sknnr_hamming_kneighbors_forest",
 ]
 
 
@@ -80,6 +81,11 @@ def load() -> C.CDLL:
     lib.sknnr_host_alloc.argtypes = [C.POINTER(vp), i64]
     lib.sknnr_host_free.argtypes = [vp]
     lib.sknnr_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.sknnr_forest_create.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
+    lib.sknnr_forest_destroy.argtypes = [vp]
+    lib.sknnr_forest_apply.argtypes = [vp, vp, i32, i64, i64, vp]
+    lib.sknnr_hamming_kneighbors_forest.argtypes = [vp, vp, vp, i32, i64, i64, i64, i32, u32, i32, vp, vp, i32,
+                                                    vp, vp]
     for name in EXPORTS:
         if name != "sknnr_last_error":
             getattr(lib, name).restype = C.c_int

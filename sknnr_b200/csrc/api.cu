@@ -90,6 +90,8 @@ struct Slot {
     DevBuf<float> qimg_tc;         // tensor-core engine query image
     DevBuf<double> z64c;           // compacted rows of the cascade's second stage
     DevBuf<int> fb2;               // second-stage failures: [0] = count, [1..] = list
+    DevBuf<uint16_t> codes;        // node codes produced by the device forest walk
+    DevBuf<int> ids32;             // node IDs of sknnr_forest_apply
     DevBuf<uint32_t> qimg_h;       // Hamming query image
     DevBuf<int> cand_idx;
     DevBuf<float> cand_thr;
@@ -106,7 +108,7 @@ struct Slot {
     long long rows_in_flight = 0;
     void release() {
         x.release(); z64.release(); qimg.release(); qimg_tc.release(); z64c.release(); fb2.release();
-        qimg_h.release(); cand_idx.release();
+        codes.release(); ids32.release(); qimg_h.release(); cand_idx.release();
         cand_thr.release(); cand_cnt.release(); fb.release(); o_dist.release();
         o_idx.release(); o_pred.release(); scratch.release();
         for (auto e : evs) cudaEventDestroy(e);
@@ -246,6 +248,18 @@ struct sknnr_hamming_index : IndexBase {
     double *d_w = nullptr, *d_lut = nullptr;
     double wsum = 0.0;
     bool uniform = true;
+};
+
+struct sknnr_forest {
+    int device = 0;
+    int n_trees = 0, n_features = 0;
+    long long n_nodes = 0;
+    ForestNode *d_nodes = nullptr;
+    int *d_roots = nullptr;
+    std::mutex lock;
+    cudaStream_t stream = nullptr;
+    DevBuf<unsigned char> x;
+    DevBuf<int> ids;
 };
 
 extern "C" {
@@ -917,26 +931,38 @@ static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *d
     return SKNNR_OK;
 }
 
-int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, int64_t n_q,
-                             int64_t ldq, int64_t row_offset, int32_t k, uint32_t flags,
-                             int32_t decimals, double *out_dist, int64_t *out_idx,
-                             int32_t weights, double *out_pred, void *stream) {
+// Shared body of sknnr_hamming_kneighbors (forest == NULL: `q` holds u16 node codes, row stride
+// ldq elements) and sknnr_hamming_kneighbors_forest (`q` holds raw feature rows of x_dtype, row
+// stride ldq elements; every chunk is walked through the forest on the device first).
+static int hamming_kneighbors_impl(sknnr_hamming_index *ix, sknnr_forest *forest, const void *q,
+                                   int32_t x_dtype, int64_t n_q, int64_t ldq, int64_t row_offset,
+                                   int32_t k, uint32_t flags, int32_t decimals, double *out_dist,
+                                   int64_t *out_idx, int32_t weights, double *out_pred, void *stream) {
     if (!ix) return fail(SKNNR_EINVAL, "index is NULL");
+    const uint16_t *q_codes = forest ? nullptr : (const uint16_t *)q;
     int kk = 0;
-    int rc = check_query_args(ix->n_ref, ix->n_out, n_q, k, flags, weights, q_codes, out_pred, kk);
+    int rc = check_query_args(ix->n_ref, ix->n_out, n_q, k, flags, weights, q, out_pred, kk);
     if (rc != SKNNR_OK) return rc;
+    if (forest) {
+        if (forest->n_trees != ix->n_trees) return fail(SKNNR_EINVAL, "forest and index disagree on the number of trees");
+        if (forest->device != ix->device) return fail(SKNNR_EINVAL, "forest and index live on different devices");
+        if (x_dtype != SKNNR_F64 && x_dtype != SKNNR_F32) return fail(SKNNR_EINVAL, "bad x_dtype");
+    }
     std::lock_guard<std::mutex> g(ix->lock);
     CK(cudaSetDevice(ix->device));
     const bool excl = flags & SKNNR_EXCLUDE_SELF;
     const bool dev_ptrs = flags & SKNNR_DEVICE_PTRS;
     bool q_on_device = dev_ptrs;
     if (excl) {
+        forest = nullptr;   // X=None: the reference plots' own codes
         q_codes = ix->d_rcodes;
         n_q = ix->n_ref;
         ldq = ix->n_trees;
         q_on_device = true;
     }
-    if (ldq < ix->n_trees) return fail(SKNNR_EINVAL, "ldq smaller than the number of trees");
+    if (!forest && ldq < ix->n_trees) return fail(SKNNR_EINVAL, "ldq smaller than the number of trees");
+    if (forest && ldq < forest->n_features) return fail(SKNNR_EINVAL, "ldx smaller than the number of features");
+    const size_t xesz = x_dtype == SKNNR_F32 ? 4 : 8;
     for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; }
     ix->stats = sknnr_stats{};
     ix->stats.n_queries = n_q;
@@ -956,7 +982,29 @@ int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, i
         }
         const uint16_t *dq;
         int64_t dld = ldq;
-        if (q_on_device) {
+        if (forest) {
+            // raw feature rows -> device -> forest walk -> 16-bit node codes, all on s.stream
+            const void *dX;
+            int64_t dldx = ldq;
+            if (q_on_device) {
+                dX = (const unsigned char *)q + (size_t)r0 * ldq * xesz;
+            } else {
+                const int64_t cols = forest->n_features;
+                CK(s.x.reserve((size_t)rows * cols * xesz));
+                CK(cudaMemcpy2DAsync(s.x.p, (size_t)cols * xesz, (const unsigned char *)q + (size_t)r0 * ldq * xesz,
+                                     (size_t)ldq * xesz, (size_t)cols * xesz, (size_t)rows,
+                                     cudaMemcpyHostToDevice, s.stream));
+                ix->stats.h2d_bytes += rows * cols * (int64_t)xesz;
+                dX = s.x.p;
+                dldx = cols;
+            }
+            CK(s.codes.reserve((size_t)rows * ix->n_trees));
+            CK(launch_forest_apply(dX, x_dtype == SKNNR_F32, dldx, rows, forest->n_features, forest->d_nodes,
+                                   forest->d_roots, forest->n_trees, s.codes.p, nullptr, ix->n_trees, s.stream));
+            ix->stats.kernel_launches++;
+            dq = s.codes.p;
+            dld = ix->n_trees;
+        } else if (q_on_device) {
             dq = q_codes + (size_t)r0 * ldq;
         } else {
             CK(s.x.reserve((size_t)rows * ix->n_trees * 2));
@@ -1002,6 +1050,117 @@ int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, i
             CK(cudaStreamSynchronize(s.stream));
             ix->harvest(s);
         }
+    }
+    return SKNNR_OK;
+}
+
+int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, int64_t n_q,
+                             int64_t ldq, int64_t row_offset, int32_t k, uint32_t flags,
+                             int32_t decimals, double *out_dist, int64_t *out_idx,
+                             int32_t weights, double *out_pred, void *stream) {
+    return hamming_kneighbors_impl(ix, nullptr, q_codes, 0, n_q, ldq, row_offset, k, flags, decimals,
+                                   out_dist, out_idx, weights, out_pred, stream);
+}
+
+int sknnr_hamming_kneighbors_forest(sknnr_hamming_index *ix, sknnr_forest *forest, const void *X,
+                                    int32_t x_dtype, int64_t n_q, int64_t ldx, int64_t row_offset,
+                                    int32_t k, uint32_t flags, int32_t decimals, double *out_dist,
+                                    int64_t *out_idx, int32_t weights, double *out_pred, void *stream) {
+    if (!forest) return fail(SKNNR_EINVAL, "forest is NULL");
+    return hamming_kneighbors_impl(ix, forest, X, x_dtype, n_q, ldx, row_offset, k, flags, decimals,
+                                   out_dist, out_idx, weights, out_pred, stream);
+}
+
+// -----------------------------------------------------------------------------------------
+int sknnr_forest_create(const int32_t *tree_offsets, const int32_t *children_left,
+                        const int32_t *children_right, const int32_t *feature, const double *threshold,
+                        const uint8_t *missing_go_to_left, const uint16_t *node_code, int32_t n_trees,
+                        int32_t n_features, int32_t device, sknnr_forest **out) {
+    if (!tree_offsets || !children_left || !children_right || !feature || !threshold || !out || n_trees < 1 ||
+        n_features < 1)
+        return fail(SKNNR_EINVAL, "bad arguments to sknnr_forest_create");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(SKNNR_ENODEV, "no CUDA device: sknnr_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(SKNNR_EINVAL, "bad device ordinal");
+    if (forest_smem_bytes(n_features) > 227 * 1024) return fail(SKNNR_EUNSUP, "too many features for the forest kernel");
+    const long long n_nodes = tree_offsets[n_trees];
+    if (n_nodes < n_trees) return fail(SKNNR_EINVAL, "bad tree offsets");
+    std::vector<ForestNode> nodes((size_t)n_nodes);
+    std::vector<int> roots(n_trees);
+    for (int t = 0; t < n_trees; ++t) {
+        const int lo = tree_offsets[t], hi = tree_offsets[t + 1];
+        if (hi <= lo) return fail(SKNNR_EINVAL, "empty tree");
+        roots[t] = lo;
+        for (int i = lo; i < hi; ++i) {
+            ForestNode nd{};
+            const int l = children_left[i], r = children_right[i];
+            if (l < 0) {   // leaf ($SP/sklearn/tree/_tree.pyx: TREE_LEAF = -1)
+                nd.left = nd.right = -1;
+                nd.code = node_code ? (int)node_code[i] : (i - lo);
+            } else {
+                if (l >= hi - lo || r < 0 || r >= hi - lo) return fail(SKNNR_EINVAL, "child index out of range");
+                if (feature[i] < 0 || feature[i] >= n_features) return fail(SKNNR_EINVAL, "feature index out of range");
+                nd.left = lo + l;
+                nd.right = lo + r;
+                nd.thr = threshold[i];
+                nd.feat = feature[i] | ((missing_go_to_left && missing_go_to_left[i]) ? (int)0x80000000u : 0);
+            }
+            nodes[(size_t)i] = nd;
+        }
+    }
+    sknnr_forest *f = new sknnr_forest();
+    f->device = device;
+    f->n_trees = n_trees;
+    f->n_features = n_features;
+    f->n_nodes = n_nodes;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_nodes, nodes.size() * sizeof(ForestNode));
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_nodes, nodes.data(), nodes.size() * sizeof(ForestNode), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_roots, roots.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_roots, roots.data(), roots.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        sknnr_forest_destroy(f);
+        CK(e);
+    }
+    *out = f;
+    return SKNNR_OK;
+}
+
+int sknnr_forest_destroy(sknnr_forest *f) {
+    if (!f) return SKNNR_OK;
+    cudaSetDevice(f->device);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    cudaFree(f->d_nodes);
+    cudaFree(f->d_roots);
+    f->x.release();
+    f->ids.release();
+    delete f;
+    return SKNNR_OK;
+}
+
+int sknnr_forest_apply(sknnr_forest *f, const void *X, int32_t x_dtype, int64_t n_q, int64_t ldx,
+                       int32_t *out_ids) {
+    if (!f || !X || !out_ids || n_q < 0) return fail(SKNNR_EINVAL, "NULL argument");
+    if (ldx < f->n_features) return fail(SKNNR_EINVAL, "ldx smaller than the number of features");
+    if (x_dtype != SKNNR_F64 && x_dtype != SKNNR_F32) return fail(SKNNR_EINVAL, "bad x_dtype");
+    std::lock_guard<std::mutex> g(f->lock);
+    CK(cudaSetDevice(f->device));
+    const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
+    const int64_t chunk = g_opt.chunk_rows;
+    for (int64_t r0 = 0; r0 < n_q; r0 += chunk) {
+        const int64_t rows = std::min(chunk, n_q - r0);
+        CK(f->x.reserve((size_t)rows * f->n_features * esz));
+        CK(f->ids.reserve((size_t)rows * f->n_trees));
+        CK(cudaMemcpy2DAsync(f->x.p, (size_t)f->n_features * esz, (const unsigned char *)X + (size_t)r0 * ldx * esz,
+                             (size_t)ldx * esz, (size_t)f->n_features * esz, (size_t)rows, cudaMemcpyHostToDevice,
+                             f->stream));
+        CK(launch_forest_apply(f->x.p, x_dtype == SKNNR_F32, f->n_features, rows, f->n_features, f->d_nodes,
+                               f->d_roots, f->n_trees, nullptr, f->ids.p, f->n_trees, f->stream));
+        CK(cudaMemcpyAsync(out_ids + r0 * f->n_trees, f->ids.p, (size_t)rows * f->n_trees * 4, cudaMemcpyDeviceToHost,
+                           f->stream));
+        CK(cudaStreamSynchronize(f->stream));
     }
     return SKNNR_OK;
 }

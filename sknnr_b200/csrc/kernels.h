@@ -108,6 +108,22 @@ cudaError_t launch_hamming_finish(const int *cand_idx, const int *cand_cnt, int 
                                   const double *lut, long long n_q, const FinishParams &fp,
                                   cudaStream_t st);
 
+// ---- forest.cu (RFNodeTransformer.transform on the device) -------------------------------
+// One node of the flattened forests, 32 bytes.  left < 0: leaf (`code` = the 16-bit node code the
+// Hamming index uses for it).  feat: feature index, bit 31 set = missing values go left.
+struct __align__(16) ForestNode {
+    double thr;
+    int left, right;
+    int feat, code;
+    int pad[2];
+};
+size_t forest_smem_bytes(int d);
+// out_ids != null: node IDs relative to each tree's root (transform parity, int32 [n_q, ld_out]);
+// else out_codes: 16-bit node codes [n_q, ld_out]
+cudaError_t launch_forest_apply(const void *X, int x_is_f32, long long ldx, long long n_q, int d,
+                                const ForestNode *nodes, const int *roots, int n_trees,
+                                uint16_t *out_codes, int *out_ids, long long ld_out, cudaStream_t st);
+
 // ---- misc ------------------------------------------------------------------------------
 cudaError_t launch_fp32_peak(float *sink, int iters, int grid, cudaStream_t st);
 

@@ -1,8 +1,10 @@
 """Random-forest node transformer for RFNN: one forest per target, ``transform`` returns the
 terminal-node ID of every tree (mirrors ref:src/sknnr/transformers/_tree_node_transformer.py
 and _rfnode_transformer.py).  Forest TRAINING is scikit-learn's (out of the hot-path scope);
-``transform`` still walks the trees with scikit-learn's ``apply`` on the host - the GPU forest
-walk is row f1 of the scope table (next) - and hands int64 node IDs to the Hamming kernels.
+``transform`` walks the fitted trees on the GPU (``ForestIndex``: scikit-learn's ``tree_`` arrays
+flattened, ``Tree._apply_dense`` semantics replicated bit for bit - scope row f1), and
+``RFNNRegressor`` queries go raw features -> forest walk -> Hamming search without the node IDs
+ever leaving the device.
 """
 
 from __future__ import annotations
@@ -151,16 +153,45 @@ class RFNodeTransformer(TransformerMixin, BaseEstimator):
                            for j in range(e.n_estimators)], dtype=object)
 
     # -- transform ----------------------------------------------------------------------
-    def transform(self, X):
+    def _trees(self):
+        """Fitted scikit-learn ``Tree`` objects in ``transform``'s column order."""
+        return [t.tree_ for est in self.estimators_ for t in est.estimators_]
+
+    def _forest_index(self, node_code_tables=None):
+        """Device copy of the trees (a cache: never pickled, rebuilt on demand).  A copy made with
+        ``node_code_tables`` also serves the fused Hamming query of the estimator that owns them."""
+        from .._engine import ForestIndex
+
+        key = "_forest_index_coded" if node_code_tables is not None else "_forest_index_plain"
+        fx = self.__dict__.get(key)
+        if fx is not None and key == "_forest_index_coded" and self.__dict__.get("_forest_tables_id") != id(node_code_tables):
+            fx = None   # the owning estimator rebuilt its code tables (refit)
+        if fx is None:
+            fx = ForestIndex(self._trees(), self.n_features_in_, node_code_tables)
+            self.__dict__[key] = fx
+            if key == "_forest_index_coded":
+                self.__dict__["_forest_tables_id"] = id(node_code_tables)
+        return fx
+
+    def __getstate__(self):
+        state = super().__getstate__()
+        for key in ("_forest_index_coded", "_forest_index_plain", "_forest_tables_id"):
+            state.pop(key, None)
+        return state
+
+    def _validate_query(self, X):
+        """Input validation of ``transform`` (feature names, shape, NaN) plus scikit-learn's own
+        float32 check of ``est.apply`` ($SP/sklearn/tree/_classes.py _validate_X_predict)."""
         check_is_fitted(self)
         X_arr = validate_data(self, X=X, reset=False, ensure_min_features=1, ensure_min_samples=1)
-        ids = []
-        for est in self.estimators_:
-            a = est.apply(X_arr)
-            if a.ndim == 3:
-                a = np.swapaxes(a, 1, 2).reshape(a.shape[0], -1)
-            ids.append(a)
-        return np.hstack(ids).astype("int64")
+        with np.errstate(over="ignore"):
+            X32 = np.asarray(X_arr, dtype=np.float32)
+        check_array(X32, ensure_all_finite=True, estimator=self)
+        return X_arr
+
+    def transform(self, X):
+        X_arr = self._validate_query(X)
+        return self._forest_index().apply(X_arr)
 
     def fit_transform(self, X, y):
         return self.fit(X, y).transform(X)

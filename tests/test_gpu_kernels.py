@@ -335,3 +335,63 @@ def test_tensor_engine_duplicates_and_queries_on_plots():
     assert np.isfinite(p_g).all()
     w = (d_g[:400] == 0.0).astype(float)
     np.testing.assert_allclose(p_g[:400], orc.weighted_average(y, i_g[:400], w), rtol=1e-12, atol=1e-12)
+
+
+# ---- forest walk (scope row f1) -----------------------------------------------------------
+@pytest.mark.parametrize("kind", ["regressor", "classifier", "multi"])
+def test_forest_apply_bit_exact_with_sklearn(kind):
+    """RFNodeTransformer.transform on the device == hstack(est.apply(X)) of scikit-learn
+    (ref:src/sknnr/transformers/_tree_node_transformer.py:177-201), for float64 and float32
+    inputs, values that sit exactly on thresholds included."""
+    from sknnr_b200.transformers import RFNodeTransformer
+
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((1500, 11)) * np.array([1, 10, 0.1, 1000, 1, 1, 5, 1, 1, 1e-3, 1]) + 3.0
+    X[:, 6] = np.round(X[:, 6])                      # few distinct values -> thresholds between them
+    if kind == "regressor":
+        y = X[:, :1] * 2 + rng.standard_normal((1500, 1))
+    elif kind == "classifier":
+        y = (X[:, 1] > 3).astype(int).astype(str).reshape(-1, 1)
+    else:
+        y = np.column_stack([X[:, 0] + rng.standard_normal(1500), np.round(X[:, 6]), X[:, 3] * 0.01])
+    tr = RFNodeTransformer(n_estimators=23, random_state=1, min_samples_leaf=3).fit(X, y)
+    Q = np.vstack([X[:300], rng.standard_normal((700, 11)) * 3 + 3.0])
+    # rows that sit exactly on (float32) thresholds of the first trees
+    t0 = tr.estimators_[0].estimators_[0].tree_
+    inner = np.flatnonzero(t0.children_left >= 0)[:50]
+    for j, n in enumerate(inner):
+        Q[j, t0.feature[n]] = np.float32(t0.threshold[n])
+    want = np.hstack([e.apply(Q) for e in tr.estimators_]).astype(np.int64)
+    got = tr.transform(Q)
+    assert got.dtype == np.int64 and got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+    want32 = np.hstack([e.apply(Q.astype(np.float32)) for e in tr.estimators_]).astype(np.int64)
+    np.testing.assert_array_equal(tr.transform(Q.astype(np.float32)), want32)
+    with pytest.raises(ValueError):
+        tr.transform(np.full((2, 11), 1e300))        # not representable in float32, as est.apply rejects it
+
+
+def test_rfnn_fused_forest_query_equals_two_step_path():
+    """RFNNRegressor.kneighbors / predict on raw features (forest walk fused in front of the Hamming
+    search) == Hamming search on the node IDs scikit-learn's apply returns, bit for bit."""
+    import sknnr_b200 as S
+
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((900, 9))
+    y = np.column_stack([X[:, 0] * 2 + rng.standard_normal(900), X[:, 1] - X[:, 2]])
+    Q = rng.standard_normal((400, 9))
+    est = S.RFNNRegressor(n_estimators=31, n_neighbors=4, random_state=0, weights="distance").fit(X, y)
+    ids_ref = np.hstack([e.apply(X) for e in est.transformer_.estimators_]).astype(np.int64)
+    ids_q = np.hstack([e.apply(Q) for e in est.transformer_.estimators_]).astype(np.int64)
+    np.testing.assert_array_equal(est.transformer_.transform(X), ids_ref)
+    st = orc.FittedState("hamming", fit_Z=ids_ref, y=y, hamming_w=est.hamming_weights_)
+    d_o, i_o = orc.kneighbors(st, ids_q, k=4, transformed=True)
+    d, i = est.kneighbors(Q)                                   # fused: raw rows in
+    np.testing.assert_array_equal(i, i_o)
+    np.testing.assert_array_equal(d, d_o)
+    d2, i2 = est.regressor_.kneighbors(ids_q)                  # two-step: node IDs in
+    np.testing.assert_array_equal(i2, i)
+    np.testing.assert_array_equal(d2, d)
+    p_o = orc.weighted_average(y, i_o, orc.get_weights(d_o, "distance"))
+    np.testing.assert_allclose(est.predict(Q), p_o, rtol=RTOL, atol=1e-10)
+    assert est.regressor_._get_index().stats()["kernel_launches"] == 4   # forest + pack + search + finish
