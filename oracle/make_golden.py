@@ -34,6 +34,7 @@ from sklearn.model_selection import train_test_split  # noqa: E402
 import sknnr  # noqa: E402
 from sknnr import (  # noqa: E402
     EuclideanKNNRegressor,
+    GBNNRegressor,
     GNNRegressor,
     MahalanobisKNNRegressor,
     MSNRegressor,
@@ -200,8 +201,72 @@ def rfnn_case():
     print("wrote rfnn", ids_tr.shape, ids_tr.max())
 
 
+def mixed_y_fit(ytr):
+    # regression + 3-class classification targets of the reference's mixed-forest test
+    # (ref:tests/test_regressions.py:158-176)
+    cols = [c for c in ytr.columns if c.endswith("_BA") and c != "Total_BA"]
+    mx = ytr[cols].idxmax(axis=1)
+    mx = mx.where(mx.isin(["ABGR_BA", "TSHE_BA"]), other="OTHER")
+    return ytr[["Total_BA"]].assign(MAX_SPECIES=mx)
+
+
+def flat_trees(transformer):
+    """scikit-learn tree_ arrays of every tree in transform's column order, concatenated."""
+    trees = []
+    for est in transformer.estimators_:
+        e = est.estimators_
+        for c in range(e.shape[1]):
+            for s_ in range(e.shape[0]):
+                trees.append(e[s_, c].tree_)
+    offs = np.zeros(len(trees) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([t.node_count for t in trees])
+    cat = lambda n, dt: np.concatenate([np.asarray(getattr(t, n)) for t in trees]).astype(dt)  # noqa: E731
+    return {"tree_offsets": offs, "tree_left": cat("children_left", np.int32),
+            "tree_right": cat("children_right", np.int32), "tree_feature": cat("feature", np.int32),
+            "tree_threshold": cat("threshold", np.float64)}
+
+
+def gbnn_case():
+    """GBNNRegressor (scope row f3): train-improvement tree weights make the Hamming weights
+    unequal; the mixed case adds a 3-class GradientBoostingClassifier (3 trees per stage)."""
+    Xtr, Xte, ytr, yte = moscow_split()
+    out = {"versions": VERSIONS}
+    yf = mixed_y_fit(ytr)
+    out["mixed_yfit_total_ba"] = yf["Total_BA"].to_numpy()
+    out["mixed_yfit_max_species"] = yf["MAX_SPECIES"].to_numpy().astype("U8")
+    for tag, y_fit in (("", None), ("mixed_", yf)):
+        est = GBNNRegressor(n_neighbors=5, random_state=42).fit(Xtr, ytr, y_fit=y_fit)
+        ids_tr = est.transformer_.transform(Xtr)
+        ids_te = est.transformer_.transform(Xte)
+        assert ids_tr.max() < 2**15 and ids_te.max() < 2**15
+        out[tag + "ids_train"] = ids_tr.astype(np.int16)
+        out[tag + "ids_test"] = ids_te.astype(np.int16)
+        out[tag + "hamming_w"] = est.hamming_weights_
+        out[tag + "tree_weights"] = np.hstack(est.transformer_.tree_weights_)
+        out[tag + "n_trees_per_iteration"] = np.asarray(est.transformer_.n_trees_per_iteration_)
+        out[tag + "y"] = est.regressor_._y
+        for k, v in flat_trees(est.transformer_).items():
+            out[tag + k] = v
+        out[tag + "live_ref_dist"], out[tag + "live_ref_nn"] = est.kneighbors()
+        out[tag + "live_tgt_dist"], out[tag + "live_tgt_nn"] = est.kneighbors(Xte)
+        out[tag + "live_ref_pred"] = est.independent_prediction_
+        out[tag + "live_ref_score"] = np.float64(est.independent_score_)
+        out[tag + "live_tgt_pred"] = est.predict(Xte)
+    # the reference's own golden vectors for these cases
+    for rt, short in (("reference", "ref"), ("target", "tgt")):
+        for k, v in load_gold(f"test_kneighbors_{rt}_full_gbnn_k5_index_.npz").items():
+            out[f"refgold_{short}_index_{k}"] = v
+        for k, v in load_gold(f"test_predict_{rt}_unweighted_full_gbnn_k5_.npz").items():
+            out[f"refgold_{short}_unweighted_{k}"] = v
+        for k, v in load_gold(f"test_estimators_with_mixed_type_forests_{rt}_gbnn_.npz").items():
+            out[f"refgold_mixed_{short}_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "moscow_gbnn.npz"), **out)
+    print("wrote gbnn", out["ids_train"].shape, out["mixed_ids_train"].shape,
+          sorted(k for k in out if k.startswith("refgold")))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    float_cases()
-    config_cases()
-    rfnn_case()
+    cases = {"float": float_cases, "config": config_cases, "rfnn": rfnn_case, "gbnn": gbnn_case}
+    for name in (sys.argv[1:] or list(cases)):
+        cases[name]()

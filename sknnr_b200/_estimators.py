@@ -1,6 +1,6 @@
-"""The six estimators of the hot-path scope: one-method subclasses that choose the transformer
+"""The estimators of the hot-path scope: one-method subclasses that choose the transformer
 (mirrors ref:src/sknnr/_euclidean.py:55-56, _mahalanobis.py:56-57, _msn.py:68-69, _gnn.py:69-70,
-_weighted_trees.py:18-140 and _rfnn.py:16-239).  GBNN is outside BASELINE.json's scope list."""
+_weighted_trees.py:18-140, _rfnn.py:16-239 and - scope row f3 - _gbnn.py:16-249)."""
 
 from __future__ import annotations
 
@@ -10,6 +10,7 @@ from ._base import OrdinationKNeighborsRegressor, TransformedKNeighborsRegressor
 from .transformers import (
     CCATransformer,
     CCorATransformer,
+    GBNodeTransformer,
     MahalanobisTransformer,
     RFNodeTransformer,
     StandardScalerWithDOF,
@@ -130,3 +131,51 @@ class RFNNRegressor(WeightedTreesNNRegressor):
                  "oob_score", "n_jobs", "random_state", "verbose", "warm_start", "class_weight_clf",
                  "ccp_alpha", "max_samples", "monotonic_cst"]
         return RFNodeTransformer(**{n: getattr(self, n) for n in names})
+
+
+class GBNNRegressor(WeightedTreesNNRegressor):
+    """Gradient Boosting Nearest Neighbours imputation (mirrors ref:src/sknnr/_gbnn.py:16-249):
+    one boosted model per target, neighbours by Hamming distance over node IDs with every tree
+    weighted by its share of the training-loss reduction."""
+
+    def __init__(self, *, loss_reg="squared_error", loss_clf="log_loss", learning_rate=0.1,
+                 n_estimators=100, subsample=1.0, criterion="friedman_mse", min_samples_split=2,
+                 min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_depth=3,
+                 min_impurity_decrease=0.0, init=None, random_state=None, max_features=None,
+                 alpha_reg=0.9, verbose=0, max_leaf_nodes=None, warm_start=False,
+                 validation_fraction=0.1, n_iter_no_change=None, tol=0.0001, ccp_alpha=0.0,
+                 forest_weights="uniform", tree_weighting_method="train_improvement",
+                 n_neighbors=5, weights="uniform", n_jobs=None):
+        self.loss_reg = loss_reg
+        self.loss_clf = loss_clf
+        self.learning_rate = learning_rate
+        self.n_estimators = n_estimators
+        self.subsample = subsample
+        self.criterion = criterion
+        self.min_samples_split = min_samples_split
+        self.min_samples_leaf = min_samples_leaf
+        self.min_weight_fraction_leaf = min_weight_fraction_leaf
+        self.max_depth = max_depth
+        self.min_impurity_decrease = min_impurity_decrease
+        self.init = init
+        self.random_state = random_state
+        self.max_features = max_features
+        self.alpha_reg = alpha_reg
+        self.verbose = verbose
+        self.max_leaf_nodes = max_leaf_nodes
+        self.warm_start = warm_start
+        self.validation_fraction = validation_fraction
+        self.n_iter_no_change = n_iter_no_change
+        self.tol = tol
+        self.ccp_alpha = ccp_alpha
+        self.forest_weights = forest_weights
+        self.tree_weighting_method = tree_weighting_method
+        super().__init__(n_neighbors=n_neighbors, weights=weights, n_jobs=n_jobs)
+
+    def _get_transformer(self):
+        names = ["loss_reg", "loss_clf", "learning_rate", "n_estimators", "subsample", "criterion",
+                 "min_samples_split", "min_samples_leaf", "min_weight_fraction_leaf", "max_depth",
+                 "min_impurity_decrease", "init", "random_state", "max_features", "alpha_reg",
+                 "verbose", "max_leaf_nodes", "warm_start", "validation_fraction",
+                 "n_iter_no_change", "tol", "ccp_alpha", "tree_weighting_method"]
+        return GBNodeTransformer(**{n: getattr(self, n) for n in names})

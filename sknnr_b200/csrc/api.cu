@@ -248,6 +248,10 @@ struct sknnr_hamming_index : IndexBase {
     double *d_w = nullptr, *d_lut = nullptr;
     double wsum = 0.0;
     bool uniform = true;
+    // unequal weights: 16-bit fixed-point filter weights (two trees per word, like the code images)
+    uint32_t *d_wq = nullptr;
+    double wq_scale = 0.0, wq_err = 0.0;
+    bool wq_ok = false;
 };
 
 struct sknnr_forest {
@@ -833,7 +837,33 @@ int sknnr_hamming_index_create(const uint16_t *ref_codes, int64_t n_ref, int32_t
         acc = acc + w[0];
         lut[m] = acc / den;
     }
+    // Fixed-point weights of the filter: w_t = scale * wq_t + e_t, wq_t in [0, 65535].  The certificate
+    // needs sum |e_t| plus the rounding of two left-to-right float64 sums ("weighted Hamming").
+    std::vector<uint32_t> wq((size_t)ix->n_chunks * HAM_WC, 0u);
+    {
+        double wmax = 0.0;
+        bool okw = true;
+        for (int t = 0; t < n_trees; ++t) {
+            if (!(w[t] >= 0.0) || !std::isfinite(w[t])) okw = false;
+            wmax = std::max(wmax, w[t]);
+        }
+        ix->wq_ok = okw && wmax > 0.0 && std::isfinite(den) && n_trees <= 32768;
+        if (ix->wq_ok) {
+            const double scale = wmax / 65535.0;
+            double err = 0.0;
+            for (int t = 0; t < n_trees; ++t) {
+                double qv = std::nearbyint(w[t] / scale);
+                qv = std::min(65535.0, std::max(0.0, qv));
+                err += std::fabs(w[t] - scale * qv);
+                wq[t / 2] |= (uint32_t)qv << (16 * (t & 1));
+            }
+            ix->wq_scale = scale;
+            ix->wq_err = err * (1.0 + 1e-9) + 4.0 * n_trees * std::ldexp(1.0, -53) * den;
+        }
+    }
     cudaError_t e = cudaMalloc(&ix->d_rcodes, (size_t)n_ref * n_trees * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->d_wq, wq.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(ix->d_wq, wq.data(), wq.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
         e = cudaMemcpy(ix->d_rcodes, ref_codes, (size_t)n_ref * n_trees * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&ix->d_w, (size_t)n_trees * 8);
@@ -858,6 +888,7 @@ int sknnr_hamming_index_destroy(sknnr_hamming_index *ix) {
     if (!ix) return SKNNR_OK;
     ix->release_common();
     cudaFree(ix->d_rcodes); cudaFree(ix->d_rimg); cudaFree(ix->d_w); cudaFree(ix->d_lut);
+    cudaFree(ix->d_wq);
     delete ix;
     return SKNNR_OK;
 }
@@ -891,43 +922,79 @@ static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *d
     fp.n_out = ix->n_out;
     fp.out_pred = o_pred;
 
-    const int kc = pick_kc(kk, 0);
-    const bool fast = ix->uniform && kc != 0 && ix->n_chunks * HAM_WC <= 2048 &&
-                      g_opt.engine != SKNNR_ENGINE_EXACT;
-    ix->stats.engine = fast ? SKNNR_ENGINE_SIMT : SKNNR_ENGINE_EXACT;
-    if (!fast) {
-        ExactArgs ea{};
-        ea.metric = 1;
-        ea.qcodes = dq;
-        ea.rcodes = ix->d_rcodes;
-        ea.n_trees = ix->n_trees;
-        ea.ldc = ix->n_trees;
-        // queries may have their own row stride
-        ea.w = ix->d_w;
-        ea.wsum = ix->wsum;
-        ea.n_q = rows;
-        ea.n_ref = (int)ix->n_ref;
-        ea.grid = (int)std::min<int64_t>(rows, (int64_t)ix->n_sm * 2);
+    // equal weights: integer counts are exact, kc = k suffices.  Unequal weights: the fixed-point
+    // filter keeps >= 8 spare candidates for the certificate of hamming_refine_kernel.
+    const bool exact_only = g_opt.engine == SKNNR_ENGINE_EXACT;
+    const int kc_u = pick_kc(kk, 0);
+    const int kc_w = std::max(16, pick_kc(kk, 8));
+    const bool fast_u = ix->uniform && kc_u != 0 && ix->n_chunks * HAM_WC <= 2048 && !exact_only;
+    const bool fast_w = !fast_u && !ix->uniform && ix->wq_ok && pick_kc(kk, 8) != 0 && !exact_only;
+    ix->stats.engine = (fast_u || fast_w) ? SKNNR_ENGINE_SIMT : SKNNR_ENGINE_EXACT;
+
+    ExactArgs ea{};
+    ea.metric = 1;
+    ea.qcodes = dq;
+    ea.ldq = ldq;
+    ea.rcodes = ix->d_rcodes;
+    ea.n_trees = ix->n_trees;
+    ea.w = ix->d_w;
+    ea.wsum = ix->wsum;
+    ea.n_q = rows;
+    ea.n_ref = (int)ix->n_ref;
+    ea.grid = (int)std::min<int64_t>(rows, (int64_t)ix->n_sm * 2);
+    if (!fast_u) {
         CK(s.scratch.reserve((size_t)ix->n_sm * 2 * ix->n_ref));
         ea.scratch = s.scratch.p;
-        if (ldq != ix->n_trees) return fail(SKNNR_EUNSUP, "strided codes with unequal weights");
+    }
+    if (!fast_u && !fast_w) {
         if (g_opt.timing) CK(s.mark(st));
         CK(launch_exact(ea, fp, st));
         if (g_opt.timing) CK(s.mark(st));
         ix->stats.kernel_launches++;
         return SKNNR_OK;
     }
+    const int kc = fast_u ? kc_u : kc_w;
     const int64_t n_qtiles = (rows + QTILE - 1) / QTILE;
     CK(s.qimg_h.reserve((size_t)n_qtiles * ix->n_chunks * HAM_WC * QTILE));
     CK(s.cand_idx.reserve((size_t)rows * kc));
     CK(s.cand_cnt.reserve((size_t)rows * kc));
     CK(launch_hamming_pack(dq, rows, ldq, ix->n_trees, ix->n_chunks, QTILE, 31743, s.qimg_h.p, st));
     if (g_opt.timing) CK(s.mark(st));
-    CK(launch_hamming_search(s.qimg_h.p, ix->d_rimg, ix->n_chunks, ix->n_rtiles, rows,
-                             (int)ix->n_ref, kc, s.cand_idx.p, s.cand_cnt.p, st));
+    CK(launch_hamming_search(s.qimg_h.p, ix->d_rimg, fast_w ? ix->d_wq : nullptr, ix->n_chunks, ix->n_rtiles,
+                             rows, (int)ix->n_ref, kc, s.cand_idx.p, s.cand_cnt.p, st));
     if (g_opt.timing) CK(s.mark(st));
-    CK(launch_hamming_finish(s.cand_idx.p, s.cand_cnt.p, kc, ix->d_lut, rows, fp, st));
-    ix->stats.kernel_launches += 3;
+    if (fast_u) {
+        CK(launch_hamming_finish(s.cand_idx.p, s.cand_cnt.p, kc, ix->d_lut, rows, fp, st));
+        ix->stats.kernel_launches += 3;
+        return SKNNR_OK;
+    }
+    CK(s.fb.reserve((size_t)rows + 1));
+    CK(cudaMemsetAsync(s.fb.p, 0, sizeof(int), st));
+    HammingRefineArgs ha{};
+    ha.cand_idx = s.cand_idx.p;
+    ha.cand_cnt = s.cand_cnt.p;
+    ha.kc = kc;
+    ha.qcodes = dq;
+    ha.ldq = ldq;
+    ha.rcodes = ix->d_rcodes;
+    ha.n_trees = ix->n_trees;
+    ha.w = ix->d_w;
+    ha.wsum = ix->wsum;
+    ha.scale = ix->wq_scale;
+    ha.err = ix->wq_err;
+    ha.n_q = rows;
+    ha.fb_count = s.fb.p;
+    ha.fb_list = s.fb.p + 1;
+    CK(launch_hamming_refine(ha, fp, st));
+    // exhaustive float64 search of the uncertified rows
+    ea.list = s.fb.p + 1;
+    ea.count = s.fb.p;
+    CK(launch_exact(ea, fp, st));
+    CK(cudaMemcpyAsync(&s.h_fb[0], s.fb.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    s.h_fb[1] = 0;
+    s.fb_pending = true;
+    s.rows_in_flight = 0;
+    ix->stats.kernel_launches += 4;
     return SKNNR_OK;
 }
 

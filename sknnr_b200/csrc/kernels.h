@@ -74,10 +74,10 @@ struct ExactArgs {
     const double *z64;
     const double *ref64;
     int d;
-    const uint16_t *qcodes; // [n_q, ldc]
-    const uint16_t *rcodes; // [n_ref, ldc]
+    const uint16_t *qcodes; // [n_q, ldq]
+    const uint16_t *rcodes; // [n_ref, n_trees]
     int n_trees;
-    int ldc;
+    long long ldq;
     const double *w;        // [n_trees]
     double wsum;
     long long n_q;
@@ -100,9 +100,28 @@ constexpr int HAM_WC = 32;  // packed 32-bit words (= 64 trees) per staged chunk
 cudaError_t launch_hamming_pack(const uint16_t *codes, long long n, long long ldc, int n_trees,
                                 int n_chunks, int tile, uint16_t pad_code, uint32_t *img,
                                 cudaStream_t st);
-cudaError_t launch_hamming_search(const uint32_t *qimg, const uint32_t *rimg, int n_chunks,
-                                  int n_rtiles, long long n_q, int n_ref, int kc, int *cand_idx,
-                                  int *cand_cnt, cudaStream_t st);
+// wq == null: equal weights, cand_cnt = mismatch counts.  wq [n_chunks * HAM_WC] (two 16-bit
+// fixed-point weights per word): cand_cnt = fixed-point weight sums (kc 16 or 32 only)
+cudaError_t launch_hamming_search(const uint32_t *qimg, const uint32_t *rimg, const uint32_t *wq,
+                                  int n_chunks, int n_rtiles, long long n_q, int n_ref, int kc,
+                                  int *cand_idx, int *cand_cnt, cudaStream_t st);
+// unequal weights: exact float64 distances of the candidates, certificate, finish_query or fb_list
+struct HammingRefineArgs {
+    const int *cand_idx;    // [n_q, kc]
+    const int *cand_cnt;    // [n_q, kc] fixed-point weight sums
+    int kc;
+    const uint16_t *qcodes; // [n_q, ldq]
+    long long ldq;
+    const uint16_t *rcodes; // [n_ref, n_trees]
+    int n_trees;
+    const double *w;        // [n_trees]
+    double wsum;            // left-to-right float64 sum of w
+    double scale, err;      // w_t = scale * wq_t + e_t, err >= sum |e_t| + float64 summation slack
+    long long n_q;
+    int *fb_count;
+    int *fb_list;
+};
+cudaError_t launch_hamming_refine(const HammingRefineArgs &a, const FinishParams &fp, cudaStream_t st);
 // mismatch counts -> float64 distances through the host-built table, then finish_query
 cudaError_t launch_hamming_finish(const int *cand_idx, const int *cand_cnt, int kc,
                                   const double *lut, long long n_q, const FinishParams &fp,

@@ -152,8 +152,8 @@ __device__ __forceinline__ double exact_pair(const ExactArgs &a, long long q, in
     }
     // weighted Hamming: left-to-right float64 sum of w_t over mismatching trees / sum(w)
     // ($SP/scipy/spatial/distance.py:1718-1723 -> cdist_hamming)
-    const uint16_t *qc = a.qcodes + q * a.ldc;
-    const uint16_t *rc = a.rcodes + (long long)j * a.ldc;
+    const uint16_t *qc = a.qcodes + q * a.ldq;
+    const uint16_t *rc = a.rcodes + (long long)j * a.n_trees;
     double num = 0.0;
     for (int t = 0; t < a.n_trees; ++t) {
         if (qc[t] != rc[t]) num = __dadd_rn(num, a.w[t]);

@@ -1,62 +1,16 @@
-"""Random-forest node transformer for RFNN: one forest per target, ``transform`` returns the
-terminal-node ID of every tree (mirrors ref:src/sknnr/transformers/_tree_node_transformer.py
-and _rfnode_transformer.py).  Forest TRAINING is scikit-learn's (out of the hot-path scope);
-``transform`` walks the fitted trees on the GPU (``ForestIndex``: scikit-learn's ``tree_`` arrays
-flattened, ``Tree._apply_dense`` semantics replicated bit for bit - scope row f1), and
-``RFNNRegressor`` queries go raw features -> forest walk -> Hamming search without the node IDs
-ever leaving the device.
-"""
+"""Random-forest node transformer for RFNN (mirrors
+ref:src/sknnr/transformers/_rfnode_transformer.py); fit / transform live in ``_treenode``."""
 
 from __future__ import annotations
 
-from collections import Counter
-
 import numpy as np
-from sklearn.base import BaseEstimator, TransformerMixin
 from sklearn.ensemble import RandomForestClassifier, RandomForestRegressor
-from sklearn.utils.validation import check_array, check_is_fitted, validate_data
+from sklearn.utils.validation import check_is_fitted
+
+from ._treenode import TreeNodeTransformer
 
 
-def _is_nan_like(v) -> bool:
-    return v is None or (isinstance(v, float) and np.isnan(v)) or type(v).__name__ == "NAType"
-
-
-def _target_names(y) -> list:
-    if hasattr(y, "columns") and hasattr(y, "dtypes"):
-        return list(y.columns)
-    if hasattr(y, "name") and hasattr(y, "dtype") and not isinstance(y, np.ndarray):
-        return ["0"] if y.name is None else [y.name]
-    arr = np.asarray(y, dtype=object)
-    return [str(i) for i in range(1 if arr.ndim == 1 else arr.shape[1])]
-
-
-def _target_dtypes(y) -> list:
-    """Smallest NumPy dtype holding each target column; pandas categoricals keep their tag."""
-    arr = np.asarray(y, dtype=object)
-    if arr.ndim == 1:
-        arr = arr.reshape(-1, 1)
-    promoted = [np.asarray(arr[:, i].tolist()).dtype for i in range(arr.shape[1])]
-    native = None
-    if hasattr(y, "columns") and hasattr(y, "dtypes"):
-        native = list(getattr(y.dtypes, "values", y.dtypes))
-    elif hasattr(y, "name") and hasattr(y, "dtype") and not isinstance(y, np.ndarray):
-        native = [y.dtype]
-    if native is None:
-        return promoted
-    return [n if str(n) == "category" else p for p, n in zip(promoted, native)]
-
-
-def _is_numeric(dt) -> bool:
-    try:
-        return bool(np.issubdtype(np.dtype(dt), np.number))
-    except TypeError:
-        kind = getattr(dt, "kind", None)
-        if kind:
-            return kind in "iuf"
-        raise TypeError(f"Unsupported type {dt}") from None
-
-
-class RFNodeTransformer(TransformerMixin, BaseEstimator):
+class RFNodeTransformer(TreeNodeTransformer):
     def __init__(self, n_estimators=50, criterion_reg="squared_error", criterion_clf="gini",
                  max_depth=None, min_samples_split=2, min_samples_leaf=5,
                  min_weight_fraction_leaf=0.0, max_features_reg=1.0, max_features_clf="sqrt",
@@ -85,46 +39,7 @@ class RFNodeTransformer(TransformerMixin, BaseEstimator):
         self.max_samples = max_samples
         self.monotonic_cst = monotonic_cst
 
-    # -- fit (cold path) ----------------------------------------------------------------
-    def _prepare_targets(self, y, info):
-        arr = np.asarray(y, dtype=object)
-        if arr.ndim == 1:
-            arr = arr.reshape(-1, 1)
-        out = []
-        for i, (name, dt) in enumerate(info.items()):
-            col = arr[:, i]
-            if any(_is_nan_like(v) for v in col):
-                raise ValueError(f"Target {name} has NaN-like elements.")
-            if str(dt) == "category":
-                col = np.asarray(col.tolist())
-            else:
-                try:
-                    npdt = np.dtype(dt)
-                except TypeError:
-                    npdt = None
-                if npdt is not None:
-                    if np.issubdtype(npdt, np.str_):
-                        odd = {type(v) for v in col if not np.issubdtype(type(v), np.str_)}
-                        if odd:
-                            raise ValueError(
-                                f"Target {name} has non-string types ({odd}) that cannot be "
-                                f"safely converted to a string dtype ({npdt}).")
-                    col = col.astype(npdt)
-            out.append(check_array(col, ensure_all_finite=True, dtype=None, ensure_2d=False, estimator=self))
-        return out
-
     def fit(self, X, y):
-        X_arr = validate_data(self, X=X, reset=True)
-        if y is None:
-            raise ValueError(f"{type(self).__name__} requires y to be passed, but the target y is None.")
-        names = _target_names(y)
-        if len(set(names)) != len(names):
-            dup = [n for n, c in Counter(names).items() if c > 1]
-            raise ValueError(f"Duplicate feature names found: {dup}.")
-        info = dict(zip(names, _target_dtypes(y)))
-        targets = self._prepare_targets(y, info)
-        self.estimator_type_dict_ = {
-            n: ("regression" if _is_numeric(dt) else "classification") for n, dt in info.items()}
         common = dict(
             n_estimators=self.n_estimators, max_depth=self.max_depth,
             min_samples_split=self.min_samples_split, min_samples_leaf=self.min_samples_leaf,
@@ -133,71 +48,23 @@ class RFNodeTransformer(TransformerMixin, BaseEstimator):
             bootstrap=self.bootstrap, oob_score=self.oob_score, n_jobs=self.n_jobs,
             random_state=self.random_state, verbose=self.verbose, warm_start=self.warm_start,
             ccp_alpha=self.ccp_alpha, max_samples=self.max_samples, monotonic_cst=self.monotonic_cst)
-        kinds = list(self.estimator_type_dict_.values())
-        self.estimators_ = []
-        for kind, target in zip(kinds, targets):
-            if kind == "regression":
-                est = RandomForestRegressor(criterion=self.criterion_reg, max_features=self.max_features_reg, **common)
-            else:
-                est = RandomForestClassifier(criterion=self.criterion_clf, max_features=self.max_features_clf,
-                                             class_weight=self.class_weight_clf, **common)
-            self.estimators_.append(est.fit(X_arr, target))
-        self.n_forests_ = len(self.estimators_)
-        self.n_trees_per_iteration_ = [1] * self.n_forests_
-        self.tree_weights_ = [np.full(self.n_estimators, 1.0 / self.n_estimators) for _ in range(self.n_forests_)]
-        return self
+        return self._fit(
+            X, y,
+            lambda: RandomForestRegressor(criterion=self.criterion_reg, max_features=self.max_features_reg, **common),
+            lambda: RandomForestClassifier(criterion=self.criterion_clf, max_features=self.max_features_clf,
+                                           class_weight=self.class_weight_clf, **common))
+
+    def _set_n_trees_per_iteration(self):
+        return [1] * self.n_forests_
+
+    def _set_tree_weights(self, X, y):
+        return [np.full(self.n_estimators, 1.0 / self.n_estimators, dtype=np.float64)
+                for _ in range(self.n_forests_)]
+
+    def _trees(self):
+        return [t.tree_ for est in self.estimators_ for t in est.estimators_]
 
     def get_feature_names_out(self, input_features=None):
         check_is_fitted(self, "estimators_")
         return np.asarray([f"rf{i}_tree{j}" for i, e in enumerate(self.estimators_)
                            for j in range(e.n_estimators)], dtype=object)
-
-    # -- transform ----------------------------------------------------------------------
-    def _trees(self):
-        """Fitted scikit-learn ``Tree`` objects in ``transform``'s column order."""
-        return [t.tree_ for est in self.estimators_ for t in est.estimators_]
-
-    def _forest_index(self, node_code_tables=None):
-        """Device copy of the trees (a cache: never pickled, rebuilt on demand).  A copy made with
-        ``node_code_tables`` also serves the fused Hamming query of the estimator that owns them."""
-        from .._engine import ForestIndex
-
-        key = "_forest_index_coded" if node_code_tables is not None else "_forest_index_plain"
-        fx = self.__dict__.get(key)
-        if fx is not None and key == "_forest_index_coded" and self.__dict__.get("_forest_tables_id") != id(node_code_tables):
-            fx = None   # the owning estimator rebuilt its code tables (refit)
-        if fx is None:
-            fx = ForestIndex(self._trees(), self.n_features_in_, node_code_tables)
-            self.__dict__[key] = fx
-            if key == "_forest_index_coded":
-                self.__dict__["_forest_tables_id"] = id(node_code_tables)
-        return fx
-
-    def __getstate__(self):
-        state = super().__getstate__()
-        for key in ("_forest_index_coded", "_forest_index_plain", "_forest_tables_id"):
-            state.pop(key, None)
-        return state
-
-    def _validate_query(self, X):
-        """Input validation of ``transform`` (feature names, shape, NaN) plus scikit-learn's own
-        float32 check of ``est.apply`` ($SP/sklearn/tree/_classes.py _validate_X_predict)."""
-        check_is_fitted(self)
-        X_arr = validate_data(self, X=X, reset=False, ensure_min_features=1, ensure_min_samples=1)
-        with np.errstate(over="ignore"):
-            X32 = np.asarray(X_arr, dtype=np.float32)
-        check_array(X32, ensure_all_finite=True, estimator=self)
-        return X_arr
-
-    def transform(self, X):
-        X_arr = self._validate_query(X)
-        return self._forest_index().apply(X_arr)
-
-    def fit_transform(self, X, y):
-        return self.fit(X, y).transform(X)
-
-    def __sklearn_tags__(self):
-        tags = super().__sklearn_tags__()
-        tags.target_tags.required = True
-        tags.transformer_tags.preserves_dtype = ["int64"]
-        return tags

@@ -128,6 +128,39 @@ def test_rfnn_end_to_end_matches_live_reference():
     assert np.array_equal(d, g["live_tgt_dist_nonuniform"])
 
 
+def test_gbnn_end_to_end_matches_live_reference():
+    """GBNNRegressor (scope row f3) end to end - boosted models trained by scikit-learn, forest walk
+    and weighted-Hamming search on the device - against the live reference: bit-equal distances,
+    indices equal up to boundary ties, same predictions and score."""
+    import warnings
+
+    import pandas as pd
+
+    import sknnr_b200 as S
+
+    g = load_golden("moscow_gbnn.npz")
+    Xtr, Xte, ytr, yte, _ = _split()
+    y_fit_mixed = pd.DataFrame({"Total_BA": g["mixed_yfit_total_ba"], "MAX_SPECIES": g["mixed_yfit_max_species"]})
+    for tag, y_fit in (("", None), ("mixed_", y_fit_mixed)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", FutureWarning)
+            est = S.GBNNRegressor(n_neighbors=5, random_state=42).fit(Xtr, ytr, y_fit=y_fit)
+        ids_te = est.transformer_.transform(Xte)
+        if not np.array_equal(ids_te, g[tag + "ids_test"].astype(np.int64)):
+            pytest.skip("scikit-learn grew different boosted trees than the golden generator's")
+        np.testing.assert_allclose(est.hamming_weights_, g[tag + "hamming_w"], rtol=1e-12)
+        if not np.array_equal(est.hamming_weights_, g[tag + "hamming_w"]):
+            continue   # weights differ in the last bit: distances cannot be bit-equal
+        d, i = est.kneighbors(Xte)
+        assert np.array_equal(d, g[tag + "live_tgt_dist"])
+        orc.assert_tie_aware_equal(d, i, g[tag + "live_tgt_dist"], g[tag + "live_tgt_nn"], rtol=0, atol=0, gap_rtol=0)
+        d, i = est.kneighbors()
+        assert np.array_equal(d, g[tag + "live_ref_dist"])
+        np.testing.assert_allclose(est.predict(Xte), g[tag + "live_tgt_pred"], rtol=1e-12)
+        np.testing.assert_allclose(est.independent_prediction_, g[tag + "live_ref_pred"], rtol=1e-12)
+        assert est.independent_score_ == pytest.approx(float(g[tag + "live_ref_score"]), abs=1e-12)
+
+
 def test_estimator_hygiene_pickle_lists_gridsearch_and_errors():
     import sknnr_b200 as S
     from sklearn.model_selection import GridSearchCV

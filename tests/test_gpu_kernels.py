@@ -395,3 +395,128 @@ def test_rfnn_fused_forest_query_equals_two_step_path():
     p_o = orc.weighted_average(y, i_o, orc.get_weights(d_o, "distance"))
     np.testing.assert_allclose(est.predict(Q), p_o, rtol=RTOL, atol=1e-10)
     assert est.regressor_._get_index().stats()["kernel_launches"] == 4   # forest + pack + search + finish
+
+
+# ---- weighted Hamming / GBNN (scope row f3) ------------------------------------------------
+def test_hamming_golden_gbnn_weighted_filter_bit_exact():
+    """GBNN's train-improvement weights: fixed-point filter + float64 refine + certificate must
+    reproduce the oracle and the live reference bit for bit (3500 trees; mixed model 400 trees)."""
+    from sknnr_b200 import _lib as L
+
+    g = load_golden("moscow_gbnn.npz")
+    for tag in ("", "mixed_"):
+        ref = g[tag + "ids_train"].astype(np.int64)
+        tgt = g[tag + "ids_test"].astype(np.int64)
+        w, y = g[tag + "hamming_w"], g[tag + "y"]
+        st = orc.FittedState("hamming", fit_Z=ref, y=y, hamming_w=w)
+        ix = _ham_index(ref.astype(np.uint16), w, y)
+        d_o, i_o = orc.kneighbors(st, tgt, k=5)
+        d_g, i_g, p_g = ix.query(tgt.astype(np.uint16), 5, weights="uniform", with_pred=True)
+        assert ix.stats()["engine"] == L.ENGINE_SIMT          # the filter ran, not the exhaustive kernel
+        np.testing.assert_array_equal(i_g, i_o)
+        assert np.array_equal(d_g, d_o)
+        assert np.array_equal(d_g, g[tag + "live_tgt_dist"])
+        orc.assert_tie_aware_equal(d_g, i_g, g[tag + "live_tgt_dist"], g[tag + "live_tgt_nn"], rtol=0, atol=0, gap_rtol=0)
+        np.testing.assert_allclose(p_g, g[tag + "live_tgt_pred"], rtol=1e-12)
+        d_o, i_o = orc.kneighbors(st, None, k=5)
+        d_g, i_g, _ = ix.query(None, 5, exclude_self=True)
+        np.testing.assert_array_equal(i_g, i_o)
+        assert np.array_equal(d_g, d_o)
+        assert np.array_equal(d_g, g[tag + "live_ref_dist"])
+
+
+@pytest.mark.parametrize(("n_ref", "n_q", "T", "k", "n_codes", "wkind"), [
+    (3000, 1000, 500, 7, 40, "decay"), (500, 300, 63, 5, 3, "random"), (1000, 257, 130, 1, 31743, "decay"),
+    (2000, 400, 64, 12, 8, "zeros"), (2500, 300, 1000, 20, 6, "decay"), (700, 200, 33, 28, 4, "random"),
+    (12, 50, 40, 5, 3, "random"), (1500, 300, 96, 5, 2, "two"),
+])
+def test_weighted_hamming_synthetic_bit_exact(n_ref, n_q, T, k, n_codes, wkind):
+    """Unequal weights of several shapes (geometric decay like boosting stages, zeros, only two
+    distinct values -> masses of exactly tied distances that the certificate must hand to the
+    exhaustive kernel), k up to 28 (> 24: exhaustive only), fewer references than candidates."""
+    from sknnr_b200 import _lib as L
+
+    rng = np.random.default_rng(11)
+    R = rng.integers(0, n_codes, size=(n_ref, T))
+    Q = R[rng.integers(0, n_ref, size=n_q)].copy()
+    flip = rng.random(Q.shape) < 0.4
+    Q[flip] = rng.integers(0, n_codes, size=int(flip.sum()))
+    if wkind == "decay":
+        w = 0.97 ** np.arange(T) * (1.0 + 0.1 * rng.random(T))
+    elif wkind == "random":
+        w = rng.random(T) + 0.01
+    elif wkind == "zeros":
+        w = rng.random(T)
+        w[::3] = 0.0
+    else:
+        w = np.where(np.arange(T) % 2 == 0, 1.0, 3.0)
+    w = w / w.sum()
+    st = orc.FittedState("hamming", fit_Z=R, y=np.zeros((n_ref, 1)), hamming_w=w)
+    d_o, i_o = orc.kneighbors(st, Q, k=k)
+    ix = _ham_index(R.astype(np.uint16), w)
+    d_g, i_g, _ = ix.query(Q.astype(np.uint16), k)
+    stats = ix.stats()
+    assert stats["engine"] == (L.ENGINE_SIMT if k <= 24 else L.ENGINE_EXACT)
+    np.testing.assert_array_equal(i_g, i_o)
+    assert np.array_equal(d_g, d_o)
+    if wkind in ("decay", "random") and n_ref > 32 and k <= 24:
+        assert stats["n_fallback"] <= n_q // 20         # the filter certifies nearly every row
+    L.set_option("engine", L.ENGINE_EXACT)
+    try:
+        d_e, i_e, _ = ix.query(Q.astype(np.uint16), k)
+    finally:
+        L.set_option("engine", L.ENGINE_AUTO)
+    np.testing.assert_array_equal(i_e, i_g)
+    assert np.array_equal(d_e, d_g)
+
+
+def test_gb_forest_apply_and_fused_gbnn_query():
+    """GBNodeTransformer.transform on the device == scikit-learn's apply with the reference's
+    class-major column order (ref:src/sknnr/transformers/_tree_node_transformer.py:190-200), and
+    GBNNRegressor on raw features (forest walk + weighted Hamming filter fused) == the oracle on
+    scikit-learn's node IDs."""
+    import warnings
+
+    import sknnr_b200 as S
+
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((800, 7))
+    cls = np.where(X[:, 0] + 0.3 * rng.standard_normal(800) > 0.5, "a", np.where(X[:, 1] > 0, "b", "c"))
+    y = np.column_stack([X[:, 0] * 2 + rng.standard_normal(800), X[:, 1] - X[:, 2]])
+    import pandas as pd
+    y_fit = pd.DataFrame({"t0": y[:, 0], "kind": cls})
+    Q = rng.standard_normal((300, 7))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", FutureWarning)
+        est = S.GBNNRegressor(n_estimators=40, n_neighbors=4, random_state=0, weights="distance").fit(X, y, y_fit=y_fit)
+    tr = est.transformer_
+    assert tr.n_trees_per_iteration_ == [1, 3]
+
+    def sk_apply(A):
+        cols = []
+        for e in tr.estimators_:
+            a = e.apply(A)
+            if a.ndim == 3:
+                a = np.swapaxes(a, 1, 2).reshape(a.shape[0], -1)
+            cols.append(a)
+        return np.hstack(cols).astype(np.int64)
+
+    ids_ref, ids_q = sk_apply(X), sk_apply(Q)
+    np.testing.assert_array_equal(tr.transform(X), ids_ref)
+    np.testing.assert_array_equal(tr.transform(Q.astype(np.float32)), sk_apply(Q.astype(np.float32)))
+    w = est.hamming_weights_
+    assert w.shape == (160,) and len(np.unique(w)) > 20
+    st = orc.FittedState("hamming", fit_Z=ids_ref, y=y, hamming_w=w)
+    d_o, i_o = orc.kneighbors(st, ids_q, k=4, transformed=True)
+    d, i = est.kneighbors(Q)
+    np.testing.assert_array_equal(i, i_o)
+    np.testing.assert_array_equal(d, d_o)
+    d2, i2 = est.regressor_.kneighbors(ids_q)
+    np.testing.assert_array_equal(i2, i)
+    np.testing.assert_array_equal(d2, d)
+    p_o = orc.weighted_average(y, i_o, orc.get_weights(d_o, "distance"))
+    np.testing.assert_allclose(est.predict(Q), p_o, rtol=RTOL, atol=1e-10)
+    d_o, i_o = orc.kneighbors(st, None, k=4)
+    d, i = est.kneighbors()
+    np.testing.assert_array_equal(i, i_o)
+    np.testing.assert_array_equal(d, d_o)

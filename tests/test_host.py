@@ -120,17 +120,20 @@ def test_signatures_match_reference_surface():
         assert list(inspect.signature(cls).parameters) == ["n_neighbors", "n_components"] + base[1:]
     rf = list(inspect.signature(S.RFNNRegressor).parameters)
     assert rf[0] == "n_estimators" and rf[-3:] == ["forest_weights", "n_neighbors", "weights"] and len(rf) == 24
+    gb = list(inspect.signature(S.GBNNRegressor).parameters)   # ref:src/sknnr/_gbnn.py:160-193
+    assert gb[:3] == ["loss_reg", "loss_clf", "learning_rate"] and len(gb) == 27
+    assert gb[-5:] == ["forest_weights", "tree_weighting_method", "n_neighbors", "weights", "n_jobs"]
     kn = list(inspect.signature(S.RawKNNRegressor.kneighbors).parameters)
     assert kn == ["self", "X", "n_neighbors", "return_distance", "return_dataframe_index",
                   "use_deterministic_ordering"]
     assert S.RawKNNRegressor.DISTANCE_PRECISION_DECIMALS == 10
-    for cls in (S.EuclideanKNNRegressor, S.MSNRegressor, S.RFNNRegressor, S.RawKNNRegressor):
+    for cls in (S.EuclideanKNNRegressor, S.MSNRegressor, S.RFNNRegressor, S.GBNNRegressor, S.RawKNNRegressor):
         est = cls()
         assert type(est)(**est.get_params()).get_params().keys() == est.get_params().keys()
 
 
 @pytest.mark.parametrize("name", ["RawKNNRegressor", "EuclideanKNNRegressor", "MahalanobisKNNRegressor",
-                                  "MSNRegressor", "GNNRegressor", "RFNNRegressor"])
+                                  "MSNRegressor", "GNNRegressor", "RFNNRegressor", "GBNNRegressor"])
 def test_unfitted_estimators_raise(name):
     import sknnr_b200 as S
 
@@ -139,3 +142,54 @@ def test_unfitted_estimators_raise(name):
         getattr(S, name)().kneighbors(X)
     with pytest.raises(NotFittedError):
         getattr(S, name)().predict(X)
+
+
+def test_gbnode_transformer_fit_side_matches_reference():
+    """Fit side of GBNN (cold path, scikit-learn trains the boosted models): tree weights, trees per
+    iteration, Hamming weights and the column order of ``transform`` equal the live reference's
+    (ref:src/sknnr/transformers/_gbnode_transformer.py:20-56,288-310; _weighted_trees.py:65-98).
+    The node IDs are checked with scikit-learn's own ``Tree.apply`` on the trees in ``_trees()``
+    order - the device walk of the same arrays is a GPU test."""
+    import pandas as pd
+    import warnings
+
+    from sknnr_b200._estimators import GBNNRegressor
+    from sknnr_b200.transformers import GBNodeTransformer
+
+    g = load_golden("moscow_gbnn.npz")
+    sp = load_golden("moscow_split.npz")
+    Xtr, ytr = sp["X_train"], sp["y_train"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", FutureWarning)
+        tr = GBNodeTransformer(random_state=42).fit(Xtr, ytr)
+    assert tr.n_forests_ == ytr.shape[1] and tr.n_trees_per_iteration_ == [1] * ytr.shape[1]
+    trees = tr._trees()
+    ids = np.stack([t.apply(Xtr.astype(np.float32)) for t in trees], axis=1)
+    if not np.array_equal(ids, g["ids_train"].astype(np.int64)):
+        pytest.skip("scikit-learn grew different boosted trees than the golden generator's")
+    np.testing.assert_allclose(np.hstack(tr.tree_weights_), g["tree_weights"], rtol=1e-12)
+    assert list(tr.get_feature_names_out()[:2]) == ["gb0_tree0", "gb0_tree1"]
+
+    # hamming_weights_ = tree weights x forest weights / trees per iteration, without a device
+    est = GBNNRegressor(random_state=42)
+    est.transformer_ = tr
+    np.testing.assert_allclose(est._get_hamming_weights(), g["hamming_w"], rtol=1e-12)
+
+    # mixed targets: one regression model + one 3-class classifier (3 trees per stage, class-major)
+    y_fit = pd.DataFrame({"Total_BA": g["mixed_yfit_total_ba"], "MAX_SPECIES": g["mixed_yfit_max_species"]})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", FutureWarning)
+        trm = GBNodeTransformer(random_state=42).fit(Xtr, y_fit)
+    assert trm.n_trees_per_iteration_ == [1, 3]
+    assert trm.estimator_type_dict_ == {"Total_BA": "regression", "MAX_SPECIES": "classification"}
+    ids = np.stack([t.apply(Xtr.astype(np.float32)) for t in trm._trees()], axis=1)
+    if np.array_equal(ids, g["mixed_ids_train"].astype(np.int64)):
+        np.testing.assert_allclose(np.hstack(trm.tree_weights_), g["mixed_tree_weights"], rtol=1e-12)
+        est.transformer_ = trm
+        np.testing.assert_allclose(est._get_hamming_weights(), g["mixed_hamming_w"], rtol=1e-12)
+    assert trm.get_feature_names_out()[100] == "gb1_cls0_tree0"
+    with pytest.raises(ValueError, match="tree_weighting_method"):
+        GBNodeTransformer(tree_weighting_method="nope", n_estimators=2).fit(Xtr, ytr[:, :1])
+    tu = GBNodeTransformer(tree_weighting_method="uniform", n_estimators=4).fit(Xtr, ytr[:, :2])
+    assert all(np.array_equal(w, np.full(4, 0.25)) for w in tu.tree_weights_)
+

@@ -162,3 +162,34 @@ def test_hamming_oracle_matches_live_rfnn():
     st2 = orc.FittedState(kind="hamming", fit_Z=st.fit_Z, y=st.y, hamming_w=g["hamming_w_nonuniform"])
     d, i = orc.kneighbors(st2, g["ids_test"].astype(np.int64), k=5)
     assert np.array_equal(d, g["live_tgt_dist_nonuniform"])
+
+
+def test_hamming_oracle_matches_live_gbnn():
+    """GBNN (scope row f3): train-improvement tree weights are unequal, so the distance is a genuine
+    float64 weighted sum.  The oracle must reproduce the live reference bit for bit, for the
+    all-regression model (3500 trees) and the mixed model with a 3-class boosted classifier."""
+    g = load_golden("moscow_gbnn.npz")
+    for tag in ("", "mixed_"):
+        w = g[tag + "hamming_w"]
+        assert len(np.unique(w)) > 10 and np.all(w >= 0) and abs(w.sum() - 1.0) < 1e-9
+        st = orc.FittedState(kind="hamming", fit_Z=g[tag + "ids_train"].astype(np.int64), y=g[tag + "y"], hamming_w=w)
+        for X, key in ((g[tag + "ids_test"].astype(np.int64), "tgt"), (None, "ref")):
+            d, i = orc.kneighbors(st, X, k=5)
+            assert np.array_equal(d, g[f"{tag}live_{key}_dist"])
+            orc.assert_tie_aware_equal(d, i, g[f"{tag}live_{key}_dist"], g[f"{tag}live_{key}_nn"],
+                                       rtol=0, atol=0, gap_rtol=0)
+        pred = orc.predict(st, g[tag + "ids_test"].astype(np.int64), k=5)
+        np.testing.assert_allclose(pred, g[tag + "live_tgt_pred"], rtol=1e-12)
+
+
+def test_gbnn_live_outputs_agree_with_reference_goldens():
+    """The fixture's live outputs against the reference's own stored vectors.  The mixed-forest
+    case agrees at the tolerances of ref:tests/test_regressions.py:125-142.  The 35-target case
+    does NOT: the stored vectors were written under another scikit-learn build whose boosted trees
+    differ (the unmodified reference run in this image misses them by up to 0.035), so that case is
+    pinned on the live reference only - the assertion below documents the state of affairs."""
+    g = load_golden("moscow_gbnn.npz")
+    np.testing.assert_allclose(g["mixed_live_ref_dist"], g["refgold_mixed_ref_dist"], atol=1e-8)
+    np.testing.assert_allclose(g["mixed_live_tgt_dist"], g["refgold_mixed_tgt_dist"], atol=1e-2)
+    assert g["live_ref_dist"].shape == g["refgold_ref_index_dist"].shape
+    assert np.abs(g["live_ref_dist"] - g["refgold_ref_index_dist"]).max() < 0.05
