@@ -155,9 +155,13 @@ int sknnr_index_stats(sknnr_index *index, sknnr_stats *out);
  *             the host maps each tree's node IDs (int64 from
  *             ref:src/sknnr/transformers/_tree_node_transformer.py:177-201) to dense codes
  *             in [0, 31743]; 31743 is reserved for "matches nothing".
- *   w         [n_trees] f64 hamming weights.  Equal weights use the integer kernel and a
- *             host-built table of the float64 distances reachable (bit-exact with SciPy's
- *             left-to-right sums); unequal weights use the exact float64 kernel.
+ *   w         [n_trees] f64 hamming weights.  Equal weights (RFNNRegressor) use the integer
+ *             kernel and a host-built table of the float64 distances reachable (bit-exact with
+ *             SciPy's left-to-right sums).  Unequal weights (GBNNRegressor's tree weights,
+ *             ref:src/sknnr/transformers/_gbnode_transformer.py:288-310; user forest_weights)
+ *             run a 16-bit fixed-point filter, recompute the survivors in float64 in SciPy's
+ *             order and certify the top k; uncertified rows, negative weights and k > 24 use
+ *             the exhaustive float64 kernel.  Results are bit-equal in every case.
  *   y         [n_ref, n_out] f64 or NULL.                                                  */
 int sknnr_hamming_index_create(const uint16_t *ref_codes, int64_t n_ref, int32_t n_trees,
                                const double *w, const double *y, int32_t n_out,

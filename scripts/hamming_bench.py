@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sknnr_b200 import _lib as L
 from sknnr_b200._engine import HammingIndex
 
-def main(n_ref=20000, n_q=500000, T=500, k=7):
+def main(n_ref=20000, n_q=500000, T=500, k=7, weighted=False):
     rng = np.random.default_rng(0)
     # node ids of ~60-leaf trees; queries are perturbed copies of plots so neighbours are meaningful
     Rc = rng.integers(0, 60, size=(n_ref, T)).astype(np.uint16)
@@ -13,6 +13,9 @@ def main(n_ref=20000, n_q=500000, T=500, k=7):
     flip = rng.random(Qc.shape) < 0.5
     Qc[flip] = rng.integers(0, 60, size=int(flip.sum())).astype(np.uint16)
     w = np.full(T, 1.0 / T)
+    if weighted:   # boosting-like weights: geometric decay per 100-tree model, GBNN (scope row f3)
+        w = np.tile(0.97 ** np.arange(100), (T + 99) // 100)[:T] * (1 + 0.1 * rng.random(T))
+        w /= w.sum()
     L.set_option("timing", 1)
     hx = HammingIndex(Rc, w, device=0)
     hx.query(Qc[:50000], k)
@@ -20,7 +23,7 @@ def main(n_ref=20000, n_q=500000, T=500, k=7):
     d, i, _ = hx.query(Qc, k)
     dt = time.perf_counter() - t0
     st = hx.stats()
-    print(f"hamming n_ref={n_ref} T={T} n_q={n_q} k={k}: e2e {n_q/dt/1e6:.3f} M queries/s ({dt*1e3:.1f} ms), "
+    print(f"hamming{' (unequal weights)' if weighted else ''} n_ref={n_ref} T={T} n_q={n_q} k={k}: e2e {n_q/dt/1e6:.3f} M queries/s ({dt*1e3:.1f} ms), "
           f"search kernel {st['search_ms']:.1f} ms = {n_q*n_ref*T/st['search_ms']/1e9:.1f} T id-compares/s, stats {st}")
 
 def forest_main(n_ref=20000, n_q=1000000, d=16, n_targets=10, n_estimators=50, k=7):
@@ -47,5 +50,9 @@ def forest_main(n_ref=20000, n_q=1000000, d=16, n_targets=10, n_estimators=50, k
 
 
 if __name__ == "__main__":
-    main()
-    forest_main()
+    if "weighted" in sys.argv:
+        main(weighted=True)
+        main(n_q=200000, T=3500, weighted=True)
+    else:
+        main()
+        forest_main()
