@@ -211,6 +211,27 @@ int sknnr_hamming_kneighbors_forest(sknnr_hamming_index *index, sknnr_forest *fo
                                     int32_t decimals, double *out_dist, int64_t *out_idx,
                                     int32_t weights, double *out_pred, void *stream);
 
+/* ---- Raster front end (scope row f4) -----------------------------------------------------
+ * The caller either side of the path when the queries are the pixels of a map (the
+ * "sknnr-spatial"-style loop around est.kneighbors / est.predict, ref:src/sknnr/_base.py:285-352):
+ * flatten a band-major image to [n_pix, d], drop masked pixels, query, write band-major layers.
+ * Here the image block goes to the device as it is and the transpose, the mask, the compaction
+ * and the scatter back run next to the search.
+ *
+ *   bands      host, band b = bands + b * band_stride elements of x_dtype, n_pix pixels each
+ *              (index->d_in bands, raw feature space)
+ *   a pixel is masked when any band is NaN / +-inf, or equals `nodata` while use_nodata != 0
+ *   the unmasked pixels, in pixel order, are the query rows 0 .. n_valid-1 of one
+ *   sknnr_kneighbors call (that numbering feeds the deterministic ordering key)
+ *   out_dist / out_idx [k][n_pix], out_pred [n_out][n_pix]: band-major layers (any may be NULL as
+ *              in sknnr_kneighbors); masked pixels receive fill_dist / fill_idx / fill_pred
+ *   flags      SKNNR_DETERMINISTIC or 0;  n_valid (may be NULL) <- number of unmasked pixels  */
+int sknnr_raster_kneighbors(sknnr_index *index, const void *bands, int32_t x_dtype, int64_t n_pix,
+                            int64_t band_stride, int32_t use_nodata, double nodata, int32_t k,
+                            uint32_t flags, int32_t decimals, double *out_dist, int64_t *out_idx,
+                            int32_t weights, double *out_pred, double fill_dist, int64_t fill_idx,
+                            double fill_pred, int64_t *n_valid);
+
 /* Pinned host memory for callers that stream large rasters (cudaHostAlloc / cudaFreeHost). */
 int sknnr_host_alloc(void **ptr, int64_t bytes);
 int sknnr_host_free(void *ptr);

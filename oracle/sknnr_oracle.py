@@ -361,6 +361,37 @@ def predict(state: FittedState, X=None, k=5, weights="uniform", **kw):
 
 
 # ----------------------------------------------------------------------------------
+# raster caller: what a map-producing caller does around the path
+# ----------------------------------------------------------------------------------
+def raster_query(state: FittedState, image, k=5, nodata=None, weights=None, deterministic=True,
+                 decimals=10, fill_dist=np.nan, fill_idx=-1, fill_pred=np.nan):
+    """The host-side loop around ref:src/sknnr/_base.py:285-352 for a band-major image
+    ``[bands, H, W]``: flatten to ``[H*W, bands]`` rows, keep the pixels whose bands are all finite
+    and different from ``nodata``, query them in pixel order as ONE kneighbors / predict call, and
+    scatter the results back into ``[k, H, W]`` / ``[n_out, H, W]`` layers (fill where masked)."""
+    image = np.asarray(image)
+    nb, hw = image.shape[0], image.shape[1:]
+    X = image.reshape(nb, -1).T
+    valid = np.isfinite(X.astype(np.float64)).all(axis=1)
+    if nodata is not None:
+        valid &= ~(X == nodata).any(axis=1)
+    n_pix = X.shape[0]
+    dist = np.full((k, n_pix), fill_dist, dtype=np.float64)
+    idx = np.full((k, n_pix), fill_idx, dtype=np.int64)
+    pred = None
+    if weights is not None:
+        pred = np.full((state.y.shape[1], n_pix), fill_pred, dtype=np.float64)
+    if valid.any():
+        d, i = kneighbors(state, np.asarray(X[valid], dtype=np.float64), k, deterministic, decimals)
+        dist[:, valid] = d.T
+        idx[:, valid] = i.T
+        if weights is not None:
+            pred[:, valid] = weighted_average(state.y, i, get_weights(d, weights)).T
+    out = (dist.reshape(k, *hw), idx.reshape(k, *hw))
+    return out + ((pred.reshape(-1, *hw),) if weights is not None else ())
+
+
+# ----------------------------------------------------------------------------------
 # comparators (SURVEY.md section 8c)
 # ----------------------------------------------------------------------------------
 def assert_tie_aware_equal(dist, idx, ref_dist, ref_idx, rtol=1e-5, atol=1e-9, gap_rtol=2e-6):

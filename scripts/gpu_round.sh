@@ -1,2 +1,2 @@
 set -x
-timeout 600 python scripts/hamming_bench.py weighted 2>&1 | tail -4
+timeout 600 python scripts/raster_bench.py 2>&1 | tail -4

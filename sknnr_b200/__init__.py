@@ -15,9 +15,11 @@ from ._estimators import (
     RFNNRegressor,
 )
 
+from .raster import kneighbors_raster, predict_raster
+
 __version__ = "0.1.0"
 
 __all__ = [
     "RawKNNRegressor", "EuclideanKNNRegressor", "MahalanobisKNNRegressor", "MSNRegressor",
-    "GNNRegressor", "RFNNRegressor", "GBNNRegressor",
+    "GNNRegressor", "RFNNRegressor", "GBNNRegressor", "kneighbors_raster", "predict_raster",
 ]

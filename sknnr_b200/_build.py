@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libsknnr_b200.so"
-SOURCES = ["api.cu", "search_simt.cu", "search_tc.cu", "refine.cu", "project.cu", "hamming.cu", "forest.cu", "misc.cu"]
+SOURCES = ["api.cu", "search_simt.cu", "search_tc.cu", "refine.cu", "project.cu", "hamming.cu", "forest.cu", "raster.cu", "misc.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "sknnr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -27,7 +27,7 @@ EXPORTS = [
     "sknnr_hamming_index_destroy", "sknnr_hamming_kneighbors",
     "sknnr_hamming_weighted_average", "sknnr_hamming_index_stats", "sknnr_host_alloc",
     "sknnr_host_free", "sknnr_measure_fp32_peak", "sknnr_forest_create", "sknnr_forest_destroy",
-    "sknnr_forest_apply", "sknnr_hamming_kneighbors_forest",
+    "sknnr_forest_apply", "sknnr_hamming_kneighbors_forest", "sknnr_raster_kneighbors",
 ]
 
 
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     lib.sknnr_forest_apply.argtypes = [vp, vp, i32, i64, i64, vp]
     lib.sknnr_hamming_kneighbors_forest.argtypes = [vp, vp, vp, i32, i64, i64, i64, i32, u32, i32, vp, vp, i32,
                                                     vp, vp]
+    lib.sknnr_raster_kneighbors.argtypes = [vp, vp, i32, i64, i64, i32, C.c_double, i32, u32, i32, vp, vp, i32,
+                                            vp, C.c_double, i64, C.c_double, C.POINTER(i64)]
     for name in EXPORTS:
         if name != "sknnr_last_error":
             getattr(lib, name).restype = C.c_int

@@ -101,6 +101,13 @@ struct Slot {
     DevBuf<long long> o_idx;
     DevBuf<double> o_pred;
     DevBuf<double> scratch;        // exact kernel distance scratch [grid, n_ref]
+    // raster front end: compacted feature rows, pixel -> row map, group offsets, band-major results
+    DevBuf<unsigned char> xc;
+    DevBuf<int> r_pos, r_cnt;
+    DevBuf<double> r_dist, r_pred;
+    DevBuf<long long> r_idx;
+    int *h_cnt = nullptr;          // pinned: valid pixels of the block in flight
+    cudaEvent_t ev_cnt = nullptr;
     std::vector<cudaEvent_t> evs;  // pooled (start, stop) pairs around the search kernels
     size_t ev_used = 0;            // events handed out since the last harvest
     int *h_fb = nullptr;           // pinned: [0] first-stage, [1] second-stage failures in flight
@@ -111,6 +118,10 @@ struct Slot {
         codes.release(); ids32.release(); qimg_h.release(); cand_idx.release();
         cand_thr.release(); cand_cnt.release(); fb.release(); o_dist.release();
         o_idx.release(); o_pred.release(); scratch.release();
+        xc.release(); r_pos.release(); r_cnt.release(); r_dist.release(); r_pred.release(); r_idx.release();
+        if (h_cnt) cudaFreeHost(h_cnt);
+        if (ev_cnt) cudaEventDestroy(ev_cnt);
+        h_cnt = nullptr; ev_cnt = nullptr;
         for (auto e : evs) cudaEventDestroy(e);
         evs.clear();
         ev_used = 0;
@@ -177,6 +188,8 @@ struct IndexBase {
             CK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
             CK(cudaHostAlloc((void **)&s.h_fb, 2 * sizeof(int), cudaHostAllocDefault));
             s.h_fb[0] = s.h_fb[1] = 0;
+            CK(cudaHostAlloc((void **)&s.h_cnt, sizeof(int), cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&s.ev_cnt, cudaEventDisableTiming));
         }
         return SKNNR_OK;
     }
@@ -752,6 +765,123 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             }
     }
     // a device-pointer call is not synchronised: its counters are harvested by the stats query
+    return SKNNR_OK;
+}
+
+// Raster front end (scope row f4).  Per block of pixels, on the block's slot stream:
+//   A: H2D of the d band segments -> mask + scan -> count to the host        (issued AHEAD blocks early)
+//   B: gather (compaction + transpose) -> run_chunk on the compacted rows -> scatter to band-major
+//      layers -> D2H of the layers
+// The count is the only value the host waits for; everything else stays asynchronous.
+int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype, int64_t n_pix,
+                            int64_t band_stride, int32_t use_nodata, double nodata, int32_t k,
+                            uint32_t flags, int32_t decimals, double *out_dist, int64_t *out_idx,
+                            int32_t weights, double *out_pred, double fill_dist, int64_t fill_idx,
+                            double fill_pred, int64_t *n_valid_out) {
+    if (!ix) return fail(SKNNR_EINVAL, "index is NULL");
+    if (flags & ~(uint32_t)SKNNR_DETERMINISTIC)
+        return fail(SKNNR_EINVAL, "sknnr_raster_kneighbors accepts SKNNR_DETERMINISTIC only");
+    int kk = 0;
+    int rc = check_query_args(ix->n_ref, ix->n_out, n_pix, k, flags, weights, bands, out_pred, kk);
+    if (rc != SKNNR_OK) return rc;
+    if (x_dtype != SKNNR_F64 && x_dtype != SKNNR_F32) return fail(SKNNR_EINVAL, "bad x_dtype");
+    if (band_stride < n_pix) return fail(SKNNR_EINVAL, "band_stride smaller than the number of pixels");
+    std::lock_guard<std::mutex> g(ix->lock);
+    CK(cudaSetDevice(ix->device));
+    const int d = ix->d_in;
+    const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
+    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; }
+    ix->stats = sknnr_stats{};
+    if (n_valid_out) *n_valid_out = 0;
+    if (n_pix == 0) return SKNNR_OK;
+
+    const int64_t chunk = std::min<int64_t>(g_opt.chunk_rows, (n_pix + 1023) / 1024 * 1024);
+    const int64_t n_blocks = (n_pix + chunk - 1) / chunk;
+    constexpr int AHEAD = 3;   // < kSlots: a slot is reused only after its previous block's D2H
+    auto stage_a = [&](int64_t b) -> int {
+        Slot &s = ix->slots[b % IndexBase::kSlots];
+        const int64_t p0 = b * chunk, rows = std::min(chunk, n_pix - p0);
+        CK(cudaStreamSynchronize(s.stream));   // the slot's previous block is complete
+        s.tail_pending = false;
+        ix->harvest(s);
+        CK(s.x.reserve((size_t)rows * d * esz));
+        CK(s.r_pos.reserve((size_t)rows));
+        CK(s.r_cnt.reserve((size_t)(rows + RASTER_GROUP - 1) / RASTER_GROUP + 2));
+        CK(cudaMemcpy2DAsync(s.x.p, (size_t)rows * esz, (const unsigned char *)bands + (size_t)p0 * esz,
+                             (size_t)band_stride * esz, (size_t)rows * esz, (size_t)d,
+                             cudaMemcpyHostToDevice, s.stream));
+        ix->stats.h2d_bytes += rows * d * (int64_t)esz;
+        const int groups = (int)((rows + RASTER_GROUP - 1) / RASTER_GROUP);
+        CK(launch_raster_mask(s.x.p, x_dtype == SKNNR_F32, rows, d, use_nodata, nodata, s.r_pos.p,
+                              s.r_cnt.p, s.r_cnt.p + groups + 1, s.stream));
+        CK(cudaMemcpyAsync(s.h_cnt, s.r_cnt.p + groups + 1, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaEventRecord(s.ev_cnt, s.stream));
+        ix->stats.kernel_launches += 2;
+        return SKNNR_OK;
+    };
+    int64_t issued = 0, valid_before = 0;
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        while (issued < n_blocks && issued < b + AHEAD) {
+            rc = stage_a(issued++);
+            if (rc != SKNNR_OK) return rc;
+        }
+        Slot &s = ix->slots[b % IndexBase::kSlots];
+        const int64_t p0 = b * chunk, rows = std::min(chunk, n_pix - p0);
+        CK(cudaEventSynchronize(s.ev_cnt));
+        const int64_t nv = *s.h_cnt;
+        if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen) ix->tensor_demoted = true;
+        double *o_dist = nullptr, *o_pred = nullptr;
+        long long *o_idx = nullptr;
+        if (nv > 0) {
+            CK(s.xc.reserve((size_t)nv * d * esz));
+            CK(launch_raster_gather(s.x.p, x_dtype == SKNNR_F32, rows, d, s.r_cnt.p, s.r_pos.p, s.xc.p, s.stream));
+            if (out_dist) { CK(s.o_dist.reserve((size_t)nv * k)); o_dist = s.o_dist.p; }
+            if (out_idx) { CK(s.o_idx.reserve((size_t)nv * k)); o_idx = s.o_idx.p; }
+            if (weights != SKNNR_W_NONE) { CK(s.o_pred.reserve((size_t)nv * ix->n_out)); o_pred = s.o_pred.p; }
+            rc = run_chunk(ix, s, s.xc.p, x_dtype == SKNNR_F32, d, false, nv, valid_before, k, flags, decimals,
+                           weights, o_dist, o_idx, o_pred);
+            if (rc != SKNNR_OK) return rc;
+            if (s.tail_pending) CK(cudaStreamWaitEvent(s.stream, s.ev_tail, 0));
+            ix->stats.kernel_launches++;
+        } else {
+            // nothing valid: every pixel of the block gets the fill values (pos is all zeros = "row 0",
+            // so flip it to -1 through a gather over an empty row set)
+            CK(s.xc.reserve(16));
+            CK(launch_raster_gather(s.x.p, x_dtype == SKNNR_F32, rows, d, s.r_cnt.p, s.r_pos.p, s.xc.p, s.stream));
+        }
+        ix->stats.n_queries += nv;
+        valid_before += nv;
+        if (out_dist) {
+            CK(s.r_dist.reserve((size_t)rows * k));
+            CK(launch_raster_scatter_f64(s.r_pos.p, rows, o_dist, k, fill_dist, s.r_dist.p, rows, s.stream));
+            CK(cudaMemcpy2DAsync(out_dist + p0, (size_t)n_pix * 8, s.r_dist.p, (size_t)rows * 8, (size_t)rows * 8,
+                                 (size_t)k, cudaMemcpyDeviceToHost, s.stream));
+            ix->stats.d2h_bytes += rows * k * 8;
+            ix->stats.kernel_launches++;
+        }
+        if (out_idx) {
+            CK(s.r_idx.reserve((size_t)rows * k));
+            CK(launch_raster_scatter_i64(s.r_pos.p, rows, o_idx, k, (long long)fill_idx, s.r_idx.p, rows, s.stream));
+            CK(cudaMemcpy2DAsync(out_idx + p0, (size_t)n_pix * 8, s.r_idx.p, (size_t)rows * 8, (size_t)rows * 8,
+                                 (size_t)k, cudaMemcpyDeviceToHost, s.stream));
+            ix->stats.d2h_bytes += rows * k * 8;
+            ix->stats.kernel_launches++;
+        }
+        if (weights != SKNNR_W_NONE) {
+            CK(s.r_pred.reserve((size_t)rows * ix->n_out));
+            CK(launch_raster_scatter_f64(s.r_pos.p, rows, o_pred, ix->n_out, fill_pred, s.r_pred.p, rows, s.stream));
+            CK(cudaMemcpy2DAsync(out_pred + p0, (size_t)n_pix * 8, s.r_pred.p, (size_t)rows * 8, (size_t)rows * 8,
+                                 (size_t)ix->n_out, cudaMemcpyDeviceToHost, s.stream));
+            ix->stats.d2h_bytes += rows * ix->n_out * 8;
+            ix->stats.kernel_launches++;
+        }
+    }
+    for (auto &s : ix->slots) {
+        CK(cudaStreamSynchronize(s.stream));
+        s.tail_pending = false;
+        ix->harvest(s);
+    }
+    if (n_valid_out) *n_valid_out = valid_before;
     return SKNNR_OK;
 }
 

@@ -143,6 +143,19 @@ cudaError_t launch_forest_apply(const void *X, int x_is_f32, long long ldx, long
                                 const ForestNode *nodes, const int *roots, int n_trees,
                                 uint16_t *out_codes, int *out_ids, long long ld_out, cudaStream_t st);
 
+// ---- raster.cu (band-major raster blocks in, band-major result layers out) ------------------
+constexpr int RASTER_GROUP = 1024;   // pixels per CTA of the mask / gather kernels
+// pos [rows] <- valid flags, counts [groups + 1] <- exclusive group offsets (+ total), *total_out <- total
+cudaError_t launch_raster_mask(const void *bands, int x_is_f32, long long rows, int d, int use_nodata,
+                               double nodata, int *pos, int *counts, int *total_out, cudaStream_t st);
+// pos <- compacted row (or -1); xc [n_valid, d] <- the valid pixels' feature rows, pixel order kept
+cudaError_t launch_raster_gather(const void *bands, int x_is_f32, long long rows, int d, const int *offs,
+                                 int *pos, void *xc, cudaStream_t st);
+cudaError_t launch_raster_scatter_f64(const int *pos, long long rows, const double *src, int width,
+                                      double fill, double *out, long long ld_out, cudaStream_t st);
+cudaError_t launch_raster_scatter_i64(const int *pos, long long rows, const long long *src, int width,
+                                      long long fill, long long *out, long long ld_out, cudaStream_t st);
+
 // ---- misc ------------------------------------------------------------------------------
 cudaError_t launch_fp32_peak(float *sink, int iters, int grid, cudaStream_t st);
 

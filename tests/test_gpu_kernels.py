@@ -520,3 +520,95 @@ def test_gb_forest_apply_and_fused_gbnn_query():
     d, i = est.kneighbors()
     np.testing.assert_array_equal(i, i_o)
     np.testing.assert_array_equal(d, d_o)
+
+
+# ---- raster front end (scope row f4) ---------------------------------------------------------
+@pytest.mark.parametrize(("hw", "dtype", "nodata", "chunk"), [
+    ((97, 131), np.float64, None, 4096), ((64, 200), np.float32, -9999.0, 4096),
+    ((33, 1000), np.float64, -1.0, 1 << 20), ((5, 7), np.float32, None, 4096),
+])
+def test_raster_kneighbors_equals_row_query_and_oracle(hw, dtype, nodata, chunk):
+    """Band-major image in, band-major layers out == the oracle's flatten / mask / query / scatter
+    loop, and bit-equal to this library's own row query on the unmasked pixels.  Covers several
+    pixel blocks per call (chunk_rows 4096), a block with no valid pixel, NaN / inf / nodata masks
+    and band-strided float32 input."""
+    from sknnr_b200 import _lib as L
+
+    d, k = 9, 5
+    R, _, y = _synthetic(3000, 10, d)
+    mean, scale = R.mean(0), R.std(0, ddof=1)
+    st = orc.FittedState("euclidean", fit_Z=(R - mean) / scale, y=y, center=mean, scale=scale)
+    ix = _index(st)
+    rng = np.random.default_rng(21)
+    n_pix = hw[0] * hw[1]
+    big = np.zeros((d, n_pix + 13), dtype=dtype)          # bands strided by more than n_pix
+    img = big[:, :n_pix]
+    img[...] = rng.standard_normal((d, n_pix)).astype(dtype)
+    drop = rng.random(n_pix) < 0.3
+    img[rng.integers(0, d, size=n_pix)[drop], np.flatnonzero(drop)] = np.nan
+    img[2, ::17] = np.inf
+    if nodata is not None:
+        img[rng.integers(0, d), ::11] = nodata
+    if n_pix > 3 * 4096:
+        img[0, 4096:8192] = np.nan                         # a whole block without a valid pixel
+    image = img.reshape(d, *hw)
+    L.set_option("chunk_rows", chunk)
+    try:
+        dist, idx, pred, n_valid = ix.query_raster(img, k, nodata=nodata, weights="distance", with_pred=True)
+    finally:
+        L.set_option("chunk_rows", 1 << 20)
+    X = img.T.astype(np.float64)
+    valid = np.isfinite(X).all(1)
+    if nodata is not None:
+        valid &= ~(img.T == nodata).any(1)
+    assert n_valid == int(valid.sum()) and 0 < n_valid < n_pix
+    # masked pixels: fill values
+    assert np.isnan(dist[:, ~valid]).all() and (idx[:, ~valid] == -1).all() and np.isnan(pred[:, ~valid]).all()
+    # unmasked pixels: bit-equal to the row query of the same library ...
+    d_r, i_r, p_r = ix.query(np.ascontiguousarray(img.T[valid]), k, weights="distance", with_pred=True)
+    np.testing.assert_array_equal(idx[:, valid].T, i_r)
+    np.testing.assert_array_equal(dist[:, valid].T, d_r)
+    np.testing.assert_array_equal(pred[:, valid].T, p_r)
+    # ... and equal to the oracle's raster loop
+    d_o, i_o, p_o = orc.raster_query(st, image, k=k, nodata=nodata, weights="distance")
+    orc.assert_tie_aware_equal(dist[:, valid].T, idx[:, valid].T, d_o.reshape(k, -1)[:, valid].T,
+                               i_o.reshape(k, -1)[:, valid].T, rtol=RTOL, atol=1e-7)
+    same = (idx == i_o.reshape(k, -1)).all(axis=0) & valid
+    np.testing.assert_allclose(pred[:, same], p_o.reshape(y.shape[1], -1)[:, same], rtol=RTOL, atol=1e-8)
+
+
+def test_raster_estimator_helpers():
+    """predict_raster / kneighbors_raster on fitted estimators: == predict / kneighbors on the
+    flattened valid pixels (uniform, distance and callable weights), fills, and input errors."""
+    import sknnr_b200 as S
+
+    g = load_golden("moscow_split.npz")
+    Xtr, ytr, Xte = g["X_train"], g["y_train"], g["X_test"]
+    rng = np.random.default_rng(3)
+    pix = np.vstack([Xte, Xtr[:27]])                        # 60 pixels -> 6 x 10 image
+    image = np.ascontiguousarray(pix.T).reshape(Xtr.shape[1], 6, 10).copy()
+    image[3, 2, 5] = np.nan
+    image[0, 0, 0] = -9999.0
+    valid = np.ones(60, dtype=bool)
+    valid[[25, 0]] = False
+    for cls, kw in ((S.MSNRegressor, {}), (S.EuclideanKNNRegressor, {"weights": "distance"}),
+                    (S.GNNRegressor, {"weights": lambda dd: 1.0 / (1.0 + dd)}), (S.RawKNNRegressor, {})):
+        est = cls(n_neighbors=5, **kw).fit(Xtr, ytr)
+        pr = S.predict_raster(est, image, nodata=-9999.0, fill_value=-1.0)
+        assert pr.shape == (ytr.shape[1], 6, 10)
+        flat = pr.reshape(ytr.shape[1], -1)
+        assert (flat[:, ~valid] == -1.0).all()
+        np.testing.assert_allclose(flat[:, valid].T, est.predict(pix[valid]), rtol=1e-12, atol=1e-12)
+        dist, idx = S.kneighbors_raster(est, image, nodata=-9999.0)
+        d_r, i_r = est.kneighbors(pix[valid])
+        np.testing.assert_array_equal(idx.reshape(5, -1)[:, valid].T, i_r)
+        np.testing.assert_array_equal(dist.reshape(5, -1)[:, valid].T, d_r)
+        assert (idx.reshape(5, -1)[:, ~valid] == -1).all()
+        only = S.kneighbors_raster(est, image.astype(np.float32), n_neighbors=3, nodata=-9999.0, return_distance=False)
+        assert only.shape == (3, 6, 10) and only.dtype == np.int64
+    with pytest.raises(ValueError, match="features"):
+        S.predict_raster(est, image[:-1])
+    with pytest.raises(ValueError, match="bands, height, width"):
+        S.predict_raster(est, pix)
+    with pytest.raises(NotImplementedError):
+        S.predict_raster(S.RFNNRegressor(n_estimators=3, n_neighbors=2).fit(Xtr, ytr), image)
