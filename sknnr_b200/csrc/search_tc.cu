@@ -212,39 +212,60 @@ struct ThrCnt {
 // KC-th smallest.  Entries equal to the new threshold are kept only up to KC entries in total;
 // the dropped ones are >= the threshold, which is all the certificate needs.  Called by all 32
 // lanes (data-independent network, no divergence).
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// (the slow paths take 32-bit shared-memory addresses, not generic pointers: `cs0` = address of
+// slot 0 of the calling thread's score column; slot j lies j * LD * 4 bytes further and the index
+// column CAP * LD * 4 bytes behind the score column - nothing else has to stay live in the scanner
+// loop on their behalf)
 template <int KC, int CAP, int LD>
-__device__ __noinline__ ThrCnt tc_compact_all(float *col_s, int *col_i, float thr, int cnt) {
+__device__ __noinline__ ThrCnt tc_compact_all(uint32_t cs0, float thr, int cnt) {
     static_assert(KC < CAP, "the buffer needs slack above KC");
     constexpr int SORT = CAP <= 16 ? 16 : 32;
+    constexpr uint32_t IOFF = CAP * LD * 4, STEP = LD * 4;
     __syncwarp();
     float s[SORT];
 #pragma unroll
-    for (int j = 0; j < SORT; ++j) s[j] = (j < CAP && j < cnt) ? col_s[j * LD] : SK_INF_F;
+    for (int j = 0; j < SORT; ++j) s[j] = (j < CAP && j < cnt) ? lds_f32(cs0 + j * STEP) : SK_INF_F;
     sort_regs<SORT>(s);
     const float t = s[KC - 1];  // +inf while the buffer holds fewer than KC entries
     int n_less = 0;
 #pragma unroll
     for (int j = 0; j < KC - 1; ++j) n_less += (s[j] < t) ? 1 : 0;
     int quota = KC - n_less;    // entries equal to t that may stay
-    int w = 0;
+    uint32_t w = cs0;
+    int nw = 0;
 #pragma unroll 4
     for (int j = 0; j < CAP; ++j) {
-        const float v = col_s[j * LD];
-        const int id = col_i[j * LD];
+        const float v = lds_f32(cs0 + j * STEP);
+        const int id = lds_s32(cs0 + IOFF + j * STEP);
         const bool valid = j < cnt;
         const bool lt = valid && (v < t);
         const bool eq = valid && (v == t) && quota > 0;
         if (eq) --quota;
         if (lt || eq) {
-            col_s[w * LD] = v;
-            col_i[w * LD] = id;
-            ++w;
+            st_shared_b32(w, __float_as_uint(v));
+            st_shared_b32(w + IOFF, (uint32_t)id);
+            w += STEP;
+            ++nw;
         }
     }
     __syncwarp();
     ThrCnt out;
     out.thr = fminf(thr, t);
-    out.cnt = w;
+    out.cnt = nw;
     return out;
 }
 
@@ -253,20 +274,20 @@ __device__ __noinline__ ThrCnt tc_compact_all(float *col_s, int *col_i, float th
 // lane and appends the survivors to lane L's candidate buffer, compacting the warp's buffers
 // whenever it would overflow.  Used when the in-lane path below ran out of buffer slots.
 template <int KC, int CAP, int LD>
-__device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, float *buf_s, int *buf_i, const float *scratch,
-                                               int col, int lane, float thr, int cnt) {
-    const float x = scratch[lane];                 // score of lane L's query vs reference idb+lane
+__device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, uint32_t cs0, uint32_t scratch_a, int lane,
+                                               float thr, int cnt) {
+    constexpr uint32_t IOFF = CAP * LD * 4, STEP = LD * 4;
+    const float x = lds_f32(scratch_a + 4u * lane);   // score of lane L's query vs reference idb+lane
     float thrL = __shfl_sync(SK_FULL, thr, L);
     int cntL = __shfl_sync(SK_FULL, cnt, L);
     unsigned pending = __ballot_sync(SK_FULL, x < thrL);
-    float *cs = buf_s + (col - lane + L);
-    int *ci = buf_i + (col - lane + L);
+    const uint32_t csL = cs0 + 4u * (uint32_t)(L - lane);   // lane L's column
     while (pending) {
         unsigned take = pending;
         if (cntL + __popc(pending) > CAP) {
             if (cntL > KC) {
                 if (lane == L) cnt = cntL;  // entries appended earlier in this loop
-                const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + col, buf_i + col, thr, cnt);
+                const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, cnt);
                 thr = tc.thr;
                 cnt = tc.cnt;
                 thrL = __shfl_sync(SK_FULL, thr, L);
@@ -280,8 +301,8 @@ __device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, float *buf_s, int
         }
         if ((take >> lane) & 1u) {
             const int slot = cntL + __popc(take & ((1u << lane) - 1u));
-            cs[slot * LD] = x;
-            ci[slot * LD] = idb + lane;
+            st_shared_b32(csL + slot * STEP, __float_as_uint(x));
+            st_shared_b32(csL + IOFF + slot * STEP, (uint32_t)(idb + lane));
         }
         cntL += __popc(take);
         pending &= ~take;
@@ -296,9 +317,6 @@ __device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, float *buf_s, int
 // in-lane append of the values of v[0..N) below thr (references id0 ..), N <= 3: every value is
 // stored at the lane's next free slot and the slot only advances for the values that qualify, so
 // there is no branch per value.  The caller guarantees N free slots.
-__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 // `ps` = shared-memory address of the lane's next free score slot (the index slot lies IOFF bytes
 // further); see the comment above for the protocol
 template <int N, int LD, int IOFF>
@@ -319,10 +337,9 @@ __device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, uint
 // any cross-lane traffic: the tree's intermediate minima (four groups of <= 9 values) locate the
 // values below the threshold, which the lane appends to its own candidate buffer column.
 // `cs0` = shared-memory address of slot 0 of this thread's candidate column.
-template <int KC, int CAP, int LD, bool DBG>
-__device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, float *buf_s, int *buf_i,
-                                           float *scratch, uint32_t cs0, int lane, float &thr, int &cnt,
-                                           int dbg) {
+template <int KC, int CAP, int LD, int EPI_WARPS, bool DBG>
+__device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uint32_t cs0, int lane, float &thr,
+                                           int &cnt, int dbg) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -349,8 +366,7 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
     }
     // keep room for the usual one or two appends; compaction also refreshes the thresholds
     if (__any_sync(SK_FULL, hit && cnt > CAP - 3)) {
-        const int col = threadIdx.x;
-        const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + col, buf_i + col, thr, cnt);
+        const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, cnt);
         thr = tc.thr;
         cnt = tc.cnt;
         hit = m < thr;
@@ -376,18 +392,19 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, flo
     unsigned ovf = __ballot_sync(SK_FULL, over);
     if (ovf) {
         if (over) cnt = cnt0;
+        // the warp's scratch line lies in front of the candidate buffers: [EPI_WARPS][32] floats
+        const uint32_t tid = threadIdx.x;
+        const uint32_t scratch_a = cs0 - 4u * tid - (uint32_t)EPI_WARPS * 128u + (tid >> 5) * 128u;
         while (ovf) {  // warp-uniform
             const int L = __ffs(ovf) - 1;
             ovf &= ovf - 1;
             __syncwarp();
             if (lane == L) {
-                float4 *sc = reinterpret_cast<float4 *>(scratch);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sc[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i = 0; i < 32; ++i) st_shared_b32(scratch_a + 4u * i, __float_as_uint(v[i]));
             }
             __syncwarp();
-            const ThrCnt tc = tc_process_coop<KC, CAP, LD>(L, idb, buf_s, buf_i, scratch, (int)threadIdx.x, lane,
-                                                           thr, cnt);
+            const ThrCnt tc = tc_process_coop<KC, CAP, LD>(L, idb, cs0, scratch_a, lane, thr, cnt);
             thr = tc.thr;
             cnt = tc.cnt;
         }
@@ -548,7 +565,6 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         const int h = (warp >> 2) % MT;
         const int qslot = h * TC_M + (warp & 3) * 32 + lane;   // query within the CTA = TMEM lane of M tile h
         const uint32_t tlane = tmem_base + (((uint32_t)((warp & 3) * 32)) << 16) + (uint32_t)(p * CH * 32);
-        float *scratch = scratch_all + warp * 32;
         float thr = SK_INF_F;
         int cnt = 0;
         uint32_t R[CH][32];
@@ -590,14 +606,13 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
                                aempty_a0 + 8u * sl, lane,
                            [&](const uint32_t (&r)[32], auto ic) {
                                constexpr int c = decltype(ic)::value;
-                               tc_process<KC, CAP, LD, DBG>(r, idb + c * 32, buf_s, buf_i, scratch, cs0, lane, thr,
-                                                       cnt, dbg);
+                               tc_process<KC, CAP, LD, EPI_WARPS, DBG>(r, idb + c * 32, cs0, lane, thr, cnt, dbg);
                            });
         }
 
         // ---- final compaction, then every thread writes the candidates of its (query, stream) ----
         {
-            const ThrCnt tc = tc_compact_all<KC, CAP, LD>(buf_s + col, buf_i + col, thr, cnt);
+            const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, cnt);
             thr = tc.thr;
             cnt = tc.cnt;
         }
