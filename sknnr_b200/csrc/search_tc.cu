@@ -49,6 +49,7 @@
 // TF32 values, [chunk][row][4]; core matrix = 8 rows x 16 B contiguous, SBO = 128 B between row
 // groups, LBO = rows * 16 B between K chunks.  The images are pre-arranged in HBM in exactly
 // this order, so a plain bulk copy stages them.
+#include <cstdio>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -201,6 +202,10 @@ __device__ __forceinline__ float tc_min32(const uint32_t (&r)[32]) {
     const float b3 = fminf(a[9], a[10]);
     return fminf(fminf(b0, b1), fminf(b2, b3));
 }
+
+// diagnostics of the debug instantiation (tc_debug bit 3): chunk visits, events, hit lanes,
+// proactive compactions, cooperative fallbacks - printed by the last CTA
+__device__ unsigned long long g_tc_counters[8];
 
 struct ThrCnt {
     float thr;
@@ -359,6 +364,11 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uin
     const float m = fminf(fminf(b0, b1), fminf(b2, b3));
     bool hit = m < thr;
     const unsigned hits = __ballot_sync(SK_FULL, hit);
+    if (DBG && (dbg & 8) && lane == 0) {
+        atomicAdd(&g_tc_counters[0], 1ull);
+        if (hits) atomicAdd(&g_tc_counters[1], 1ull);
+        atomicAdd(&g_tc_counters[2], (unsigned long long)__popc(hits));
+    }
     if (hits == 0u) return;
     if (DBG && (dbg & 1)) {  // timing experiment: count the hits, skip the hit path (results are wrong)
         cnt = (cnt + __popc(hits)) & 7;
@@ -366,6 +376,7 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uin
     }
     // keep room for the usual one or two appends; compaction also refreshes the thresholds
     if (__any_sync(SK_FULL, hit && cnt > CAP - 3)) {
+        if (DBG && (dbg & 8) && lane == 0) atomicAdd(&g_tc_counters[3], 1ull);
         const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, cnt);
         thr = tc.thr;
         cnt = tc.cnt;
@@ -391,6 +402,7 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uin
     // chunk for it through the cooperative path (which compacts as often as needed)
     unsigned ovf = __ballot_sync(SK_FULL, over);
     if (ovf) {
+        if (DBG && (dbg & 8) && lane == 0) atomicAdd(&g_tc_counters[4], (unsigned long long)__popc(ovf));
         if (over) cnt = cnt0;
         // the warp's scratch line lies in front of the candidate buffers: [EPI_WARPS][32] floats
         const uint32_t tid = threadIdx.x;
@@ -601,7 +613,8 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         // ---- main pass ----
         for (; t < n_seq; ++t) {
             const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
-            const int idb = (t - n_seed) * TC_N + p * CH * 32;
+            // warp-uniform (t and p are): kept in a uniform register instead of a spilled vector one
+            const int idb = __shfl_sync(SK_FULL, (t - n_seed) * TC_N + p * CH * 32, 0);
             tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), afull_a0 + 8u * sl, (uint32_t)((j >> 2) & 1),
                                aempty_a0 + 8u * sl, lane,
                            [&](const uint32_t (&r)[32], auto ic) {
@@ -637,6 +650,9 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     __syncthreads();
     tc_fence_after();
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
+    if (DBG && (dbg & 8) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
+        printf("tc counters (up to the last CTA): chunks %llu events %llu hit-lanes %llu compactions %llu coop %llu\n",
+               g_tc_counters[0], g_tc_counters[1], g_tc_counters[2], g_tc_counters[3], g_tc_counters[4]);
 }
 
 int g_tc_debug = 0;  // timing experiments only (set through the "tc_debug" option)
