@@ -470,7 +470,9 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     uint64_t *qbar = aempty + TC_SLOTS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qbar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the shuffle tells the compiler that `warp` (and every role / slot / address value derived from
+    // it) is warp-uniform: those live in uniform registers, not in the scanners' 96 vector registers
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full[s], 1);
@@ -613,8 +615,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         // ---- main pass ----
         for (; t < n_seq; ++t) {
             const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
-            // warp-uniform (t and p are): kept in a uniform register instead of a spilled vector one
-            const int idb = __shfl_sync(SK_FULL, (t - n_seed) * TC_N + p * CH * 32, 0);
+            const int idb = (t - n_seed) * TC_N + p * CH * 32;   // warp-uniform, like t and p
             tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), afull_a0 + 8u * sl, (uint32_t)((j >> 2) & 1),
                                aempty_a0 + 8u * sl, lane,
                            [&](const uint32_t (&r)[32], auto ic) {
