@@ -67,7 +67,11 @@ template <int MT_, int NS_, int CAP_> struct TcCfg {
     static constexpr int QT = MT * TC_M;                  // queries per CTA
     static constexpr int EPI_WARPS = MT * 4 * NS;         // scanner warps: (stream, M tile, lane quarter)
     static constexpr int THREADS = (EPI_WARPS + MT + 1) * 32;  // + MT MMA issuer warps + TMA producer warp
-    static constexpr int LD = QT * NS + 1;                // slot stride (odd: a column's slots hit 32 banks)
+    // slot stride of the candidate buffers: a power of two, so that a thread's slot count sits in the
+    // high bits of its buffer offset (4 * column + count * LD * 4).  Threads work on their own
+    // columns (bank = column mod 32, no conflicts); only the rare cooperative path, where a warp
+    // writes into ONE column, serialises on a bank.
+    static constexpr int LD = QT * NS;
     static constexpr int SORT = CAP <= 16 ? 16 : 32;      // width of the register sorting network
     static_assert(CAP <= SORT && CAP % 2 == 0, "candidate buffer shape");
     static constexpr int CH = 4 / NS;                     // 32-column chunks a scanner warp reads per job
@@ -325,15 +329,12 @@ __device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, uint32_t cs0, uin
 // `ps` = shared-memory address of the lane's next free score slot (the index slot lies IOFF bytes
 // further); see the comment above for the protocol
 template <int N, int LD, int IOFF>
-__device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, uint32_t &ps, int &cnt) {
+__device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, uint32_t bs0, uint32_t &pr) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        st_shared_b32(ps, __float_as_uint(v[j]));
-        st_shared_b32(ps + IOFF, (uint32_t)(id0 + j));
-        if (v[j] < thr) {
-            ps += LD * 4;
-            ++cnt;
-        }
+        st_shared_b32(bs0 + pr, __float_as_uint(v[j]));
+        st_shared_b32(bs0 + pr + IOFF, (uint32_t)(id0 + j));
+        if (v[j] < thr) pr += LD * 4;
     }
 }
 
@@ -342,9 +343,15 @@ __device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, uint
 // any cross-lane traffic: the tree's intermediate minima (four groups of <= 9 values) locate the
 // values below the threshold, which the lane appends to its own candidate buffer column.
 // `cs0` = shared-memory address of slot 0 of this thread's candidate column.
+// The thread's candidate count lives in `pr`, the offset of its next free score slot from the
+// start `bs0` of the score buffer: pr = 4 * column + count * LD * 4 with LD * 4 a power of two above
+// 4 * column, so "fewer than three free slots" is one compare of pr with a constant and the hit
+// path only ever bumps that offset.
 template <int KC, int CAP, int LD, int EPI_WARPS, bool DBG>
-__device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uint32_t cs0, int lane, float &thr,
-                                           int &cnt, int dbg) {
+__device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uint32_t bs0, int lane, float &thr,
+                                           uint32_t &pr, int dbg) {
+    constexpr uint32_t STEP = LD * 4, IOFF = CAP * LD * 4, FULL = (CAP - 2) * STEP;
+    static_assert((STEP & (STEP - 1)) == 0, "slot stride must be a power of two");
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -371,26 +378,27 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uin
     }
     if (hits == 0u) return;
     if (DBG && (dbg & 1)) {  // timing experiment: count the hits, skip the hit path (results are wrong)
-        cnt = (cnt + __popc(hits)) & 7;
+        pr = (pr & (STEP - 1)) + (((pr / STEP) + __popc(hits)) & 7) * STEP;
         return;
     }
-    // keep room for the usual one or two appends; compaction also refreshes the thresholds
-    if (__any_sync(SK_FULL, hit && cnt > CAP - 3)) {
+    // a triple is appended only while three slots are free (pr < FULL); keep room for the usual one
+    // or two appends - compaction also refreshes the thresholds
+    if (__any_sync(SK_FULL, hit && pr >= FULL)) {
         if (DBG && (dbg & 8) && lane == 0) atomicAdd(&g_tc_counters[3], 1ull);
-        const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, cnt);
+        const uint32_t c4 = pr & (STEP - 1);   // 4 * column
+        const ThrCnt tc = tc_compact_all<KC, CAP, LD>(bs0 + c4, thr, (int)(pr / STEP));
         thr = tc.thr;
-        cnt = tc.cnt;
+        pr = c4 + (uint32_t)tc.cnt * STEP;
         hit = m < thr;
     }
-    const int cnt0 = cnt;
-    bool over = false;
+    const uint32_t pr0 = pr;
     if (hit) {
-        uint32_t ps = cs0 + (uint32_t)(cnt * LD * 4);
-        // descend the tree: group of <= 9 values -> triple -> values; every triple needs 3 free slots
+        // descend the tree: group of <= 9 values -> triple -> values.  Out of room: bit 0 of pr is set
+        // (offsets are multiples of 4) and pr >= FULL stays true
 #define SK_TC_TRIPLE(I, N)                                                      \
         if (fminf(fminf(v[3 * (I)], v[3 * (I) + 1]), v[3 * (I) + ((N) == 3 ? 2 : 1)]) < thr) { \
-            if (cnt > CAP - 3) over = true;                                     \
-            else tc_leaf<N, LD, CAP * LD * 4>(v + 3 * (I), idb + 3 * (I), thr, ps, cnt);  \
+            if (pr >= FULL) pr |= 1u;                                           \
+            else tc_leaf<N, LD, IOFF>(v + 3 * (I), idb + 3 * (I), thr, bs0, pr); \
         }
         if (b0 < thr) { SK_TC_TRIPLE(0, 3) SK_TC_TRIPLE(1, 3) SK_TC_TRIPLE(2, 3) }
         if (b1 < thr) { SK_TC_TRIPLE(3, 3) SK_TC_TRIPLE(4, 3) SK_TC_TRIPLE(5, 3) }
@@ -400,13 +408,15 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uin
     }
     // rare: a lane found more values than it had free slots -> undo its appends and redo the
     // chunk for it through the cooperative path (which compacts as often as needed)
-    unsigned ovf = __ballot_sync(SK_FULL, over);
+    unsigned ovf = __ballot_sync(SK_FULL, (pr & 1u) != 0u);
     if (ovf) {
         if (DBG && (dbg & 8) && lane == 0) atomicAdd(&g_tc_counters[4], (unsigned long long)__popc(ovf));
-        if (over) cnt = cnt0;
+        if (pr & 1u) pr = pr0;
+        float thr2 = thr;
+        int cnt = (int)(pr / STEP);
+        const uint32_t c4 = pr & (STEP - 1), cs0 = bs0 + c4;
         // the warp's scratch line lies in front of the candidate buffers: [EPI_WARPS][32] floats
-        const uint32_t tid = threadIdx.x;
-        const uint32_t scratch_a = cs0 - 4u * tid - (uint32_t)EPI_WARPS * 128u + (tid >> 5) * 128u;
+        const uint32_t scratch_a = bs0 - (uint32_t)EPI_WARPS * 128u + (c4 >> 7) * 128u;
         while (ovf) {  // warp-uniform
             const int L = __ffs(ovf) - 1;
             ovf &= ovf - 1;
@@ -416,10 +426,12 @@ __device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uin
                 for (int i = 0; i < 32; ++i) st_shared_b32(scratch_a + 4u * i, __float_as_uint(v[i]));
             }
             __syncwarp();
-            const ThrCnt tc = tc_process_coop<KC, CAP, LD>(L, idb, cs0, scratch_a, lane, thr, cnt);
-            thr = tc.thr;
+            const ThrCnt tc = tc_process_coop<KC, CAP, LD>(L, idb, cs0, scratch_a, lane, thr2, cnt);
+            thr2 = tc.thr;
             cnt = tc.cnt;
         }
+        thr = thr2;
+        pr = c4 + (uint32_t)cnt * STEP;
     }
 }
 
@@ -580,7 +592,6 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         const int qslot = h * TC_M + (warp & 3) * 32 + lane;   // query within the CTA = TMEM lane of M tile h
         const uint32_t tlane = tmem_base + (((uint32_t)((warp & 3) * 32)) << 16) + (uint32_t)(p * CH * 32);
         float thr = SK_INF_F;
-        int cnt = 0;
         uint32_t R[CH][32];
         int t = 0;                            // position in the tile sequence; this warp's job = t * MT + h
         const uint32_t afull_a0 = smem_u32(afull), aempty_a0 = smem_u32(aempty);
@@ -613,6 +624,8 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         }
 
         // ---- main pass ----
+        const uint32_t bs0 = smem_u32(buf_s);   // uniform
+        uint32_t pr = 4u * (uint32_t)col;       // offset of this thread's next free slot (4 * col + count * LD * 4)
         for (; t < n_seq; ++t) {
             const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
             const int idb = (t - n_seed) * TC_N + p * CH * 32;   // warp-uniform, like t and p
@@ -620,13 +633,14 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
                                aempty_a0 + 8u * sl, lane,
                            [&](const uint32_t (&r)[32], auto ic) {
                                constexpr int c = decltype(ic)::value;
-                               tc_process<KC, CAP, LD, EPI_WARPS, DBG>(r, idb + c * 32, cs0, lane, thr, cnt, dbg);
+                               tc_process<KC, CAP, LD, EPI_WARPS, DBG>(r, idb + c * 32, bs0, lane, thr, pr, dbg);
                            });
         }
 
         // ---- final compaction, then every thread writes the candidates of its (query, stream) ----
+        int cnt;
         {
-            const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, cnt);
+            const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, (int)(pr / (uint32_t)(LD * 4)));
             thr = tc.thr;
             cnt = tc.cnt;
         }
@@ -668,7 +682,7 @@ static constexpr int TC_MT = 2;
 
 size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns) {
     const size_t a = (size_t)kc_tot * TC_M * TC_ROWB, b = (size_t)kc_tot * TC_N * TC_ROWB;
-    const size_t ld = (size_t)TC_MT * TC_M * ns + 1, cap = ns == 2 ? 16 : 32;
+    const size_t ld = (size_t)TC_MT * TC_M * ns, cap = ns == 2 ? 16 : 32;
     return TC_MT * a + nstage * b + (size_t)TC_MT * 4 * ns * 32 * 4 + 2 * cap * ld * 4 +
            (size_t)(2 * nstage + 2 * TC_SLOTS + 1) * 8 + 16;
 }
