@@ -624,7 +624,9 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         }
 
         // ---- main pass ----
-        const uint32_t bs0 = smem_u32(buf_s);   // uniform
+        // shared-window address of buf_s, derived from the array's own shared address (no generic
+        // pointer round trip): uniform
+        const uint32_t bs0 = smem_u32(smem_raw) + MT * a_bytes + (uint32_t)nstage * b_bytes + EPI_WARPS * 128u;
         uint32_t pr = 4u * (uint32_t)col;       // offset of this thread's next free slot (4 * col + count * LD * 4)
         for (; t < n_seq; ++t) {
             const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
