@@ -380,8 +380,8 @@ def run_ours(a, rank, world, local_rank):
             "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 = dense TF32, of measured" if peaks
                             else "fallback 1400 bf16 sustained / 2 (B200_PROFILING.md), of fallback"),
             # dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-row launch, ncu --set full
-            # (profiles/r01_search_tc_v9.md); scaled to this run's rows per launch
-            "traffic": 237.3e6 * (n_q / n_chunks) / float(1 << 20) if d == 32 else None,
+            # (profiles/r01_search_tc_v11.md); scaled to this run's rows per launch
+            "traffic": 231.9e6 * (n_q / n_chunks) / float(1 << 20) if d == 32 else None,
             "algorithmic_flops_per_launch": flops / n_chunks,
             "launches_per_step": n_chunks, "kernel_ms_per_step": search_ms,
             "fp32_simt_peak_measured": fp32_peak,

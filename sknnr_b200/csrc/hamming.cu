@@ -112,7 +112,8 @@ hamming_search_kernel(const uint32_t *__restrict__ qimg, const uint32_t *__restr
     uint64_t *empty = full + nstage;
     uint32_t *wq_s = reinterpret_cast<uint32_t *>(empty + nstage);   // WTD only
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full[s], 1);
@@ -356,7 +357,8 @@ cudaError_t launch_hamming_search(const uint32_t *qimg, const uint32_t *rimg, co
 // numerator >= scale * amax - err; the top k are final when the k-th exact numerator is below that.
 __global__ void __launch_bounds__(256)
 hamming_refine_kernel(HammingRefineArgs a, FinishParams fp) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * 8 + warp;
     if (q >= a.n_q) return;
     int id = 0x7fffffff, aq = 0;
@@ -403,7 +405,8 @@ cudaError_t launch_hamming_refine(const HammingRefineArgs &a, const FinishParams
 __global__ void __launch_bounds__(256)
 hamming_finish_kernel(const int *__restrict__ cand_idx, const int *__restrict__ cand_cnt, int kc,
                       const double *__restrict__ lut, long long n_q, FinishParams fp) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * 8 + warp;
     if (q >= n_q) return;
     double d = SK_INF_D;

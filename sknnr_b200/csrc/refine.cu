@@ -66,7 +66,8 @@ __device__ __forceinline__ double dist2_serial(const double *__restrict__ zq, co
 
 __global__ void __launch_bounds__(REFINE_WARPS * 32)
 refine_kernel(RefineArgs a, FinishParams fp) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * REFINE_WARPS + warp;
     if (q >= a.n_q || (a.n_rows_dev && q >= *a.n_rows_dev)) return;
     const double *zq = a.z64 + q * a.d;
@@ -167,7 +168,8 @@ exact_kernel(ExactArgs a, FinishParams fp) {
     __shared__ int red_i[EXACT_THREADS / 32];
     __shared__ double sel_d[MAXK];
     __shared__ int sel_i[MAXK];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long n_rows = a.list ? (long long)(*a.count) : a.n_q;
     double *scr = a.scratch + (size_t)blockIdx.x * a.n_ref;
     const int kk = fp.k + (fp.exclude_self ? 1 : 0);
@@ -240,7 +242,8 @@ __global__ void weighted_average_kernel(const long long *__restrict__ idx,
                                         const double *__restrict__ w, long long n_q, int k,
                                         const double *__restrict__ y, int n_out,
                                         double *__restrict__ out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (q >= n_q) return;
     double denom = 0.0;

@@ -52,7 +52,8 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
     uint64_t *empty = full + nstage;
     uint64_t *qbar = empty + nstage;
 
-    const int warp = threadIdx.x >> 5;
+    // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
