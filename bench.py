@@ -143,24 +143,31 @@ def cpu_reference_leg(a, rows, repeats=1):
 
     reg = KNeighborsRegressor(n_neighbors=a.k, algorithm="brute", weights="distance").fit(fit_Z, y)
     best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        Z = orc.affine_project(Q, mean, scale, None)
-        dist, idx = reg.kneighbors(Z)
-        dist, idx = orc.deterministic_order(dist, idx)
-        orc.weighted_average(y, idx, orc.get_weights(dist, "distance"))
-        best = min(best, time.perf_counter() - t0)
+    # every host thread the process may use, whatever OMP_NUM_THREADS says (torchrun exports
+    # OMP_NUM_THREADS=1 to its workers, which would make this a one-core number)
+    from threadpoolctl import threadpool_limits
+
+    with threadpool_limits(limits=usable_cores()):
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            Z = orc.affine_project(Q, mean, scale, None)
+            dist, idx = reg.kneighbors(Z)
+            dist, idx = orc.deterministic_order(dist, idx)
+            orc.weighted_average(y, idx, orc.get_weights(dist, "distance"))
+            best = min(best, time.perf_counter() - t0)
     return rows / best, best
 
 
-def host_threads():
+def usable_cores():
     try:
-        from threadpoolctl import threadpool_info
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return max(os.cpu_count() or 1, 1)
 
-        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        n = 1
-    return max(n, 1), os.cpu_count()
+
+def host_threads():
+    """(threads the CPU leg runs with, cores of the box)."""
+    return usable_cores(), os.cpu_count()
 
 
 def run_reference(a, rank):
