@@ -232,6 +232,16 @@ int sknnr_raster_kneighbors(sknnr_index *index, const void *bands, int32_t x_dty
                             int32_t weights, double *out_pred, double fill_dist, int64_t fill_idx,
                             double fill_pred, int64_t *n_valid);
 
+/* The same for the tree-node estimators (RFNN / GBNN): the unmasked pixels' feature rows are walked
+ * through `forest` on the device and searched in the Hamming index (forest->n_features bands).  */
+int sknnr_hamming_raster_kneighbors_forest(sknnr_hamming_index *index, sknnr_forest *forest,
+                                           const void *bands, int32_t x_dtype, int64_t n_pix,
+                                           int64_t band_stride, int32_t use_nodata, double nodata,
+                                           int32_t k, uint32_t flags, int32_t decimals,
+                                           double *out_dist, int64_t *out_idx, int32_t weights,
+                                           double *out_pred, double fill_dist, int64_t fill_idx,
+                                           double fill_pred, int64_t *n_valid);
+
 /* Pinned host memory for callers that stream large rasters (cudaHostAlloc / cudaFreeHost). */
 int sknnr_host_alloc(void **ptr, int64_t bytes);
 int sknnr_host_free(void *ptr);

@@ -109,6 +109,41 @@ class _IndexBase:
         return f
 
 
+def _raster_call(index, fn, handles, n_bands, bands, k, *, nodata=None, deterministic=True, decimals=10,
+                 weights=None, with_pred=False, return_distance=True, return_index=True, fill_dist=np.nan,
+                 fill_idx=-1, fill_pred=np.nan, out_dist=None, out_idx=None, out_pred=None):
+    """Shared body of the raster entry points (sknnr_raster_kneighbors and its Hamming + forest twin)."""
+    bands = np.asarray(bands)
+    if bands.dtype != np.float32:
+        bands = np.asarray(bands, dtype=np.float64)
+    if bands.ndim != 2 or bands.shape[0] != n_bands:
+        raise ValueError(f"the image has {bands.shape[0] if bands.ndim == 2 else '?'} bands, "
+                         f"but {n_bands} are expected")
+    n_pix = bands.shape[1]
+    if n_pix and (bands.strides[1] != bands.itemsize or bands.strides[0] % bands.itemsize
+                  or bands.strides[0] < n_pix * bands.itemsize):
+        bands = np.ascontiguousarray(bands)
+    stride = bands.strides[0] // bands.itemsize if bands.shape[0] > 1 and n_pix else max(n_pix, 1)
+    mode = _weights_mode(weights, with_pred)
+
+    def _out(given, shape, dt):
+        if given is None:
+            return np.empty(shape, dtype=dt)
+        if given.shape != shape or given.dtype != dt or not given.flags.c_contiguous:
+            raise ValueError(f"preallocated output must be C-contiguous {dt} of shape {shape}")
+        return given
+
+    dist = _out(out_dist, (k, n_pix), np.float64) if return_distance else None
+    idx = _out(out_idx, (k, n_pix), np.int64) if return_index else None
+    pred = _out(out_pred, (index.n_out, n_pix), np.float64) if mode != L.W_NONE else None
+    n_valid = C.c_int64(0)
+    L.check(fn(*handles, _ptr(bands), L.F32 if bands.dtype == np.float32 else L.F64, n_pix, stride,
+               0 if nodata is None else 1, 0.0 if nodata is None else float(nodata), int(k),
+               index._flags(False, deterministic), int(decimals), _ptr(dist), _ptr(idx), mode, _ptr(pred),
+               float(fill_dist), int(fill_idx), float(fill_pred), C.byref(n_valid)))
+    return dist, idx, pred, n_valid.value
+
+
 class KNNIndex(_IndexBase):
     """Fitted state of one Euclidean-space estimator on the device.
 
@@ -176,43 +211,13 @@ class KNNIndex(_IndexBase):
         return dist, idx, pred
 
     # -- raster query: band-major image in, band-major layers out (scope row f4) -------
-    def query_raster(self, bands, k, *, nodata=None, deterministic=True, decimals=10, weights=None,
-                     with_pred=False, return_distance=True, return_index=True, fill_dist=np.nan,
-                     fill_idx=-1, fill_pred=np.nan, out_dist=None, out_idx=None, out_pred=None):
+    def query_raster(self, bands, k, **kw):
         """``bands``: ``[d_in, n_pix]`` float32/float64, pixels contiguous within a band (bands may
         be strided).  A pixel with a NaN / inf band, or a band equal to ``nodata``, is masked and
         receives the fill values; the others are queried in pixel order.  Returns
         ``(dist [k, n_pix], idx [k, n_pix], pred [n_out, n_pix], n_valid)``; ``out_*`` are optional
         preallocated C-contiguous result arrays (e.g. from :func:`pinned_empty`)."""
-        bands = np.asarray(bands)
-        if bands.dtype != np.float32:
-            bands = np.asarray(bands, dtype=np.float64)
-        if bands.ndim != 2 or bands.shape[0] != self.d_in:
-            raise ValueError(f"the image has {bands.shape[0] if bands.ndim == 2 else '?'} bands, "
-                             f"but {self.d_in} are expected")
-        n_pix = bands.shape[1]
-        if n_pix and (bands.strides[1] != bands.itemsize or bands.strides[0] % bands.itemsize
-                      or bands.strides[0] < n_pix * bands.itemsize):
-            bands = np.ascontiguousarray(bands)
-        stride = bands.strides[0] // bands.itemsize if bands.shape[0] > 1 and n_pix else max(n_pix, 1)
-        mode = _weights_mode(weights, with_pred)
-        def _out(given, shape, dt):
-            if given is None:
-                return np.empty(shape, dtype=dt)
-            if given.shape != shape or given.dtype != dt or not given.flags.c_contiguous:
-                raise ValueError(f"preallocated output must be C-contiguous {dt} of shape {shape}")
-            return given
-
-        dist = _out(out_dist, (k, n_pix), np.float64) if return_distance else None
-        idx = _out(out_idx, (k, n_pix), np.int64) if return_index else None
-        pred = _out(out_pred, (self.n_out, n_pix), np.float64) if mode != L.W_NONE else None
-        n_valid = C.c_int64(0)
-        L.check(self._lib.sknnr_raster_kneighbors(
-            self._h, _ptr(bands), L.F32 if bands.dtype == np.float32 else L.F64, n_pix, stride,
-            0 if nodata is None else 1, 0.0 if nodata is None else float(nodata), int(k),
-            self._flags(False, deterministic), int(decimals), _ptr(dist), _ptr(idx), mode, _ptr(pred),
-            float(fill_dist), int(fill_idx), float(fill_pred), C.byref(n_valid)))
-        return dist, idx, pred, n_valid.value
+        return _raster_call(self, self._lib.sknnr_raster_kneighbors, (self._h,), self.d_in, bands, k, **kw)
 
     # -- device-pointer query (benchmarks, multi-GPU pipelines) -------------------------
     def query_device(self, x_ptr, x_is_f32, n_q, ldx, k, *, dist_ptr=0, idx_ptr=0, pred_ptr=0,
@@ -307,6 +312,12 @@ class HammingIndex(_IndexBase):
             int(row_offset), int(k), self._flags(False, deterministic), int(decimals), _ptr(dist),
             _ptr(idx), mode, _ptr(pred), None))
         return dist, idx, pred
+
+    def query_raster_forest(self, forest, bands, k, **kw):
+        """:meth:`KNNIndex.query_raster` for the tree-node estimators: the unmasked pixels' feature
+        rows are walked through ``forest`` and searched here without leaving the device."""
+        return _raster_call(self, self._lib.sknnr_hamming_raster_kneighbors_forest, (self._h, forest._h),
+                            forest.n_features, bands, k, **kw)
 
     def query_device(self, q_ptr, n_q, ldq, k, *, dist_ptr=0, idx_ptr=0, pred_ptr=0, weights=None,
                      deterministic=True, decimals=10, row_offset=0, stream=0):

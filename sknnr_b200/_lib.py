@@ -28,6 +28,7 @@ EXPORTS = [
     "sknnr_hamming_weighted_average", "sknnr_hamming_index_stats", "sknnr_host_alloc",
     "sknnr_host_free", "sknnr_measure_fp32_peak", "sknnr_forest_create", "sknnr_forest_destroy",
     "sknnr_forest_apply", "sknnr_hamming_kneighbors_forest", "sknnr_raster_kneighbors",
+    "sknnr_hamming_raster_kneighbors_forest",
 ]
 
 
@@ -88,6 +89,7 @@ def load() -> C.CDLL:
                                                     vp, vp]
     lib.sknnr_raster_kneighbors.argtypes = [vp, vp, i32, i64, i64, i32, C.c_double, i32, u32, i32, vp, vp, i32,
                                             vp, C.c_double, i64, C.c_double, C.POINTER(i64)]
+    lib.sknnr_hamming_raster_kneighbors_forest.argtypes = [vp] + lib.sknnr_raster_kneighbors.argtypes
     for name in EXPORTS:
         if name != "sknnr_last_error":
             getattr(lib, name).restype = C.c_int

@@ -768,19 +768,21 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     return SKNNR_OK;
 }
 
+}  // extern "C" (the raster pipeline below is a template)
+
 // Raster front end (scope row f4).  Per block of pixels, on the block's slot stream:
 //   A: H2D of the d band segments -> mask + scan -> count to the host        (issued AHEAD blocks early)
-//   B: gather (compaction + transpose) -> run_chunk on the compacted rows -> scatter to band-major
-//      layers -> D2H of the layers
+//   B: gather (compaction + transpose) -> `run` (the index's chunk pipeline on the compacted rows)
+//      -> scatter to band-major layers -> D2H of the layers
 // The count is the only value the host waits for; everything else stays asynchronous.
-int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype, int64_t n_pix,
-                            int64_t band_stride, int32_t use_nodata, double nodata, int32_t k,
-                            uint32_t flags, int32_t decimals, double *out_dist, int64_t *out_idx,
-                            int32_t weights, double *out_pred, double fill_dist, int64_t fill_idx,
-                            double fill_pred, int64_t *n_valid_out) {
-    if (!ix) return fail(SKNNR_EINVAL, "index is NULL");
+// run(slot, xc, n_valid, first_row, o_dist, o_idx, o_pred) enqueues the search of one block.
+template <class IX, class RUN>
+static int raster_impl(IX *ix, int d, const void *bands, int32_t x_dtype, int64_t n_pix, int64_t band_stride,
+                       int32_t use_nodata, double nodata, int32_t k, uint32_t flags, int32_t weights,
+                       double *out_dist, int64_t *out_idx, double *out_pred, double fill_dist,
+                       int64_t fill_idx, double fill_pred, int64_t *n_valid_out, RUN run) {
     if (flags & ~(uint32_t)SKNNR_DETERMINISTIC)
-        return fail(SKNNR_EINVAL, "sknnr_raster_kneighbors accepts SKNNR_DETERMINISTIC only");
+        return fail(SKNNR_EINVAL, "the raster calls accept SKNNR_DETERMINISTIC only");
     int kk = 0;
     int rc = check_query_args(ix->n_ref, ix->n_out, n_pix, k, flags, weights, bands, out_pred, kk);
     if (rc != SKNNR_OK) return rc;
@@ -788,7 +790,6 @@ int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype,
     if (band_stride < n_pix) return fail(SKNNR_EINVAL, "band_stride smaller than the number of pixels");
     std::lock_guard<std::mutex> g(ix->lock);
     CK(cudaSetDevice(ix->device));
-    const int d = ix->d_in;
     const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
     for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; }
     ix->stats = sknnr_stats{};
@@ -829,25 +830,19 @@ int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype,
         const int64_t p0 = b * chunk, rows = std::min(chunk, n_pix - p0);
         CK(cudaEventSynchronize(s.ev_cnt));
         const int64_t nv = *s.h_cnt;
-        if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen) ix->tensor_demoted = true;
         double *o_dist = nullptr, *o_pred = nullptr;
         long long *o_idx = nullptr;
+        // (with nv == 0 the gather only turns the all-zero flags into "-1 = masked")
+        CK(s.xc.reserve((size_t)std::max<int64_t>(nv, 1) * d * esz));
+        CK(launch_raster_gather(s.x.p, x_dtype == SKNNR_F32, rows, d, s.r_cnt.p, s.r_pos.p, s.xc.p, s.stream));
+        ix->stats.kernel_launches++;
         if (nv > 0) {
-            CK(s.xc.reserve((size_t)nv * d * esz));
-            CK(launch_raster_gather(s.x.p, x_dtype == SKNNR_F32, rows, d, s.r_cnt.p, s.r_pos.p, s.xc.p, s.stream));
             if (out_dist) { CK(s.o_dist.reserve((size_t)nv * k)); o_dist = s.o_dist.p; }
             if (out_idx) { CK(s.o_idx.reserve((size_t)nv * k)); o_idx = s.o_idx.p; }
             if (weights != SKNNR_W_NONE) { CK(s.o_pred.reserve((size_t)nv * ix->n_out)); o_pred = s.o_pred.p; }
-            rc = run_chunk(ix, s, s.xc.p, x_dtype == SKNNR_F32, d, false, nv, valid_before, k, flags, decimals,
-                           weights, o_dist, o_idx, o_pred);
+            rc = run(s, (const void *)s.xc.p, nv, valid_before, o_dist, o_idx, o_pred);
             if (rc != SKNNR_OK) return rc;
             if (s.tail_pending) CK(cudaStreamWaitEvent(s.stream, s.ev_tail, 0));
-            ix->stats.kernel_launches++;
-        } else {
-            // nothing valid: every pixel of the block gets the fill values (pos is all zeros = "row 0",
-            // so flip it to -1 through a gather over an empty row set)
-            CK(s.xc.reserve(16));
-            CK(launch_raster_gather(s.x.p, x_dtype == SKNNR_F32, rows, d, s.r_cnt.p, s.r_pos.p, s.xc.p, s.stream));
         }
         ix->stats.n_queries += nv;
         valid_before += nv;
@@ -883,6 +878,25 @@ int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype,
     }
     if (n_valid_out) *n_valid_out = valid_before;
     return SKNNR_OK;
+}
+
+extern "C" {
+
+int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype, int64_t n_pix,
+                            int64_t band_stride, int32_t use_nodata, double nodata, int32_t k,
+                            uint32_t flags, int32_t decimals, double *out_dist, int64_t *out_idx,
+                            int32_t weights, double *out_pred, double fill_dist, int64_t fill_idx,
+                            double fill_pred, int64_t *n_valid_out) {
+    if (!ix) return fail(SKNNR_EINVAL, "index is NULL");
+    return raster_impl(ix, ix->d_in, bands, x_dtype, n_pix, band_stride, use_nodata, nodata, k, flags, weights,
+                       out_dist, out_idx, out_pred, fill_dist, fill_idx, fill_pred, n_valid_out,
+                       [&](Slot &s, const void *xc, int64_t nv, int64_t row0, double *o_dist, long long *o_idx,
+                           double *o_pred) -> int {
+                           if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen)
+                               ix->tensor_demoted = true;
+                           return run_chunk(ix, s, xc, x_dtype == SKNNR_F32, ix->d_in, false, nv, row0, k, flags,
+                                            decimals, weights, o_dist, o_idx, o_pred);
+                       });
 }
 
 int sknnr_transform(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_q, int64_t ldx,
@@ -1249,6 +1263,31 @@ static int hamming_kneighbors_impl(sknnr_hamming_index *ix, sknnr_forest *forest
         }
     }
     return SKNNR_OK;
+}
+
+// Raster front end for the tree-node estimators: band-major pixels -> compacted feature rows ->
+// forest walk -> node codes -> Hamming search -> band-major layers, all on the device.
+int sknnr_hamming_raster_kneighbors_forest(sknnr_hamming_index *ix, sknnr_forest *forest, const void *bands,
+                                           int32_t x_dtype, int64_t n_pix, int64_t band_stride,
+                                           int32_t use_nodata, double nodata, int32_t k, uint32_t flags,
+                                           int32_t decimals, double *out_dist, int64_t *out_idx,
+                                           int32_t weights, double *out_pred, double fill_dist,
+                                           int64_t fill_idx, double fill_pred, int64_t *n_valid_out) {
+    if (!ix || !forest) return fail(SKNNR_EINVAL, "index or forest is NULL");
+    if (forest->n_trees != ix->n_trees) return fail(SKNNR_EINVAL, "forest and index disagree on the number of trees");
+    if (forest->device != ix->device) return fail(SKNNR_EINVAL, "forest and index live on different devices");
+    return raster_impl(ix, forest->n_features, bands, x_dtype, n_pix, band_stride, use_nodata, nodata, k, flags,
+                       weights, out_dist, out_idx, out_pred, fill_dist, fill_idx, fill_pred, n_valid_out,
+                       [&](Slot &s, const void *xc, int64_t nv, int64_t row0, double *o_dist, long long *o_idx,
+                           double *o_pred) -> int {
+                           CK(s.codes.reserve((size_t)nv * ix->n_trees));
+                           CK(launch_forest_apply(xc, x_dtype == SKNNR_F32, forest->n_features, nv,
+                                                  forest->n_features, forest->d_nodes, forest->d_roots,
+                                                  forest->n_trees, s.codes.p, nullptr, ix->n_trees, s.stream));
+                           ix->stats.kernel_launches++;
+                           return run_hamming_chunk(ix, s, s.codes.p, ix->n_trees, nv, row0, k, flags, decimals,
+                                                    weights, o_dist, o_idx, o_pred);
+                       });
 }
 
 int sknnr_hamming_kneighbors(sknnr_hamming_index *ix, const uint16_t *q_codes, int64_t n_q,

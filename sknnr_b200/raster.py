@@ -17,14 +17,10 @@ __all__ = ["kneighbors_raster", "predict_raster"]
 
 
 def _regressor_and_image(est, image):
+    """(regressor, query function (bands, k, **kw) -> (dist, idx, pred, n_valid), bands, (H, W))."""
     check_is_fitted(est)
     reg = getattr(est, "regressor_", est)
-    if reg._metric_kind() != "euclidean":
-        raise NotImplementedError(
-            "the raster front end covers the Euclidean-space estimators; tree-node estimators "
-            "(RFNN / GBNN) take pixel rows through kneighbors / predict")
-    if hasattr(est, "transformer_") and not est._fusable():
-        raise NotImplementedError("the estimator's transformer is not an affine map")
+    kind = reg._metric_kind()
     image = np.asarray(image)
     if image.ndim != 3:
         raise ValueError(f"expected an image of shape [bands, height, width], got {image.shape}")
@@ -35,8 +31,20 @@ def _regressor_and_image(est, image):
     if image.shape[0] != n_bands:
         raise ValueError(f"X has {image.shape[0]} features, but {type(est).__name__} is expecting "
                          f"{n_bands} features as input.")
+    ix = reg._get_index()
+    if kind == "euclidean":
+        if hasattr(est, "transformer_") and not est._fusable():
+            raise NotImplementedError("the estimator's transformer is not an affine map")
+        query = ix.query_raster
+    elif hasattr(est, "transformer_") and est._forest_fusable():
+        forest = est.transformer_._forest_index(reg.__dict__.get("_node_tables"))
+        query = lambda bands, k, **kw: ix.query_raster_forest(forest, bands, k, **kw)  # noqa: E731
+    else:
+        raise NotImplementedError(
+            "a raster needs raw feature bands: Hamming searches are covered through a fitted "
+            "tree-node transformer (RFNNRegressor / GBNNRegressor), not on bare node IDs")
     bands = image.reshape(image.shape[0], -1)      # a view for C-ordered (and band-strided) images
-    return reg, bands, image.shape[1:]
+    return reg, ix, query, bands, image.shape[1:]
 
 
 def kneighbors_raster(est, image, n_neighbors=None, *, nodata=None, return_distance=True,
@@ -44,9 +52,9 @@ def kneighbors_raster(est, image, n_neighbors=None, *, nodata=None, return_dista
     """Neighbours of every pixel.  Returns ``(dist [k, H, W] float64, idx [k, H, W] int64)`` (or
     ``idx`` alone); masked pixels (any band NaN / inf / ``nodata``) hold the fill values.  ``idx``
     are row numbers of the training set, as ``kneighbors(return_dataframe_index=False)`` gives."""
-    reg, bands, hw = _regressor_and_image(est, image)
+    reg, _, query, bands, hw = _regressor_and_image(est, image)
     k = reg._check_k(n_neighbors, False, bands.shape[1])
-    dist, idx, _, _ = reg._get_index().query_raster(
+    dist, idx, _, _ = query(
         bands, k, nodata=nodata, deterministic=use_deterministic_ordering,
         decimals=reg.DISTANCE_PRECISION_DECIMALS, return_distance=return_distance,
         fill_dist=fill_distance, fill_idx=fill_index)
@@ -56,17 +64,16 @@ def kneighbors_raster(est, image, n_neighbors=None, *, nodata=None, return_dista
 
 def predict_raster(est, image, *, nodata=None, fill_value=np.nan):
     """``est.predict`` for every pixel: ``[n_targets, H, W]`` float64, ``fill_value`` where masked."""
-    reg, bands, hw = _regressor_and_image(est, image)
+    reg, ix, query, bands, hw = _regressor_and_image(est, image)
     w = reg.weights
     k = reg._check_k(None, False, bands.shape[1])
-    ix = reg._get_index()
     if w in (None, "uniform", "distance"):
-        _, _, pred, _ = ix.query_raster(bands, k, nodata=nodata, weights=w, with_pred=True,
-                                        decimals=reg.DISTANCE_PRECISION_DECIMALS,
-                                        return_distance=False, return_index=False, fill_pred=fill_value)
+        _, _, pred, _ = query(bands, k, nodata=nodata, weights=w, with_pred=True,
+                              decimals=reg.DISTANCE_PRECISION_DECIMALS,
+                              return_distance=False, return_index=False, fill_pred=fill_value)
         return pred.reshape(pred.shape[0], *hw)
     # callable weights: evaluated by Python on the valid pixels' distances, averaged on the device
-    dist, idx, _, _ = ix.query_raster(bands, k, nodata=nodata, decimals=reg.DISTANCE_PRECISION_DECIMALS)
+    dist, idx, _, _ = query(bands, k, nodata=nodata, decimals=reg.DISTANCE_PRECISION_DECIMALS)
     valid = idx[0] >= 0
     out = np.full((ix.n_out, bands.shape[1]), fill_value, dtype=np.float64)
     if valid.any():

@@ -610,5 +610,19 @@ def test_raster_estimator_helpers():
         S.predict_raster(est, image[:-1])
     with pytest.raises(ValueError, match="bands, height, width"):
         S.predict_raster(est, pix)
+    # tree-node estimators: forest walk + Hamming search behind the same front end
+    import warnings
+
+    for cls, kw in ((S.RFNNRegressor, {"n_estimators": 7}), (S.GBNNRegressor, {"n_estimators": 9, "weights": "distance"})):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", FutureWarning)
+            est = cls(n_neighbors=4, random_state=0, **kw).fit(Xtr, ytr[:, :3])
+        pr = S.predict_raster(est, image, nodata=-9999.0).reshape(3, -1)
+        assert np.isnan(pr[:, ~valid]).all()
+        np.testing.assert_allclose(pr[:, valid].T, est.predict(pix[valid]), rtol=1e-12, atol=1e-12)
+        dist, idx = S.kneighbors_raster(est, image.astype(np.float32), nodata=-9999.0)
+        d_r, i_r = est.kneighbors(pix[valid].astype(np.float32))
+        np.testing.assert_array_equal(idx.reshape(4, -1)[:, valid].T, i_r)
+        np.testing.assert_array_equal(dist.reshape(4, -1)[:, valid].T, d_r)
     with pytest.raises(NotImplementedError):
-        S.predict_raster(S.RFNNRegressor(n_estimators=3, n_neighbors=2).fit(Xtr, ytr), image)
+        S.predict_raster(S.RawKNNRegressor(n_neighbors=2, metric="hamming").fit(np.arange(40).reshape(10, 4) % 3, ytr[:10]), image[:4])
