@@ -1,2 +1,2 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q -k "raster" 2>&1 | tail -25
+timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_full.log 2>&1

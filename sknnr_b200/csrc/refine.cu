@@ -31,7 +31,24 @@ __device__ __forceinline__ double dist2_lane(const double *__restrict__ zq, cons
     double acc = 0.0;
     for (int k = h; k < d; k += 16) {
         const double df = zq[k] - __ldg(r + k);
-        acc += df * df;
+        acc = __fma_rn(df, df, acc);   // explicit: which product is fused must not be the compiler's choice
+    }
+    return acc;
+}
+// The same partial with the query's features already in registers (zr[j] = zq[h + 16 j], 0 past the
+// end) and the loop unrolled: a missing feature contributes fma(0, 0, acc) = acc, so the bits equal
+// dist2_lane's.
+template <int DJ>
+__device__ __forceinline__ double dist2_lane_regs(const double (&zr)[DJ], const double *__restrict__ r, int d,
+                                                  int h) {
+    double rv[DJ];
+#pragma unroll
+    for (int j = 0; j < DJ; ++j) rv[j] = (h + 16 * j < d) ? __ldg(r + h + 16 * j) : 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < DJ; ++j) {
+        const double df = zr[j] - rv[j];
+        acc = __fma_rn(df, df, acc);
     }
     return acc;
 }
@@ -52,7 +69,7 @@ __device__ __forceinline__ double dist2_serial(const double *__restrict__ zq, co
         for (int h = 0; h < 16; ++h) {
             if (k0 + h < d) {
                 const double df = zq[k0 + h] - r[k0 + h];
-                p[h] += df * df;
+                p[h] = __fma_rn(df, df, p[h]);
             }
         }
     }
@@ -64,6 +81,8 @@ __device__ __forceinline__ double dist2_serial(const double *__restrict__ zq, co
     return p[0];
 }
 
+// DJ = ceil(d / 16) for d <= 64 (the query row lives in DJ registers per lane), 0 = any d
+template <int DJ>
 __global__ void __launch_bounds__(REFINE_WARPS * 32)
 refine_kernel(RefineArgs a, FinishParams fp) {
     // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
@@ -80,12 +99,22 @@ refine_kernel(RefineArgs a, FinishParams fp) {
     int id = 0x7fffffff;
     double d2 = SK_INF_D;
     const int my_c = lane < a.kc ? a.cand_idx[q * a.kc + lane] : -1;   // kc <= 32: one coalesced load
+    double zr[DJ > 0 ? DJ : 1];
+    if constexpr (DJ > 0) {
+#pragma unroll
+        for (int j = 0; j < DJ; ++j) zr[j] = (hl + 16 * j < a.d) ? zq[hl + 16 * j] : 0.0;
+    }
 #pragma unroll 4
     for (int i = 0; 2 * i < a.kc; ++i) {
         const int c = __shfl_sync(SK_FULL, my_c, (2 * i + half) & 31);
         const bool have = c >= 0 && c < a.n_ref;
         double acc = 0.0;
-        if (have) acc = dist2_lane(zq, a.ref64 + (long long)c * a.d, a.d, hl);
+        if (have) {
+            if constexpr (DJ > 0)
+                acc = dist2_lane_regs<DJ>(zr, a.ref64 + (long long)c * a.d, a.d, hl);
+            else
+                acc = dist2_lane(zq, a.ref64 + (long long)c * a.d, a.d, hl);
+        }
         acc = dist2_reduce16(acc);
         if (small) {
             const double other = __shfl_xor_sync(SK_FULL, acc, 16);   // the other half warp's candidate
@@ -138,7 +167,13 @@ refine_kernel(RefineArgs a, FinishParams fp) {
 cudaError_t launch_refine(const RefineArgs &a, const FinishParams &fp, cudaStream_t st) {
     if (a.n_q <= 0) return cudaSuccess;
     const long long grid = (a.n_q + REFINE_WARPS - 1) / REFINE_WARPS;
-    refine_kernel<<<(unsigned)grid, REFINE_WARPS * 32, 0, st>>>(a, fp);
+    switch (a.d <= 64 ? (a.d + 15) / 16 : 0) {
+        case 1: refine_kernel<1><<<(unsigned)grid, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+        case 2: refine_kernel<2><<<(unsigned)grid, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+        case 3: refine_kernel<3><<<(unsigned)grid, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+        case 4: refine_kernel<4><<<(unsigned)grid, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+        default: refine_kernel<0><<<(unsigned)grid, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+    }
     return cudaGetLastError();
 }
 
