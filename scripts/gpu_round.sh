@@ -1,2 +1,2 @@
 set -x
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_2gpu.log 2>&1; tail -1 gpurun_out/bench_2gpu.log | cut -c1-260
+timeout 900 python -m pytest tests -m gpu -x -q -k "c4_shape" --durations=3 2>&1 | tail -15

@@ -626,3 +626,102 @@ def test_raster_estimator_helpers():
         np.testing.assert_array_equal(dist.reshape(4, -1)[:, valid].T, d_r)
     with pytest.raises(NotImplementedError):
         S.predict_raster(S.RawKNNRegressor(n_neighbors=2, metric="hamming").fit(np.arange(40).reshape(10, 4) % 3, ytr[:10]), image[:4])
+
+
+# ---- BASELINE.json's full C3 size, through size-independent properties ----------------------
+def test_full_size_c3_properties():
+    """10M queries x 50k plots x 32 features, k = 7 (the configuration the metric is quoted on).  The
+    oracle cannot run this in seconds, so the result is checked through properties that do not
+    depend on size: ordering, index validity, distances re-derived from the returned indices,
+    exact agreement with the oracle on a random sample of rows, invariance under sharding /
+    re-chunking (checksum of checksums), and the prediction identity."""
+    from sknnr_b200 import _lib as L
+
+    n_ref, n_q, d, k = 50_000, 10_000_000, 32, 7
+    R = np.random.default_rng(0).standard_normal((n_ref, d))
+    y = np.random.default_rng(1).standard_normal((n_ref, 8))
+    mean, scale = R.mean(0), R.std(0, ddof=1)
+    st = orc.FittedState("euclidean", fit_Z=(R - mean) / scale, y=y, center=mean, scale=scale)
+    ix = _index(st)
+    Q = np.empty((n_q, d))
+    for b, ss in enumerate(np.random.SeedSequence(2).spawn(10)):
+        Q[b * 1_000_000:(b + 1) * 1_000_000] = np.random.default_rng(ss).standard_normal((1_000_000, d))
+    dist, idx, pred = ix.query(Q, k, weights="uniform", with_pred=True, deterministic=False)
+    stats = ix.stats()
+    assert stats["engine"] == L.ENGINE_TENSOR and stats["n_queries"] == n_q
+    assert stats["n_fallback"] < n_q // 50                      # the filter certifies nearly every row
+    # ordering and validity
+    assert np.all(np.diff(dist, axis=1) >= 0) and np.all(dist > 0) and np.all(np.isfinite(dist))
+    assert idx.min() >= 0 and idx.max() < n_ref
+    srt = np.sort(idx, axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])                   # no plot twice in a row's list
+    # distances belong to the returned indices (float64 recomputation on a sample)
+    rng = np.random.default_rng(5)
+    rows = rng.choice(n_q, size=20_000, replace=False)
+    Zs = (Q[rows] - mean) / scale
+    recomputed = np.sqrt(((Zs[:, None, :] - st.fit_Z[idx[rows]]) ** 2).sum(-1))
+    np.testing.assert_allclose(dist[rows], recomputed, rtol=1e-12, atol=1e-12)
+    # exact agreement with the oracle on a sample of rows
+    sub = rows[:3000]
+    d_o, i_o = orc.kneighbors(st, Q[sub], k=k, deterministic=False)
+    orc.assert_tie_aware_equal(dist[sub], idx[sub], d_o, i_o, rtol=RTOL, atol=1e-7)
+    assert (idx[sub] == i_o).mean() > 0.9999
+    # prediction identity: uniform weights = mean of the neighbours' targets
+    np.testing.assert_allclose(pred[rows], y[idx[rows]].mean(axis=1), rtol=1e-12, atol=1e-12)
+    # sharding / re-chunking invariance: two half calls with row offsets, another chunk size
+    h = n_q // 2
+    L.set_option("chunk_rows", 1 << 19)
+    try:
+        d_a, i_a, _ = ix.query(Q[:h], k, deterministic=False)
+        d_b, i_b, _ = ix.query(Q[h:], k, deterministic=False, row_offset=h)
+    finally:
+        L.set_option("chunk_rows", 1 << 20)
+    w = np.arange(1, k + 1, dtype=np.int64)
+    assert int((i_a * w).sum() + (i_b * w).sum()) == int((idx * w).sum())     # checksum of checksums
+    assert np.array_equal(i_a, idx[:h]) and np.array_equal(d_b, dist[h:])
+
+
+def test_c4_shape_hamming_properties():
+    """C4 shape (20k plots x 500 trees, k = 7) at 500k queries - a twentieth of BASELINE.json's 10M,
+    which would need 10 GB of node codes on the host - through the same size-independent properties:
+    ordering by (distance, index), distances re-derived from the returned indices, oracle agreement
+    on a sample, sharding invariance.  Equal weights (RFNN) and boosting-like unequal weights (GBNN)."""
+    n_ref, n_q, T, k = 20_000, 500_000, 500, 7
+    rng = np.random.default_rng(0)
+    Rc = rng.integers(0, 60, size=(n_ref, T)).astype(np.uint16)
+    Qc = Rc[rng.integers(0, n_ref, size=n_q)].copy()
+    flip = rng.random(Qc.shape) < 0.5
+    Qc[flip] = rng.integers(0, 60, size=int(flip.sum())).astype(np.uint16)
+    w_eq = np.full(T, 1.0 / T)
+    w_gb = np.tile(0.97 ** np.arange(100), 5) * (1 + 0.1 * rng.random(T))
+    w_gb /= w_gb.sum()
+    rows = rng.choice(n_q, size=400, replace=False)
+    for w in (w_eq, w_gb):
+        ix = _ham_index(Rc, w)
+        dist, idx, _ = ix.query(Qc, k, deterministic=False)   # plain (distance, index) order
+        assert ix.stats()["n_fallback"] <= n_q // 100
+        assert np.all(np.diff(dist, axis=1) >= 0)
+        tie = np.diff(dist, axis=1) == 0
+        assert np.all(np.diff(idx, axis=1)[tie] > 0)            # the lowest index wins every tie
+        assert idx.min() >= 0 and idx.max() < n_ref
+        # distances belong to the returned indices: SciPy's left-to-right float64 sums, bit for bit
+        mism = Qc[rows][:, None, :] != Rc[idx[rows]]
+        want = np.empty((len(rows), k))
+        for a in range(len(rows)):
+            for b in range(k):
+                acc = 0.0
+                for t in np.flatnonzero(mism[a, b]):
+                    acc += w[t]
+                want[a, b] = acc
+        den = 0.0
+        for t in range(T):
+            den += w[t]
+        assert np.array_equal(dist[rows], want / den)
+        st = orc.FittedState("hamming", fit_Z=Rc.astype(np.int64), y=np.zeros((n_ref, 1)), hamming_w=w)
+        d_o, i_o = orc.kneighbors(st, Qc[rows].astype(np.int64), k=k, deterministic=False)
+        np.testing.assert_array_equal(idx[rows], i_o)
+        assert np.array_equal(dist[rows], d_o)
+        h = n_q // 2
+        d_b, i_b, _ = ix.query(Qc[h:], k, row_offset=h, deterministic=False)
+        assert np.array_equal(i_b, idx[h:]) and np.array_equal(d_b, dist[h:])
+        ix.close()
