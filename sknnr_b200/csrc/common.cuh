@@ -335,8 +335,25 @@ __device__ __forceinline__ void det_sort(double &key, long long &sec, double &di
     }
 }
 
-__device__ __forceinline__ void finish_query(const FinishParams &p, long long q, double dist,
-                                             int id, int lane) {
+// W = 32: one query per warp (`lane` 0..31).  W = 16: one query per half warp - every shuffle,
+// vote and loop below stays inside the aligned 16-lane segment of the calling lane, `lane` is the
+// lane within the segment, and `write` = false turns a segment into a silent passenger (its
+// partner segment still needs the full warp in the shuffles).
+template <int W>
+__device__ __forceinline__ unsigned seg_ballot(bool pred) {
+    const unsigned b = __ballot_sync(SK_FULL, pred);
+    if constexpr (W == 32) {
+        return b;
+    } else {
+        unsigned lane32;
+        asm("mov.u32 %0, %%laneid;" : "=r"(lane32));
+        return (b >> (lane32 & 16u)) & 0xffffu;
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void finish_query_w(const FinishParams &p, long long q, double dist, int id,
+                                               int lane, bool write) {
     if (p.row_map) q = p.row_map[q];
     const long long row = p.row_offset + q;
     int kk = p.k + (p.exclude_self ? 1 : 0);
@@ -345,10 +362,10 @@ __device__ __forceinline__ void finish_query(const FinishParams &p, long long q,
         id = 0x7fffffff;
     }
     if (p.exclude_self) {
-        unsigned m = __ballot_sync(SK_FULL, lane < kk && (long long)id == row);
+        unsigned m = seg_ballot<W>(lane < kk && (long long)id == row);
         int pos = m ? (__ffs(m) - 1) : 0;
-        double nd = __shfl_down_sync(SK_FULL, dist, 1);
-        int ni = __shfl_down_sync(SK_FULL, id, 1);
+        double nd = __shfl_down_sync(SK_FULL, dist, 1, W);
+        int ni = __shfl_down_sync(SK_FULL, id, 1, W);
         if (lane >= pos) {
             dist = nd;
             id = ni;
@@ -360,7 +377,7 @@ __device__ __forceinline__ void finish_query(const FinishParams &p, long long q,
     }
     if (p.deterministic) {
         // row_scale = max(rowmax, 1); rounded = rint(dist / row_scale * 10^dec) / 10^dec
-        double rowmax = __shfl_sync(SK_FULL, dist, p.k - 1);  // ascending -> last is max
+        double rowmax = __shfl_sync(SK_FULL, dist, p.k - 1, W);  // ascending -> last is max
         double scale = fmax(rowmax, 1.0);
         double key = (lane < p.k) ? rint((dist / scale) * p.round_scale) / p.round_scale : SK_INF_D;
         long long diff = (long long)id - row;
@@ -371,11 +388,11 @@ __device__ __forceinline__ void finish_query(const FinishParams &p, long long q,
         // The lanes arrive sorted by (dist, id) and the key is monotone in dist, so the order can
         // only change inside a group of equal rounded keys: skip the network unless some
         // neighbouring pair is out of (key, sec) order (rare: ties to `decimals` digits).
-        const double pk = __shfl_up_sync(SK_FULL, key, 1);
-        const long long ps = __shfl_up_sync(SK_FULL, sec, 1);
+        const double pk = __shfl_up_sync(SK_FULL, key, 1, W);
+        const long long ps = __shfl_up_sync(SK_FULL, sec, 1, W);
         const bool out_of_order = lane > 0 && lane < p.k && (key < pk || (key == pk && sec < ps));
         // bitonic network on (key, sec) carrying dist; only the first k lanes hold entries, so the
-        // network spans the next power of two >= k
+        // network spans the next power of two >= k (sorting an ordered segment again is harmless)
         if (!__any_sync(SK_FULL, out_of_order)) {
         } else if (p.k <= 8)
             det_sort<8>(key, sec, dist, lane);
@@ -385,14 +402,14 @@ __device__ __forceinline__ void finish_query(const FinishParams &p, long long q,
             det_sort<32>(key, sec, dist, lane);
         id = (int)(sec & 0x7fffffffLL);
     }
-    if (lane < p.k) {
+    if (write && lane < p.k) {
         if (p.out_dist) p.out_dist[q * p.k + lane] = dist;
         if (p.out_idx) p.out_idx[q * p.k + lane] = (long long)id;
     }
     if (p.weights != 0 && p.out_pred != nullptr) {
         double w = 1.0;
         if (p.weights == 2) {
-            unsigned zm = __ballot_sync(SK_FULL, lane < p.k && dist == 0.0);
+            unsigned zm = seg_ballot<W>(lane < p.k && dist == 0.0);
             if (zm)
                 w = (dist == 0.0) ? 1.0 : 0.0;
             else
@@ -400,23 +417,28 @@ __device__ __forceinline__ void finish_query(const FinishParams &p, long long q,
         }
         if (lane >= p.k) w = 0.0;
         double denom = 0.0;
-        for (int c = 0; c < p.k; ++c) denom += __shfl_sync(SK_FULL, w, c);
-        for (int j0 = 0; j0 < p.n_out; j0 += 32) {
+        for (int c = 0; c < p.k; ++c) denom += __shfl_sync(SK_FULL, w, c, W);
+        for (int j0 = 0; j0 < p.n_out; j0 += W) {
             int j = j0 + lane;
             double num = 0.0;
             for (int c = 0; c < p.k; ++c) {
-                double wc = __shfl_sync(SK_FULL, w, c);
-                int ic = __shfl_sync(SK_FULL, id, c);
+                double wc = __shfl_sync(SK_FULL, w, c, W);
+                int ic = __shfl_sync(SK_FULL, id, c, W);
                 if (j < p.n_out && ic >= 0 && ic < p.n_ref) {
                     double yv = p.y[(long long)ic * p.n_out + j];
                     num = (p.weights == 1) ? (num + yv) : (num + yv * wc);
                 }
             }
-            if (j < p.n_out) {
+            if (write && j < p.n_out) {
                 p.out_pred[q * p.n_out + j] = (p.weights == 1) ? (num / (double)p.k) : (num / denom);
             }
         }
     }
+}
+
+__device__ __forceinline__ void finish_query(const FinishParams &p, long long q, double dist,
+                                             int id, int lane) {
+    finish_query_w<32>(p, q, dist, id, lane, true);
 }
 
 }  // namespace sk

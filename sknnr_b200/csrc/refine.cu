@@ -164,8 +164,74 @@ refine_kernel(RefineArgs a, FinishParams fp) {
     finish_query(fp, q, sqrt(d2), id, lane);
 }
 
+// Two queries per warp, one per 16-lane segment, for lists of <= 16 candidates and d <= 64 (the
+// common case: the tensor and SIMT engines' k <= 14 lists): the sort network and everything in
+// finish_query only ever needed 16 lanes, so this halves their instruction count per query.  A
+// segment takes one candidate of ITS query per pass (16 lanes on 128 consecutive bytes of the
+// reference row, 16-lane butterfly); lane i of the segment keeps candidate i.
+template <int DJ>
+__global__ void __launch_bounds__(REFINE_WARPS * 32)
+refine2_kernel(RefineArgs a, FinishParams fp) {
+    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int seg = lane >> 4, hl = lane & 15;
+    const long long n_rows = a.n_rows_dev ? min((long long)*a.n_rows_dev, a.n_q) : a.n_q;
+    const long long q0 = ((long long)blockIdx.x * REFINE_WARPS + warp) * 2;
+    if (q0 >= n_rows) return;                       // both segments idle: the whole warp leaves
+    const bool live = q0 + seg < n_rows;            // odd tail: the second segment rides along
+    const long long q = live ? q0 + seg : q0;
+    const double *zq = a.z64 + q * a.d;
+    double zr[DJ];
+#pragma unroll
+    for (int j = 0; j < DJ; ++j) zr[j] = (hl + 16 * j < a.d) ? zq[hl + 16 * j] : 0.0;
+    const int my_c = hl < a.kc ? a.cand_idx[q * a.kc + hl] : -1;
+    int id = 0x7fffffff;
+    double d2 = SK_INF_D;
+#pragma unroll 4
+    for (int i = 0; i < a.kc; ++i) {
+        const int c = __shfl_sync(SK_FULL, my_c, i, 16);
+        const bool have = c >= 0 && c < a.n_ref;
+        double acc = 0.0;
+        if (have) acc = dist2_lane_regs<DJ>(zr, a.ref64 + (long long)c * a.d, a.d, hl);
+        acc = dist2_reduce16(acc);
+        if (have && hl == i) {
+            id = c;
+            d2 = acc;
+        }
+    }
+    double qn = 0.0;
+    for (int k = hl; k < a.d; k += 16) {
+        const double df = zq[k] - a.mu[k];
+        qn += df * df;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) qn += __shfl_xor_sync(SK_FULL, qn, o);
+    warp_sort_pairs<double, 16>(d2, id, hl);   // (segment lane: both segments sort ascending)
+
+    const int kk = fp.k + (fp.exclude_self ? 1 : 0);
+    const double kth = __shfl_sync(SK_FULL, d2, kk - 1, 16);
+    float thr = a.cand_thr[q * a.n_thr];
+    for (int i = 1; i < a.n_thr; ++i) thr = fminf(thr, a.cand_thr[q * a.n_thr + i]);
+    bool ok = true;                                 // thr = +inf: the list holds every reference
+    if (thr != SK_INF_F) ok = kth < (double)thr + qn - a.eps_s * (qn + a.r2max);
+    if (live && !ok && hl == 0) {
+        const int pos = atomicAdd(a.fb_count, 1);
+        a.fb_list[pos] = a.row_map ? a.row_map[q] : (int)q;
+    }
+    finish_query_w<16>(fp, q, sqrt(d2), id, hl, live && ok);
+}
+
 cudaError_t launch_refine(const RefineArgs &a, const FinishParams &fp, cudaStream_t st) {
     if (a.n_q <= 0) return cudaSuccess;
+    if (a.kc <= 16 && a.d <= 64) {
+        const long long grid2 = (a.n_q + 2 * REFINE_WARPS - 1) / (2 * REFINE_WARPS);
+        switch ((a.d + 15) / 16) {
+            case 1: refine2_kernel<1><<<(unsigned)grid2, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+            case 2: refine2_kernel<2><<<(unsigned)grid2, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+            case 3: refine2_kernel<3><<<(unsigned)grid2, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+            default: refine2_kernel<4><<<(unsigned)grid2, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
+        }
+        return cudaGetLastError();
+    }
     const long long grid = (a.n_q + REFINE_WARPS - 1) / REFINE_WARPS;
     switch (a.d <= 64 ? (a.d + 15) / 16 : 0) {
         case 1: refine_kernel<1><<<(unsigned)grid, REFINE_WARPS * 32, 0, st>>>(a, fp); break;
