@@ -569,6 +569,15 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + sl * TC_N;
             if (elect_one()) {
+                if (DBG && (dbg & 16)) {   // timing experiment: the job's MMAs issued twice (same result)
+                    uint32_t a2 = a_lo0, b2 = b_lo_s;
+                    tc_mma_tf32(d_tmem, desc_hi | a2, desc_hi | b2, TC_IDESC, 0u);
+                    for (int ks = 1; ks < ksteps; ++ks) {
+                        a2 += a_kstep;
+                        b2 += b_kstep;
+                        tc_mma_tf32(d_tmem, desc_hi | a2, desc_hi | b2, TC_IDESC, 1u);
+                    }
+                }
                 uint32_t a_lo = a_lo0, b_lo = b_lo_s;
                 tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 0u);
 #pragma unroll 4
