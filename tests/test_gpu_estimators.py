@@ -192,3 +192,32 @@ def test_estimator_hygiene_pickle_lists_gridsearch_and_errors():
     # k = 1 on the training frame returns each row itself (ref:tests/test_estimators.py:181-201)
     idx = S.GNNRegressor(n_neighbors=1).fit(Xtr, ytr).kneighbors(Xtr, return_distance=False)
     np.testing.assert_array_equal(idx.ravel(), np.arange(len(Xtr)))
+
+
+def test_integration_stub_from_the_document_runs():
+    """The ctypes stub printed in INTEGRATION.md section 1 (what a maintainer of the reference would
+    add) is executed verbatim against the built library and must agree with the package's own
+    binding."""
+    import re
+
+    from sknnr_b200._build import lib_path
+    from sknnr_b200._engine import KNNIndex
+    from tests.conftest import ROOT
+    import os
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(import ctypes as C, numpy as np.*?)```", text, re.S).group(1)
+    code = code.replace('C.CDLL("libsknnr_b200.so")', f'C.CDLL({lib_path()!r})')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    Xtr, Xte, ytr, yte, _ = _split()
+    mean, scale = Xtr.mean(0), Xtr.std(0, ddof=1)
+    fit_z = (Xtr - mean) / scale
+    stub = ns["Index"](fit_z, ytr, mean, scale)
+    d, i, p = stub.kneighbors(Xte, 5, transformed=False, deterministic=True, decimals=10, weights=1)
+    d0, i0, p0 = KNNIndex(fit_z, mean, scale, None, ytr).query(Xte, 5, weights="uniform", with_pred=True)
+    np.testing.assert_array_equal(i, i0)
+    np.testing.assert_array_equal(d, d0)
+    np.testing.assert_array_equal(p, p0)
+    d, i, _ = stub.kneighbors(None, 5, transformed=True, deterministic=True, decimals=10)
+    assert d.shape == (len(Xtr), 5) and not np.any(i == np.arange(len(Xtr))[:, None])
