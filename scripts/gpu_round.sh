@@ -1,2 +1,3 @@
 set -x
-timeout 600 python -m pytest tests -m gpu -x -q -k "integration_stub" 2>&1 | tail -15
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_full.log 2>&1; tail -1 gpurun_out/bench_full.log | cut -c1-200

@@ -36,17 +36,31 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
     }
     const int rows = (int)min((long long)PROJ_THREADS, n_q - q0);
 
-    // coalesced load of the tile's rows, centring and scaling on the way in
-    for (int e = threadIdx.x; e < PROJ_THREADS * d_in; e += PROJ_THREADS) {
-        const int r = e / d_in, c = e - r * d_in;
-        double v = 0.0;
-        if (r < rows) {
-            v = (double)X[(q0 + r) * ldx + c];
-            if (center) v -= center[c];
-            if (scale) v /= scale[c];
+    // coalesced load of the tile's rows, centring and scaling on the way in; (row, column) advance
+    // incrementally (no integer division per element).  Without a projector the scaled value already
+    // is z: it goes to z64 from here, where consecutive threads write consecutive addresses.
+    {
+        const int dr = PROJ_THREADS / d_in, dc = PROJ_THREADS - dr * d_in;
+        int r = threadIdx.x / d_in, c = threadIdx.x - r * d_in;
+        const bool z_here = !proj && z64 && d_out == d_in;
+        for (int e = threadIdx.x; e < PROJ_THREADS * d_in; e += PROJ_THREADS) {
+            double v = 0.0;
+            if (r < rows) {
+                v = (double)X[(q0 + r) * ldx + c];
+                if (center) v -= center[c];
+                if (scale) v /= scale[c];
+                if (z_here) z64[(q0 + r) * d_out + c] = v;
+            }
+            xs[r * xs_ld + c] = v;
+            r += dr;
+            c += dc;
+            if (c >= d_in) {
+                c -= d_in;
+                ++r;
+            }
         }
-        xs[r * xs_ld + c] = v;
     }
+    const bool z_later = z64 && (proj || d_out != d_in);
     if (proj)
         for (int e = threadIdx.x; e < d_in * d_out; e += PROJ_THREADS) ps[e] = proj[e];
     __syncthreads();
@@ -87,7 +101,7 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
             const int k = k0 + kk;
             float sv = 0.0f;
             if (k < d_out && r < rows) {
-                if (z64) z64[(q0 + r) * d_out + k] = z[kk];
+                if (z_later) z64[(q0 + r) * d_out + k] = z[kk];
                 sv = (float)(-2.0 * (z[kk] - mu[k]));
             }
             svs[kk] = sv;
