@@ -1,3 +1,2 @@
 set -x
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_full.log 2>&1; tail -1 gpurun_out/bench_full.log | cut -c1-200
+for s in 2 3 4; do timeout 900 python scripts/fuzz_parity.py 150 $s 2>&1 | tail -2; done
