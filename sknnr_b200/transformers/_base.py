@@ -27,6 +27,8 @@ class DeviceProjectionMixin:
         return h
 
     def _device_transform(self, X_arr):
+        if self._affine()[3] == 0:   # n_components=0: nothing to compute (the reference returns [n, 0] too)
+            return np.empty((np.asarray(X_arr).shape[0], 0), dtype=np.float64)
         return self._projector_handle().transform(X_arr)
 
     def _drop_device_state(self):
