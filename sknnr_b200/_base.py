@@ -16,6 +16,7 @@ import numbers
 from abc import ABC, abstractmethod
 
 import numpy as np
+import scipy.sparse as sp
 from sklearn.base import BaseEstimator
 from sklearn.metrics import r2_score
 from sklearn.neighbors import KNeighborsRegressor
@@ -128,6 +129,9 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
 
     # -- fit ---------------------------------------------------------------------------
     def fit(self, X, y):
+        if sp.issparse(X):   # dense searches only (input tag sparse = False), scikit-learn's wording
+            raise TypeError("Sparse data was passed for X, but dense data is required. "
+                            "Use '.toarray()' to convert to a dense numpy array.")
         self._set_dataframe_index_in(X)
         self._drop_device_index()
         super().fit(X, y)

@@ -7,6 +7,8 @@ import numpy as np
 from sklearn.preprocessing import StandardScaler
 from sklearn.utils.validation import FLOAT_DTYPES, check_is_fitted, validate_data
 
+from .. import _cache
+
 
 class DeviceProjectionMixin:
     """``transform`` of every float transformer is one affine map
@@ -17,13 +19,12 @@ class DeviceProjectionMixin:
         raise NotImplementedError
 
     def _projector_handle(self):
-        h = self.__dict__.get("_device_projector")
+        h = _cache.get(self, "projector")
         if h is None:
             from .._engine import KNNIndex
 
             center, scale, proj, d_out = self._affine()
-            h = KNNIndex(np.zeros((1, d_out)), center, scale, proj)
-            self.__dict__["_device_projector"] = h
+            h = _cache.put(self, "projector", KNNIndex(np.zeros((1, d_out)), center, scale, proj))
         return h
 
     def _device_transform(self, X_arr):
@@ -32,12 +33,7 @@ class DeviceProjectionMixin:
         return self._projector_handle().transform(X_arr)
 
     def _drop_device_state(self):
-        self.__dict__.pop("_device_projector", None)
-
-    def __getstate__(self):
-        state = super().__getstate__()
-        state.pop("_device_projector", None)
-        return state
+        _cache.drop(self)
 
 
 class StandardScalerWithDOF(DeviceProjectionMixin, StandardScaler):
@@ -70,7 +66,11 @@ class StandardScalerWithDOF(DeviceProjectionMixin, StandardScaler):
         return self.mean_, self.scale_, None, self.n_features_in_
 
     def transform(self, X, copy=None):
-        return self._device_transform(self._validate_query(X))
+        X_arr = self._validate_query(X)
+        Z = self._device_transform(X_arr)
+        # StandardScaler preserves float32 / float64 inputs (its tag says so); the device computes in
+        # float64 and the result is rounded once
+        return Z.astype(np.float32) if X_arr.dtype == np.float32 else Z
 
 
 class ComponentReducerMixin:

@@ -15,6 +15,8 @@ import numpy as np
 from sklearn.base import BaseEstimator, TransformerMixin
 from sklearn.utils.validation import check_array, check_is_fitted, validate_data
 
+from .. import _cache
+
 
 def _is_nan_like(v) -> bool:
     return v is None or (isinstance(v, float) and np.isnan(v)) or type(v).__name__ == "NAType"
@@ -88,6 +90,7 @@ class TreeNodeTransformer(TransformerMixin, BaseEstimator, ABC):
         return out
 
     def _fit(self, X, y, make_regressor, make_classifier):
+        _cache.drop(self)        # device copies of a previous fit's trees
         X_arr = validate_data(self, X=X, reset=True)
         if y is None:
             raise ValueError(f"{type(self).__name__} requires y to be passed, but the target y is None.")
@@ -123,26 +126,20 @@ class TreeNodeTransformer(TransformerMixin, BaseEstimator, ABC):
 
     # -- transform ----------------------------------------------------------------------
     def _forest_index(self, node_code_tables=None):
-        """Device copy of the trees (a cache: never pickled, rebuilt on demand).  A copy made with
-        ``node_code_tables`` also serves the fused Hamming query of the estimator that owns them."""
+        """Device copy of the trees (a cache outside ``__dict__``: never pickled, rebuilt on demand).
+        A copy made with ``node_code_tables`` also serves the fused Hamming query of the estimator
+        that owns them."""
         from .._engine import ForestIndex
 
-        key = "_forest_index_coded" if node_code_tables is not None else "_forest_index_plain"
-        fx = self.__dict__.get(key)
-        if fx is not None and key == "_forest_index_coded" and self.__dict__.get("_forest_tables_id") != id(node_code_tables):
+        key = "forest_coded" if node_code_tables is not None else "forest_plain"
+        fx = _cache.get(self, key)
+        if fx is not None and key == "forest_coded" and _cache.get(self, "tables_id") != id(node_code_tables):
             fx = None   # the owning estimator rebuilt its code tables (refit)
         if fx is None:
-            fx = ForestIndex(self._trees(), self.n_features_in_, node_code_tables)
-            self.__dict__[key] = fx
-            if key == "_forest_index_coded":
-                self.__dict__["_forest_tables_id"] = id(node_code_tables)
+            fx = _cache.put(self, key, ForestIndex(self._trees(), self.n_features_in_, node_code_tables))
+            if key == "forest_coded":
+                _cache.put(self, "tables_id", id(node_code_tables))
         return fx
-
-    def __getstate__(self):
-        state = super().__getstate__()
-        for key in ("_forest_index_coded", "_forest_index_plain", "_forest_tables_id"):
-            state.pop(key, None)
-        return state
 
     def _validate_query(self, X):
         """Input validation of ``transform`` (feature names, shape, NaN) plus scikit-learn's own
