@@ -1332,14 +1332,17 @@ int sknnr_forest_create(const int32_t *tree_offsets, const int32_t *children_lef
             ForestNode nd{};
             const int l = children_left[i], r = children_right[i];
             if (l < 0) {   // leaf ($SP/sklearn/tree/_tree.pyx: TREE_LEAF = -1)
-                nd.left = nd.right = -1;
-                nd.code = node_code ? (int)node_code[i] : (i - lo);
+                nd.left = -1;
+                nd.right = node_code ? (int)node_code[i] : (i - lo);   // leaf: the node's code
             } else {
                 if (l >= hi - lo || r < 0 || r >= hi - lo) return fail(SKNNR_EINVAL, "child index out of range");
                 if (feature[i] < 0 || feature[i] >= n_features) return fail(SKNNR_EINVAL, "feature index out of range");
                 nd.left = lo + l;
                 nd.right = lo + r;
-                nd.thr = threshold[i];
+                // largest float32 <= threshold (exact for float32 feature values, see ForestNode)
+                float tf = (float)threshold[i];
+                if ((double)tf > threshold[i]) tf = std::nextafterf(tf, -INFINITY);
+                nd.thr = tf;
                 nd.feat = feature[i] | ((missing_go_to_left && missing_go_to_left[i]) ? (int)0x80000000u : 0);
             }
             nodes[(size_t)i] = nd;

@@ -7,12 +7,14 @@
 //
 // Semantics replicated bit for bit from scikit-learn's Tree._apply_dense:
 //   * X is cast to float32 first (DTYPE), so float64 inputs are rounded to nearest even;
-//   * at an internal node go left iff (double)x[feature] <= threshold (threshold is float64);
+//   * at an internal node go left iff (double)x[feature] <= threshold (threshold is float64) - for
+//     a float32 x that is x <= (largest float32 <= threshold), which is what the 16-byte nodes hold;
 //     NaN follows the node's missing_go_to_left flag;
 //   * a node is a leaf when children_left == -1.
 //
-// One thread walks one (query, tree) pair; a warp = 32 consecutive queries in the same tree, so
-// the top levels are a broadcast and deeper levels gather 32-byte nodes from L1/L2.  The CTA's
+// One thread walks its query through FOREST_ILP trees at a time (independent pointer chases in
+// flight: the walk is load-latency bound); a warp = 32 consecutive queries in the same trees, so the
+// top levels are a broadcast and deeper levels gather 16-byte nodes from L1/L2.  The CTA's
 // query tile lives in shared memory as float32; results are staged per 32-tree group and written
 // as whole rows.
 #include "common.cuh"
@@ -22,6 +24,10 @@ namespace sk {
 
 constexpr int FOREST_THREADS = 256;  // queries per CTA
 constexpr int FOREST_TG = 32;        // trees per staging group
+#ifndef SK_FOREST_ILP
+#define SK_FOREST_ILP 2
+#endif
+constexpr int FOREST_ILP = SK_FOREST_ILP;   // trees walked concurrently by one thread
 
 template <typename TX>
 __global__ void __launch_bounds__(FOREST_THREADS)
@@ -42,20 +48,36 @@ forest_apply_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int 
     const float *xr = xs + threadIdx.x * xs_ld;
     for (int t0 = 0; t0 < n_trees; t0 += FOREST_TG) {
         const int tn = min(FOREST_TG, n_trees - t0);
-        for (int tt = 0; tt < tn; ++tt) {
-            int node = roots[t0 + tt];
-            int result;
-            while (true) {
-                const ForestNode nd = nodes[node];
-                if (nd.left < 0) {
-                    result = out_ids ? node - roots[t0 + tt] : nd.code;
-                    break;
-                }
-                const float x = xr[nd.feat & 0x7fffffff];
-                const bool go_left = isnan(x) ? (nd.feat < 0) : ((double)x <= nd.thr);
-                node = go_left ? nd.left : nd.right;
+        for (int tt = 0; tt < tn; tt += FOREST_ILP) {
+            int node[FOREST_ILP], root[FOREST_ILP];
+            bool done[FOREST_ILP];
+#pragma unroll
+            for (int u = 0; u < FOREST_ILP; ++u) {
+                done[u] = tt + u >= tn;
+                root[u] = done[u] ? 0 : roots[t0 + tt + u];
+                node[u] = root[u];
             }
-            stage[threadIdx.x * (FOREST_TG + 1) + tt] = result;
+            while (true) {
+                bool all = true;
+                ForestNode nd[FOREST_ILP];
+#pragma unroll
+                for (int u = 0; u < FOREST_ILP; ++u)
+                    if (!done[u]) nd[u] = nodes[node[u]];
+#pragma unroll
+                for (int u = 0; u < FOREST_ILP; ++u) {
+                    if (done[u]) continue;
+                    if (nd[u].left < 0) {
+                        stage[threadIdx.x * (FOREST_TG + 1) + tt + u] = out_ids ? node[u] - root[u] : nd[u].right;
+                        done[u] = true;
+                        continue;
+                    }
+                    const float x = xr[nd[u].feat & 0x7fffffff];
+                    const bool go_left = isnan(x) ? (nd[u].feat < 0) : (x <= nd[u].thr);
+                    node[u] = go_left ? nd[u].left : nd[u].right;
+                    all = false;
+                }
+                if (all) break;
+            }
         }
         __syncthreads();
         // row-contiguous write of the group: [rows][tn]

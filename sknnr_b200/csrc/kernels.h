@@ -128,13 +128,14 @@ cudaError_t launch_hamming_finish(const int *cand_idx, const int *cand_cnt, int 
                                   cudaStream_t st);
 
 // ---- forest.cu (RFNodeTransformer.transform on the device) -------------------------------
-// One node of the flattened forests, 32 bytes.  left < 0: leaf (`code` = the 16-bit node code the
-// Hamming index uses for it).  feat: feature index, bit 31 set = missing values go left.
+// One node of the flattened forests, 16 bytes (one LDG.128).  left < 0: leaf, `right` = the 16-bit
+// node code the Hamming index uses for it.  feat: feature index, bit 31 set = missing values go left.
+// thr = the largest float32 <= scikit-learn's float64 threshold: the walked feature value x is a
+// float32, and for a float32 x  "(double)x <= threshold"  holds exactly when  x <= thr.
 struct __align__(16) ForestNode {
-    double thr;
+    float thr;
     int left, right;
-    int feat, code;
-    int pad[2];
+    int feat;
 };
 size_t forest_smem_bytes(int d);
 // out_ids != null: node IDs relative to each tree's root (transform parity, int32 [n_q, ld_out]);
