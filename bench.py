@@ -365,7 +365,9 @@ def run_ours(a, rank, world, local_rank):
     engine = int(stats.get("engine", 0))
     dpad = (d + 7) // 8 * 8
     flops = 2.0 * d * n_q * a.n_ref                      # algorithmic: 2 * d' * n_q * n_ref
-    n_chunks = max(1, -(-n_q // (1 << 20)))
+    # search launches of the device-resident step: device-pointer calls use chunks of 2 x chunk_rows
+    chunk_dev = 2 * (a.chunk_rows if a.chunk_rows > 0 else (1 << 20))
+    n_chunks = max(1, -(-n_q // chunk_dev))
     achieved = flops / (search_ms * 1e-3) / 1e12 if search_ms > 0 else None
     fp32_peak = L.measure_fp32_peak(local_rank)
     peaks = {}

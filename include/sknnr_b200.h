@@ -84,7 +84,7 @@ int sknnr_device_count(int *count);
 
 /* Global knobs (environment-style; never estimator constructor arguments):
  *   "engine"      SKNNR_ENGINE_*           (default AUTO)
- *   "chunk_rows"  rows per internal chunk  (default 1<<20)
+ *   "chunk_rows"  rows per internal chunk  (default 1<<20; device-pointer calls use twice that)
  *   "timing"      0/1 record search_ms     (default 0)
  *   "kc"          0/8/16/32 minimum length of the FP32 (SIMT) search's candidate list (default 16);
  *                 0 picks the smallest list that holds k+1 (longer lists = fewer certificate

@@ -665,7 +665,10 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     if (n_q == 0) return SKNNR_OK;
 
     cudaStream_t user_stream = (cudaStream_t)stream;
-    const int64_t chunk = std::min<int64_t>(g_opt.chunk_rows, (n_q + 255) / 256 * 256);
+    // device-resident queries have no copies to overlap: twice the chunk (fewer launches and cascade
+    // tails; measured +1.8 %), while host buffers prefer the shorter pipeline ramp of the smaller one
+    const int64_t chunk = std::min<int64_t>(dev_ptrs ? 2 * g_opt.chunk_rows : g_opt.chunk_rows,
+                                            (n_q + 255) / 256 * 256);
     // Host buffers: the first chunk's H2D copy and the last chunk's D2H copy cannot overlap any
     // kernel, so the stream of chunks ramps up (1/4, 1/2, 1, ...) and down (..., 1/2, 1/4).
     const bool ramp = !dev_ptrs && n_q >= 4 * chunk && chunk % 1024 == 0;
