@@ -12,34 +12,37 @@
 // certify are re-searched by the FP32 SIMT engine and, failing that, by the exhaustive float64
 // kernel.
 //
-// One CTA = MT x 128 queries = MT (2, 3 or 4) M=128 MMA tiles that share every reference tile
-// (N=128).  A "job" is one (reference tile, M tile) pair = K/8 tcgen05.mma into one of four
-// 128-column TMEM accumulator slots; jobs run in (tile, M tile) order and job j uses slot j % 4,
-// so the MMAs of up to 4 - MT later jobs overlap the epilogue of the current ones (MT = 2: two
-// full stages; MT = 4: each M tile's next job starts as soon as its own slot has been read).
-//   warp 4MT+1, lane 0  TMA producer: bulk copies (cp.async.bulk + mbarrier) of the query image
-//                    once and of reference tiles through an NSTAGE ring;
-//   warp 4MT, lane 0    MMA issuer: the tcgen05.mma of every job, tcgen05.commit onto the
-//                    "smem slot free" and "accumulator slot ready" mbarriers;
-//   warps 0..4MT-1   epilogue: thread <-> query (TMEM lane), four warps per M tile.  The 128 accumulator columns of a
-//                    tile are read 32 at a time with tcgen05.ld into two alternating register
-//                    buffers (the load of chunk c+1 is in flight while chunk c is reduced), a
-//                    min3 tree gives the chunk minimum, one vote tells whether any lane of the
-//                    warp beat its threshold.  A lane that did publishes its 32 scores to a
-//                    per-warp scratch line, the warp re-tests them one score per lane and the
-//                    survivors are appended to the lane's candidate buffer (32 slots per query
-//                    in shared memory).  When a buffer overflows the whole warp compacts: every
-//                    thread sorts the scores of its own buffer in registers (bitonic network),
-//                    keeps the KC smallest and lowers its threshold to the KC-th.
-//   More M tiles = more epilogue warps per SM (the epilogue is latency-bound: dependent vote /
-//   shuffle / shared-memory chains), fewer = deeper MMA look-ahead and room for a larger K.
+// One CTA = 256 queries = two M=128 MMA tiles that share every 128-plot reference tile (N=128).  A
+// "job" is one (reference tile, M tile) pair = K/8 tcgen05.mma into one of four 128-column TMEM
+// accumulator slots; jobs run in (tile, M tile) order and job j uses slot j % 4, i.e. every M tile
+// owns two slots and its MMAs run at most one job ahead of its scanners.  19 warps (ns = 2):
+//   TMA producer (1 thread)   bulk copies (cp.async.bulk + mbarrier) of the query image once and of
+//                    the reference tiles through an NSTAGE ring;
+//   MMA issuers (one warp per M tile, warp-uniform loop, one elected lane)  wait "tile staged" and
+//                    "slot drained", issue the job's tcgen05.mma, tcgen05.commit onto "slot ready"
+//                    and (both issuers) "stage free";
+//   16 scanner warps = (column stream p, M tile h, TMEM lane quarter): thread <-> (query, stream).
+//                    Per job a warp waits "slot ready", reads its stream's 64 accumulator columns
+//                    with one tcgen05.ld.x64, hands the slot back BEFORE reducing anything, then per
+//                    32-column chunk: min3 tree -> one vote "did any lane beat its threshold".  If
+//                    so the hit lanes descend the tree in-lane (group of 9 -> triple -> values) and
+//                    append (score, index) to their own candidate column in shared memory with
+//                    branch-free stores; the count of a column lives in the offset of its next free
+//                    slot (power-of-two slot stride).  When a column is nearly full the whole warp
+//                    compacts: every thread sorts its own column in registers (bitonic network),
+//                    keeps the KC smallest and lowers its threshold to the KC-th.  A lane that runs
+//                    out of slots inside one chunk is redone through a cooperative path (publish
+//                    the 32 scores to the warp's scratch line, one score per lane).
+//   All role / slot / barrier values derive from a shuffled (provably warp-uniform) warp index and
+//   live in uniform registers: the scanners have 96 vector registers, 64 of them hold a job.
+//   (ns = 1: one stream of 16 candidates, 8 scanner warps of four chunks, for k (+1) <= 14.)
 //
 // Threshold seeding.  A streaming top-KC pays KC*ln(n_ref/KC) threshold hits per query, almost
 // all of them while the threshold is still loose.  The kernel therefore first runs every
-// `seed_stride`-th reference tile in a min-only mode that keeps 32 group minima per query in
-// registers; the KC-th smallest group minimum is an upper bound of the query's KC-th best
-// score (KC distinct references reach it), so the main pass starts with a threshold close to
-// its final value and sees ~KC*(1+ln(1.4*seed_stride)) hits instead.
+// `seed_stride`-th reference tile in a min-only mode that keeps 32 group minima per (query, stream)
+// in the still unused candidate column; the KC-th smallest group minimum is an upper bound of the
+// stream's KC-th best score (KC distinct references reach it), so the main pass starts with a
+// threshold close to its final value: ~20 hits per stream instead of ~65.
 //
 // The |r|^2 term is folded into the contraction: each operand gets one extra K block holding
 // (1,1,1,0,..) on the query side and a 3-way TF32 split of |r|^2 on the reference side, so the
@@ -227,7 +230,7 @@ struct ThrCnt {
 };
 
 // Warp-wide compaction, thread-parallel: every thread reduces its OWN candidate buffer (column
-// col_s/col_i, slot stride TC_LD) to the KC smallest scores and lowers its threshold to the
+// cs0, slot stride LD) to the KC smallest scores and lowers its threshold to the
 // KC-th smallest.  Entries equal to the new threshold are kept only up to KC entries in total;
 // the dropped ones are >= the threshold, which is all the certificate needs.  Called by all 32
 // lanes (data-independent network, no divergence).
