@@ -3,7 +3,8 @@
 //                    sorts them by (distance, index), proves with a rigorous error bound that
 //                    no reference outside the survivor list can belong to the k nearest (the
 //                    "certificate"), and finishes the row (self exclusion, sknnr's
-//                    deterministic ordering, outputs, weighted average);
+//                    deterministic ordering, outputs, weighted average); refine2_kernel is the
+//                    same for lists of <= 16 candidates with two queries per warp;
 //   exact_kernel   - exhaustive float64 search for the rows whose certificate failed (and the
 //                    engine for shapes the fast kernels do not cover / unequal Hamming weights);
 //   weighted_average_kernel - seam S3 with caller-supplied weights.
