@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--tc-streams", type=int, default=0)
     ap.add_argument("--tc-debug", type=int, default=0)
     ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--host-slots", type=int, default=0)
     return ap.parse_args()
 
 
@@ -223,6 +224,8 @@ def run_ours(a, rank, world, local_rank):
         L.set_option("tc_debug", a.tc_debug)
     if a.chunk_rows:
         L.set_option("chunk_rows", a.chunk_rows)
+    if a.host_slots:
+        L.set_option("host_slots", a.host_slots)
     if a.tc_seed_stride >= 0:
         L.set_option("tc_seed_stride", a.tc_seed_stride)
 

@@ -42,6 +42,7 @@ struct Options {
     int64_t timing = 0;
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
     int64_t tc_streams = 0;     // tensor engine: candidate streams per query (0 = automatic, else 1 or 2)
+    int64_t host_slots = 8;     // chunks of a host-buffer call in flight (1..8)
     int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = off)
 } g_opt;
 
@@ -311,6 +312,9 @@ int sknnr_set_option(const char *name, int64_t value) {
     } else if (!strcmp(name, "tc_streams")) {
         if (value < 0 || value > 2) return fail(SKNNR_EINVAL, "tc_streams must be 0, 1 or 2");
         g_opt.tc_streams = value;
+    } else if (!strcmp(name, "host_slots")) {
+        if (value < 1 || value > IndexBase::kSlots) return fail(SKNNR_EINVAL, "host_slots must be 1..8");
+        g_opt.host_slots = value;
     } else if (!strcmp(name, "tc_seed_stride")) {
         if (value < 0 || value > 64) return fail(SKNNR_EINVAL, "tc_seed_stride must be 0..64");
         g_opt.tc_seed_stride = value;
@@ -687,7 +691,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
         }
         // two slots alternate: the tail of chunk c (on its slot's tail stream) overlaps the first
         // stage of chunk c + 1 (other slot's buffers)
-        Slot &s = ix->slots[dev_ptrs ? (ci & 1) : (ci % IndexBase::kSlots)];
+        Slot &s = ix->slots[dev_ptrs ? (ci & 1) : (ci % (int)g_opt.host_slots)];
         cudaStream_t saved = s.stream;
         if (dev_ptrs) {
             s.stream = user_stream;
