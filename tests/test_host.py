@@ -193,3 +193,31 @@ def test_gbnode_transformer_fit_side_matches_reference():
     tu = GBNodeTransformer(tree_weighting_method="uniform", n_estimators=4).fit(Xtr, ytr[:, :2])
     assert all(np.array_equal(w, np.full(4, 0.25)) for w in tu.tree_weights_)
 
+
+
+def test_device_cache_is_outside_the_estimator_and_dies_with_it():
+    """Device handles are cached in a weakly keyed side table (sknnr_b200/_cache.py): nothing is
+    added to the estimator's __dict__, clones and pickles never see the cache, entries vanish with
+    their owner and can be dropped on refit."""
+    import gc
+    import pickle
+
+    from sklearn.base import clone
+
+    from sknnr_b200 import _cache
+    from sknnr_b200.transformers import StandardScalerWithDOF
+
+    t = StandardScalerWithDOF().fit(np.arange(12.0).reshape(4, 3))
+    before = dict(t.__dict__)
+    _cache.put(t, "projector", object())
+    assert t.__dict__.keys() == before.keys()
+    assert _cache.get(t, "projector") is not None
+    assert _cache.get(clone(t), "projector") is None
+    assert _cache.get(pickle.loads(pickle.dumps(t)), "projector") is None
+    _cache.drop(t, "projector")
+    assert _cache.get(t, "projector") is None
+    _cache.put(t, "projector", object())
+    n = len(_cache._CACHE)
+    del t
+    gc.collect()
+    assert len(_cache._CACHE) == n - 1
