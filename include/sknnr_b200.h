@@ -35,7 +35,8 @@ extern "C" {
 #define SKNNR_ECUDA (-2)    /* CUDA runtime / launch failure                           */
 #define SKNNR_ENODEV (-3)   /* no CUDA device                                          */
 #define SKNNR_ENOMEM (-4)   /* device or pinned-host allocation failed                 */
-#define SKNNR_EUNSUP (-5)   /* shape outside what the kernels cover (k > 32, ...)      */
+#define SKNNR_EUNSUP (-5)   /* shape outside what the kernels cover                    */
+#define SKNNR_ENONFINITE (-6) /* SKNNR_CHECK_FINITE: a query value is NaN or +-inf      */
 
 /* dtype of a query matrix */
 #define SKNNR_F64 0
@@ -50,6 +51,11 @@ extern "C" {
                                    RawKNNRegressor); otherwise S2 is fused in front         */
 #define SKNNR_DEVICE_PTRS 8u    /* X and all outputs are device pointers on the handle's
                                    device; work is enqueued on `stream` and NOT synchronised */
+
+#define SKNNR_CHECK_FINITE 16u  /* host-buffer calls: fail with SKNNR_ENONFINITE when a query value
+                                   is NaN / +-inf (the projection kernel reads every value anyway;
+                                   replaces the host pass of sklearn's validate_data,
+                                   $SP/sklearn/neighbors/_base.py:831-838); outputs are undefined then */
 
 /* prediction weights (seam S3, $SP/sklearn/neighbors/_base.py:74-117) */
 #define SKNNR_W_NONE 0      /* no prediction requested                                    */
@@ -95,6 +101,9 @@ int sknnr_device_count(int *count);
  *                 streams of 8 while k (+1) <= 8, else one of 16)
  *   "tc_seed_stride" 0..64: the tensor engine pre-scans one reference tile in n to seed its
  *                 thresholds (default 4; 0 = off)
+ *   "host_threads" workers that stage pageable caller buffers through page-locked slot buffers
+ *                 (default 0 = min(8, cores / 2); read when the first pageable call starts them)
+ *   "stage_rows"  rows per chunk of a call with pageable buffers (default 1<<19)
  *   "tc_debug"    timing experiments only (bit 0 skips the hit path, bit 2 skips the tile
  *                 loads: results are wrong)                                             */
 int sknnr_set_option(const char *name, int64_t value);
@@ -247,6 +256,21 @@ int sknnr_hamming_raster_kneighbors_forest(sknnr_hamming_index *index, sknnr_for
 /* Pinned host memory for callers that stream large rasters (cudaHostAlloc / cudaFreeHost). */
 int sknnr_host_alloc(void **ptr, int64_t bytes);
 int sknnr_host_free(void *ptr);
+
+/* Device buffers shared between the one-process-per-GPU ranks of a box (the
+ * gather of (dist, idx, pred) to one rank).  The root rank allocates the full result arrays with
+ * sknnr_device_alloc and exports them (64-byte CUDA IPC handle); every other rank opens them and
+ * passes its slice as out_dist / out_idx / out_pred of a SKNNR_DEVICE_PTRS query, so the finishing
+ * kernels store their rows straight into the root's memory over NVLink - the gather is fused into
+ * the compute, no collective follows it.  sknnr_device_copy: kind 0 = device to device (async on
+ * `stream`), 1 = host to device, 2 = device to host (both synchronous).                    */
+int sknnr_device_alloc(int32_t device, void **ptr, int64_t bytes);
+int sknnr_device_free(int32_t device, void *ptr);
+int sknnr_ipc_export(int32_t device, void *ptr, void *handle64);
+int sknnr_ipc_open(int32_t device, const void *handle64, void **ptr);
+int sknnr_ipc_close(int32_t device, void *ptr);
+int sknnr_device_copy(int32_t device, void *dst, const void *src, int64_t bytes, int32_t kind,
+                      void *stream);
 
 /* FP32 FMA-pipe peak probe: runs a register-resident FFMA2 loop on every SM and returns
  * the achieved TFLOP/s (the denominator of the SIMT roofline, measured not assumed).      */

@@ -155,7 +155,7 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
         return int(n_neighbors)
 
     def _search(self, X, n_neighbors, deterministic, *, raw=False, weights=None, with_pred=False,
-                return_distance=True, forest=None):
+                return_distance=True, forest=None, on_nonfinite=None):
         """One device call.  ``raw=True``: X holds untransformed features and the projection is
         fused in front (S2+S1[+S3]); ``forest`` (a fitted tree-node transformer): X holds validated
         raw features and the forest walk is fused in front of the Hamming search; otherwise X is
@@ -171,17 +171,32 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
         if forest is not None:
             k = self._check_k(n_neighbors, False, X.shape[0])
             return ix.query_forest(forest._forest_index(self.__dict__.get("_node_tables")), X, k, **kw)
+        hamming = isinstance(ix, HammingIndex)
         if not raw:
-            X = validate_data(self, X, ensure_all_finite=True, accept_sparse=False, reset=False, order="C")
-        else:
-            # the reference rejects non-finite values when the regressor validates the
-            # transformed array ($SP/sklearn/neighbors/_base.py:831-838); an affine map keeps
-            # NaN/inf, so checking the raw array raises the same ValueError
-            assert_all_finite(X)
+            # (Euclidean searches: the finite check runs on the device, see below)
+            X = validate_data(self, X, ensure_all_finite=hamming, accept_sparse=False, reset=False, order="C")
         k = self._check_k(n_neighbors, False, X.shape[0])
-        if isinstance(ix, HammingIndex):
-            return ix.query(_encode_nodes(np.asarray(X).astype(np.int64), self._node_tables), k, **kw)
-        return ix.query(X, k, transformed=not raw, **kw)
+        if hamming:
+            Xa = np.asarray(X)
+            codes = _encode_nodes(Xa.astype(np.int64), self._node_tables)
+            if Xa.dtype.kind == "f":
+                # scipy's hamming compares values, not truncated integers: a non-integer query
+                # value equals no node ID ($SP/scipy/spatial/distance.py:1718-1723)
+                codes[Xa != np.floor(Xa)] = L.MAX_CODE
+            return ix.query(codes, k, **kw)
+        # The reference rejects non-finite values when the regressor validates the (transformed)
+        # array ($SP/sklearn/neighbors/_base.py:831-838).  The projection kernel reads every query
+        # value anyway and an affine map keeps NaN / inf, so the device does the check and the host
+        # pass over the array only happens to word the error.
+        try:
+            return ix.query(X, k, transformed=not raw, check_finite=True, **kw)
+        except L.NonFiniteInput:
+            if on_nonfinite is not None:
+                on_nonfinite()
+            if not raw:
+                validate_data(self, X, ensure_all_finite=True, accept_sparse=False, reset=False, order="C")
+            assert_all_finite(X)
+            raise
 
     def kneighbors(self, X=None, n_neighbors=None, return_distance=True,
                    return_dataframe_index=False, use_deterministic_ordering=True):
@@ -198,13 +213,13 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
         return (dist, idx) if return_distance else idx
 
     # -- predict -----------------------------------------------------------------------
-    def _predict_impl(self, X, raw, forest=None):
+    def _predict_impl(self, X, raw, forest=None, on_nonfinite=None):
         w = self.weights
         if w in (None, "uniform", "distance"):
             _, _, pred = self._search(X, None, True, raw=raw, weights=w, with_pred=True,
-                                      return_distance=False, forest=forest)
+                                      return_distance=False, forest=forest, on_nonfinite=on_nonfinite)
         else:  # callable: evaluated by Python on the distances, averaged on the device
-            dist, idx, _ = self._search(X, None, True, raw=raw, forest=forest)
+            dist, idx, _ = self._search(X, None, True, raw=raw, forest=forest, on_nonfinite=on_nonfinite)
             pred = self._get_index().weighted_average(idx, np.asarray(w(dist), dtype=np.float64))
         if self._y.ndim == 1:
             pred = pred.ravel()
@@ -280,11 +295,15 @@ class TransformedKNeighborsRegressor(BaseEstimator, ABC):
             self.dataframe_index_in_ = self.regressor_.dataframe_index_in_
         return self
 
-    def _validated_raw(self, X):
+    def _validated_raw(self, X, finite=True):
         """Run the transformer's own input validation (feature-name warnings, dtype, NaN and
-        shape errors exactly as ``transform`` would raise them) and hand back the raw array."""
+        shape errors exactly as ``transform`` would raise them) and hand back the raw array.
+        ``finite=False`` leaves the scan for NaN / inf to the device (fused affine path); when the
+        device reports one, the full validation is repeated to raise the transformer's own error."""
         check_is_fitted(self, "transformer_")
-        return self.transformer_._validate_query(X)
+        if finite:
+            return self.transformer_._validate_query(X)
+        return self.transformer_._validate_query(X, finite=False)
 
     def kneighbors(self, X=None, n_neighbors=None, return_distance=True,
                    return_dataframe_index=False, use_deterministic_ordering=True):
@@ -300,8 +319,9 @@ class TransformedKNeighborsRegressor(BaseEstimator, ABC):
                 X=self._transform_X(X), n_neighbors=n_neighbors, return_distance=return_distance,
                 return_dataframe_index=return_dataframe_index,
                 use_deterministic_ordering=use_deterministic_ordering)
-        dist, idx, _ = reg._search(self._validated_raw(X), n_neighbors, use_deterministic_ordering,
-                                   raw=True, return_distance=return_distance)
+        dist, idx, _ = reg._search(self._validated_raw(X, finite=False), n_neighbors, use_deterministic_ordering,
+                                   raw=True, return_distance=return_distance,
+                                   on_nonfinite=lambda: self._validated_raw(X))
         return reg._finish_kneighbors(dist, idx, return_distance, return_dataframe_index)
 
     def predict(self, X):
@@ -310,7 +330,8 @@ class TransformedKNeighborsRegressor(BaseEstimator, ABC):
             return self.regressor_._predict_impl(self._validated_raw(X), raw=False, forest=self.transformer_)
         if X is None or not self._fusable():
             return self.regressor_.predict(self._transform_X(X))
-        return self.regressor_._predict_impl(self._validated_raw(X), raw=True)
+        return self.regressor_._predict_impl(self._validated_raw(X, finite=False), raw=True,
+                                             on_nonfinite=lambda: self._validated_raw(X))
 
     def score(self, X, y):
         return float(r2_score(y, self.predict(X)))

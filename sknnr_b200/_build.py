@@ -32,7 +32,8 @@ def nvcc_path() -> str:
 
 
 def lib_path() -> str:
-    return os.path.join(LIBDIR, LIBNAME)
+    # SKNNR_B200_LIB: load another build of the same library (A/B timing of kernel variants)
+    return os.environ.get("SKNNR_B200_LIB") or os.path.join(LIBDIR, LIBNAME)
 
 
 def _stale(target: str, deps: list[str]) -> bool:
@@ -42,9 +43,10 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, variant: str = "", extra_flags=()) -> str:
+    """``variant``: build into lib/libsknnr_b200_<variant>.so with ``extra_flags`` (e.g. -DSK_TC_JOINT=10)."""
     nvcc = nvcc_path()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + variant if variant else ""))
     os.makedirs(objdir, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
@@ -54,7 +56,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(o, [s, *hdrs, os.path.abspath(__file__)]):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             logs[src] = r.stderr
             if r.returncode != 0:
@@ -63,7 +65,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    out = lib_path()
+    out = os.path.join(LIBDIR, LIBNAME.replace(".so", f"_{variant}.so")) if variant else os.path.join(LIBDIR, LIBNAME)
     if force or _stale(out, objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -79,4 +81,6 @@ def build(verbose: bool = False, force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, variant=var[0] if var else "",
+                extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -24,31 +25,78 @@ def default_device() -> int:
     return 0
 
 
-class _PinnedBlock:
-    """Owner of one cudaHostAlloc block (freed with the last NumPy view of it)."""
+# Page-locked blocks are pooled: cudaHostAlloc of a gigabyte takes a large fraction of a second and a
+# freshly allocated ndarray costs a page fault per 4 KiB when the results land in it, so result
+# arrays of large queries come from blocks that earlier (dead) result arrays gave back.
+_POOL_CAP = int(os.environ.get("SKNNR_B200_PINNED_POOL_MB", "4096")) << 20
+_pool: dict[int, list] = {}
+_pool_bytes = 0
+_pool_lock = threading.Lock()
 
-    def __init__(self, nbytes):
+
+def _pool_take(nbytes):
+    global _pool_bytes
+    with _pool_lock:
+        lst = _pool.get(nbytes)
+        if lst:
+            _pool_bytes -= nbytes
+            return lst.pop()
+    return None
+
+
+def _pool_give(ptr, nbytes, lib):
+    global _pool_bytes
+    with _pool_lock:
+        if _pool_bytes + nbytes <= _POOL_CAP:
+            _pool.setdefault(nbytes, []).append(ptr)
+            _pool_bytes += nbytes
+            return
+    lib.sknnr_host_free(ptr)
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; handed back to the pool with the last NumPy view of it."""
+
+    def __init__(self, nbytes, pooled=False):
         self._lib = L.load()
-        self.ptr = C.c_void_p(None)
-        L.check(self._lib.sknnr_host_alloc(C.byref(self.ptr), int(max(nbytes, 1))))
+        self.nbytes = int(max(nbytes, 1))
+        self.pooled = pooled
+        self.ptr = _pool_take(self.nbytes) if pooled else None
+        if self.ptr is None:
+            self.ptr = C.c_void_p(None)
+            L.check(self._lib.sknnr_host_alloc(C.byref(self.ptr), self.nbytes))
 
     def __del__(self):
         try:
             if self.ptr and self.ptr.value:
-                self._lib.sknnr_host_free(self.ptr)
+                if self.pooled:
+                    _pool_give(self.ptr, self.nbytes, self._lib)
+                else:
+                    self._lib.sknnr_host_free(self.ptr)
         except Exception:
             pass
 
 
-def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+def pinned_empty(shape, dtype=np.float64, pooled=False) -> np.ndarray:
     """``np.empty`` in page-locked host memory: raster callers that fill / read such buffers get
-    full-rate asynchronous copies (pageable arrays are staged by the driver at a fraction of it)."""
+    full-rate asynchronous copies (pageable arrays are staged by the library's host threads)."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
-    block = _PinnedBlock(n * dtype.itemsize)
-    buf = (C.c_char * max(n * dtype.itemsize, 1)).from_address(block.ptr.value)
+    nbytes = n * dtype.itemsize
+    if pooled:
+        nbytes = -(-max(nbytes, 1) // (1 << 20)) << 20       # size classes of 1 MiB
+    block = _PinnedBlock(nbytes, pooled)
+    buf = (C.c_char * max(nbytes, 1)).from_address(block.ptr.value)
     buf._owner = block                      # keeps the block alive as long as the array's base
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def _result_empty(shape, dtype):
+    """Result array of a query: pooled page-locked memory once it is large enough to matter."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if n >= (8 << 20) and _POOL_CAP > 0:
+        return pinned_empty(shape, dtype, pooled=True)
+    return np.empty(shape, dtype=dtype)
 
 
 def _ptr(a):
@@ -137,6 +185,10 @@ def _raster_call(index, fn, handles, n_bands, bands, k, *, nodata=None, determin
     idx = _out(out_idx, (k, n_pix), np.int64) if return_index else None
     pred = _out(out_pred, (index.n_out, n_pix), np.float64) if mode != L.W_NONE else None
     n_valid = C.c_int64(0)
+    if nodata is not None:
+        # the comparison happens in float64 on the device: a nodata literal is first rounded to the
+        # bands' own type, as an `image == nodata` test on the host would do
+        nodata = float(bands.dtype.type(nodata))
     L.check(fn(*handles, _ptr(bands), L.F32 if bands.dtype == np.float32 else L.F64, n_pix, stride,
                0 if nodata is None else 1, 0.0 if nodata is None else float(nodata), int(k),
                index._flags(False, deterministic), int(decimals), _ptr(dist), _ptr(idx), mode, _ptr(pred),
@@ -181,9 +233,11 @@ class KNNIndex(_IndexBase):
     # -- host-buffer query (the drop-in call) ------------------------------------------
     def query(self, X, k, *, exclude_self=False, deterministic=True, decimals=10,
               row_offset=0, transformed=False, weights=None, with_pred=False,
-              return_distance=True, return_index=True):
+              return_distance=True, return_index=True, check_finite=False):
         """kneighbors (+ optional predict) on host arrays.  ``X=None`` with
-        ``exclude_self`` searches the reference set against itself."""
+        ``exclude_self`` searches the reference set against itself.  ``check_finite``: the device
+        looks for NaN / inf among the query values while it projects them and the call raises
+        :class:`NonFiniteInput` (a ``ValueError``) instead of returning results."""
         if exclude_self:
             n_q, Xp, dt, ldx = self.n_ref, None, L.F64, 0
         else:
@@ -201,12 +255,14 @@ class KNNIndex(_IndexBase):
                 raise ValueError(f"X has {X.shape[1]} features, but {want} are expected")
             Xp = _ptr(X)
         mode = _weights_mode(weights, with_pred)
-        dist = np.empty((n_q, k), dtype=np.float64) if return_distance else None
-        idx = np.empty((n_q, k), dtype=np.int64) if return_index else None
-        pred = np.empty((n_q, self.n_out), dtype=np.float64) if mode != L.W_NONE else None
+        dist = _result_empty((n_q, k), np.float64) if return_distance else None
+        idx = _result_empty((n_q, k), np.int64) if return_index else None
+        pred = _result_empty((n_q, self.n_out), np.float64) if mode != L.W_NONE else None
+        flags = self._flags(exclude_self, deterministic, transformed)
+        if check_finite and not exclude_self:
+            flags |= L.CHECK_FINITE
         L.check(self._lib.sknnr_kneighbors(
-            self._h, Xp, dt, n_q, ldx, int(row_offset), int(k),
-            self._flags(exclude_self, deterministic, transformed), int(decimals),
+            self._h, Xp, dt, n_q, ldx, int(row_offset), int(k), flags, int(decimals),
             _ptr(dist), _ptr(idx), mode, _ptr(pred), None))
         return dist, idx, pred
 

@@ -15,7 +15,7 @@ from ._build import lib_path
 # mirrors include/sknnr_b200.h
 ABI_VERSION = 1
 F64, F32 = 0, 1
-EXCLUDE_SELF, DETERMINISTIC, TRANSFORMED, DEVICE_PTRS = 1, 2, 4, 8
+EXCLUDE_SELF, DETERMINISTIC, TRANSFORMED, DEVICE_PTRS, CHECK_FINITE = 1, 2, 4, 8, 16
 W_NONE, W_UNIFORM, W_DISTANCE = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TENSOR, ENGINE_EXACT = 0, 1, 2, 3
 MAX_CODE = 31743
@@ -28,7 +28,8 @@ EXPORTS = [
     "sknnr_hamming_weighted_average", "sknnr_hamming_index_stats", "sknnr_host_alloc",
     "sknnr_host_free", "sknnr_measure_fp32_peak", "sknnr_forest_create", "sknnr_forest_destroy",
     "sknnr_forest_apply", "sknnr_hamming_kneighbors_forest", "sknnr_raster_kneighbors",
-    "sknnr_hamming_raster_kneighbors_forest",
+    "sknnr_hamming_raster_kneighbors_forest", "sknnr_device_alloc", "sknnr_device_free",
+    "sknnr_ipc_export", "sknnr_ipc_open", "sknnr_ipc_close", "sknnr_device_copy",
 ]
 
 
@@ -45,6 +46,10 @@ class Stats(C.Structure):
 
 class SknnrError(RuntimeError):
     pass
+
+
+class NonFiniteInput(ValueError):
+    """SKNNR_ENONFINITE: the device found NaN / inf among the query values (SKNNR_CHECK_FINITE)."""
 
 
 _lib = None
@@ -90,6 +95,12 @@ def load() -> C.CDLL:
     lib.sknnr_raster_kneighbors.argtypes = [vp, vp, i32, i64, i64, i32, C.c_double, i32, u32, i32, vp, vp, i32,
                                             vp, C.c_double, i64, C.c_double, C.POINTER(i64)]
     lib.sknnr_hamming_raster_kneighbors_forest.argtypes = [vp] + lib.sknnr_raster_kneighbors.argtypes
+    lib.sknnr_device_alloc.argtypes = [i32, C.POINTER(vp), i64]
+    lib.sknnr_device_free.argtypes = [i32, vp]
+    lib.sknnr_ipc_export.argtypes = [i32, vp, vp]
+    lib.sknnr_ipc_open.argtypes = [i32, vp, C.POINTER(vp)]
+    lib.sknnr_ipc_close.argtypes = [i32, vp]
+    lib.sknnr_device_copy.argtypes = [i32, vp, vp, i64, i32, vp]
     for name in EXPORTS:
         if name != "sknnr_last_error":
             getattr(lib, name).restype = C.c_int
@@ -108,6 +119,8 @@ def check(rc: int) -> None:
         raise ValueError(msg)
     if rc == -5:
         raise NotImplementedError(msg)
+    if rc == -6:
+        raise NonFiniteInput(msg)
     raise SknnrError(msg)
 
 

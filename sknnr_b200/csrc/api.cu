@@ -8,10 +8,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace sk;
@@ -44,7 +48,133 @@ struct Options {
     int64_t tc_streams = 0;     // tensor engine: candidate streams per query (0 = automatic, else 1 or 2)
     int64_t host_slots = 8;     // chunks of a host-buffer call in flight (1..8)
     int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = off)
+    int64_t host_threads = 0;   // workers that stage pageable host buffers (0 = automatic)
+    int64_t stage_rows = 1 << 19; // rows per chunk of a call whose buffers are pageable
 } g_opt;
+
+// ---- host staging of pageable buffers -----------------------------------------------------
+// cudaMemcpyAsync on pageable memory goes through the driver's own bounce buffer on the calling
+// thread at a fraction of the PCIe rate.  Callers of the estimators hand over ordinary NumPy arrays,
+// so the library stages them itself: a few worker threads copy a chunk into (out of) page-locked
+// slot buffers while the GPU works on the previous chunks.
+class HostPool {
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+
+    void worker() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return !q_.empty(); });
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+        }
+    }
+
+public:
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; ++i) {
+            th_.emplace_back([this] { worker(); });
+            th_.back().detach();   // the pool lives until the process exits
+        }
+    }
+    int size() const { return (int)th_.size(); }
+    static HostPool &get() {
+        static HostPool *pool = [] {
+            int n = (int)g_opt.host_threads;
+            if (n <= 0) {
+                const unsigned hw = std::thread::hardware_concurrency();
+                n = (int)std::min(8u, std::max(1u, hw / 2));
+            }
+            return new HostPool(n - 1);   // the calling thread takes a share as well
+        }();
+        return *pool;
+    }
+    // run f(i) for i in [0, n) on the workers and the caller; returns when all are done
+    void parallel_for(int n, const std::function<void(int)> &f) {
+        if (n <= 0) return;
+        struct Sync {
+            std::mutex m;
+            std::condition_variable cv;
+            int left;
+        } sy;
+        sy.left = n - 1;
+        for (int i = 1; i < n; ++i) {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.emplace_back([&sy, &f, i] {
+                f(i);
+                std::lock_guard<std::mutex> l2(sy.m);
+                if (--sy.left == 0) sy.cv.notify_one();
+            });
+            cv_.notify_one();
+        }
+        f(0);
+        std::unique_lock<std::mutex> lk(sy.m);
+        sy.cv.wait(lk, [&] { return sy.left == 0; });
+    }
+};
+
+// rows x row_bytes from src (row stride src_ld bytes) to dst (row stride dst_ld bytes), split over the pool
+void parallel_copy_rows(void *dst, size_t dst_ld, const void *src, size_t src_ld, size_t row_bytes, int64_t rows) {
+    if (rows <= 0 || row_bytes == 0) return;
+    HostPool &pool = HostPool::get();
+    const size_t total = (size_t)rows * row_bytes;
+    int parts = (int)std::min<size_t>((size_t)pool.size() + 1, std::max<size_t>(1, total >> 21));   // >= 2 MB each
+    const int64_t per = (rows + parts - 1) / parts;
+    pool.parallel_for(parts, [&](int i) {
+        const int64_t r0 = (int64_t)i * per, r1 = std::min(rows, r0 + per);
+        if (r0 >= r1) return;
+        unsigned char *d = (unsigned char *)dst + (size_t)r0 * dst_ld;
+        const unsigned char *sp = (const unsigned char *)src + (size_t)r0 * src_ld;
+        if (dst_ld == row_bytes && src_ld == row_bytes) {
+            memcpy(d, sp, (size_t)(r1 - r0) * row_bytes);
+        } else {
+            for (int64_t r = r0; r < r1; ++r, d += dst_ld, sp += src_ld) memcpy(d, sp, row_bytes);
+        }
+    });
+}
+
+void parallel_copy_flat(void *dst, const void *src, size_t bytes) {
+    const size_t piece = 1 << 20;
+    parallel_copy_rows(dst, piece, src, piece, piece, (int64_t)(bytes / piece));
+    if (bytes % piece) memcpy((unsigned char *)dst + bytes / piece * piece, (const unsigned char *)src + bytes / piece * piece, bytes % piece);
+}
+
+// true for ordinary (not page-locked, not device, not managed) host memory
+bool is_pageable(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc((void **)&p, n * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -88,7 +218,7 @@ struct Slot {
     DevBuf<unsigned char> x;       // staged query rows (host callers)
     DevBuf<double> z64;
     DevBuf<float> qimg;
-    DevBuf<float> qimg_tc;         // tensor-core engine query image
+    DevBuf<__half> qimg_tc;        // tensor-core engine query image (FP16)
     DevBuf<double> z64c;           // compacted rows of the cascade's second stage
     DevBuf<int> fb2;               // second-stage failures: [0] = count, [1..] = list
     DevBuf<uint16_t> codes;        // node codes produced by the device forest walk
@@ -101,7 +231,6 @@ struct Slot {
     DevBuf<double> o_dist;
     DevBuf<long long> o_idx;
     DevBuf<double> o_pred;
-    DevBuf<double> scratch;        // exact kernel distance scratch [grid, n_ref]
     // raster front end: compacted feature rows, pixel -> row map, group offsets, band-major results
     DevBuf<unsigned char> xc;
     DevBuf<int> r_pos, r_cnt;
@@ -111,14 +240,24 @@ struct Slot {
     cudaEvent_t ev_cnt = nullptr;
     std::vector<cudaEvent_t> evs;  // pooled (start, stop) pairs around the search kernels
     size_t ev_used = 0;            // events handed out since the last harvest
-    int *h_fb = nullptr;           // pinned: [0] first-stage, [1] second-stage failures in flight
+    int *h_fb = nullptr;           // pinned: [0] first-stage, [1] second-stage failures, [2] non-finite flag
     bool fb_pending = false;
     long long rows_in_flight = 0;
+    DevBuf<int> nonfinite;         // [0] != 0: a query value of the chunk in flight is NaN / inf
+    bool flag_pending = false;
+    // device-pointer calls are not synchronised: the slot's scratch stays in use until ev_last
+    cudaEvent_t ev_last = nullptr;
+    bool last_pending = false;
+    // page-locked staging of pageable caller buffers (one chunk in, one chunk out) and the copy-out
+    // that is still owed to the caller once the slot's stream has drained
+    PinBuf<unsigned char> h_x, h_dist, h_idx, h_pred;
+    struct CopyOut { void *dst; const void *src; size_t bytes; };
+    std::vector<CopyOut> owed;
     void release() {
         x.release(); z64.release(); qimg.release(); qimg_tc.release(); z64c.release(); fb2.release();
         codes.release(); ids32.release(); qimg_h.release(); cand_idx.release();
         cand_thr.release(); cand_cnt.release(); fb.release(); o_dist.release();
-        o_idx.release(); o_pred.release(); scratch.release();
+        o_idx.release(); o_pred.release();
         xc.release(); r_pos.release(); r_cnt.release(); r_dist.release(); r_pred.release(); r_idx.release();
         if (h_cnt) cudaFreeHost(h_cnt);
         if (ev_cnt) cudaEventDestroy(ev_cnt);
@@ -127,6 +266,11 @@ struct Slot {
         evs.clear();
         ev_used = 0;
         if (h_fb) cudaFreeHost(h_fb);
+        nonfinite.release();
+        h_x.release(); h_dist.release(); h_idx.release(); h_pred.release();
+        owed.clear();
+        if (ev_last) cudaEventDestroy(ev_last);
+        ev_last = nullptr; last_pending = false; flag_pending = false;
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (tail_stream) cudaStreamDestroy(tail_stream);
         if (ev_stage1) cudaEventDestroy(ev_stage1);
@@ -187,8 +331,10 @@ struct IndexBase {
             CK(cudaStreamCreateWithFlags(&s.tail_stream, cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&s.ev_stage1, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
-            CK(cudaHostAlloc((void **)&s.h_fb, 2 * sizeof(int), cudaHostAllocDefault));
-            s.h_fb[0] = s.h_fb[1] = 0;
+            CK(cudaHostAlloc((void **)&s.h_fb, 4 * sizeof(int), cudaHostAllocDefault));
+            s.h_fb[0] = s.h_fb[1] = s.h_fb[2] = 0;
+            CK(s.nonfinite.reserve(1));
+            CK(cudaEventCreateWithFlags(&s.ev_last, cudaEventDisableTiming));
             CK(cudaHostAlloc((void **)&s.h_cnt, sizeof(int), cudaHostAllocDefault));
             CK(cudaEventCreateWithFlags(&s.ev_cnt, cudaEventDisableTiming));
         }
@@ -197,6 +343,9 @@ struct IndexBase {
     void release_common() {
         cudaSetDevice(device);
         for (auto &s : slots) s.release();
+        exact_scr.release(); exact_big.release();
+        if (ev_exact) cudaEventDestroy(ev_exact);
+        ev_exact = nullptr;
         if (d_y) cudaFree(d_y);
         d_y = nullptr;
     }
@@ -216,6 +365,96 @@ struct IndexBase {
             chunk_fb_seen += s.h_fb[0];
             s.fb_pending = false;
         }
+        if (s.flag_pending) {
+            if (s.h_fb[2] != 0) saw_nonfinite = true;
+            s.flag_pending = false;
+        }
+    }
+    // The exhaustive kernel's scratch ([CTAs][n_ref] distances, + the big-k selection arrays) exists
+    // once per index: its launches (cascade tails of different slots) are chained through ev_exact.
+    DevBuf<double> exact_scr, exact_big;
+    // CTAs of an exhaustive launch: two per SM, fewer when n_ref is so large that their distance
+    // rows would exceed 1 GB of scratch
+    int exact_ctas(int64_t rows) const {
+        const int64_t by_mem = std::max<int64_t>(1, (int64_t)(1 << 30) / (8 * std::max<int64_t>(n_ref, 1)));
+        return (int)std::max<int64_t>(0, std::min<int64_t>({rows, (int64_t)n_sm * 2, by_mem}));
+    }
+    cudaEvent_t ev_exact = nullptr;
+    bool exact_used = false;
+    cudaError_t launch_exact_chained(ExactArgs &ea, const FinishParams &fp, int kk, cudaStream_t st) {
+        if (ea.grid <= 0) return cudaSuccess;
+        cudaError_t e = exact_scr.reserve((size_t)exact_ctas(1 << 30) * (size_t)ea.n_ref);   // (a growing reserve frees the
+        if (e != cudaSuccess) return e;                                         //  old block: cudaFree waits)
+        ea.scratch = exact_scr.p;
+        ea.big = nullptr;
+        if (kk > MAXK) {
+            e = exact_big.reserve((size_t)ea.grid * 4 * (size_t)kk);
+            if (e != cudaSuccess) return e;
+            ea.big = exact_big.p;
+        }
+        if (!ev_exact) {
+            e = cudaEventCreateWithFlags(&ev_exact, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        if (exact_used) {
+            e = cudaStreamWaitEvent(st, ev_exact, 0);
+            if (e != cudaSuccess) return e;
+        }
+        e = launch_exact(ea, fp, st);
+        if (e != cudaSuccess) return e;
+        exact_used = true;
+        return cudaEventRecord(ev_exact, st);
+    }
+    bool saw_nonfinite = false;   // some query value of the last call was NaN / inf
+    // Wait until everything the slot was last used for is complete (its own stream, its tail, a
+    // device-pointer caller's stream), hand the staged results of that chunk to the caller and
+    // collect its counters.  After this the slot's buffers are free.
+    cudaError_t finish_slot(Slot &s) {
+        cudaError_t e = cudaStreamSynchronize(s.stream);
+        if (e == cudaSuccess && s.tail_pending) e = cudaEventSynchronize(s.ev_tail);
+        if (e == cudaSuccess && s.last_pending) e = cudaEventSynchronize(s.ev_last);
+        s.tail_pending = false;
+        s.last_pending = false;
+        if (e == cudaSuccess)
+            for (auto &c : s.owed) parallel_copy_flat(c.dst, c.src, c.bytes);
+        s.owed.clear();
+        harvest(s);
+        return e;
+    }
+    // error path: nothing of this call may still be reading or writing caller memory when it returns
+    void quiesce() {
+        for (auto &s : slots) {
+            cudaStreamSynchronize(s.stream);
+            if (s.tail_stream) cudaStreamSynchronize(s.tail_stream);
+            if (s.last_pending) cudaEventSynchronize(s.ev_last);
+            s.tail_pending = s.last_pending = s.fb_pending = s.flag_pending = false;
+            s.owed.clear();
+            s.ev_used = 0;
+        }
+        cudaGetLastError();
+    }
+};
+
+// a device-pointer call lends the caller's stream to a slot for one chunk; the slot's own stream
+// comes back whatever way the scope is left
+struct StreamLoan {
+    Slot &s;
+    cudaStream_t saved;
+    StreamLoan(Slot &slot, cudaStream_t st, bool lend) : s(slot), saved(slot.stream) {
+        if (lend) s.stream = st;
+    }
+    ~StreamLoan() { s.stream = saved; }
+};
+// leaves the handle quiescent when a call fails half way through its chunks
+struct CallGuard {
+    IndexBase *ix;
+    cudaStream_t user;
+    bool ok = false;
+    CallGuard(IndexBase *i, cudaStream_t u) : ix(i), user(u) {}
+    ~CallGuard() {
+        if (ok) return;
+        if (user) cudaStreamSynchronize(user);
+        ix->quiesce();
     }
 };
 
@@ -227,7 +466,6 @@ int check_query_args(int64_t n_ref, int n_out, int64_t n_q, int k, uint32_t flag
     if (kk > n_ref)
         return fail(SKNNR_EINVAL, excl ? "Expected n_neighbors < n_samples_fit"
                                        : "Expected n_neighbors <= n_samples_fit");
-    if (kk > MAXK) return fail(SKNNR_EUNSUP, "k (+1 with self exclusion) > 32 is not supported");
     if (excl && X != nullptr) return fail(SKNNR_EINVAL, "X must be NULL with SKNNR_EXCLUDE_SELF");
     if (!excl && (X == nullptr || n_q < 0)) return fail(SKNNR_EINVAL, "X is NULL");
     if (weights != SKNNR_W_NONE) {
@@ -249,8 +487,9 @@ struct sknnr_index : IndexBase {
     float *d_rimg = nullptr;
     int n_rtiles = 0;
     double r2max = 0.0;
-    float *d_rimg_tc = nullptr;    // tensor-core engine reference image
+    __half *d_rimg_tc = nullptr;   // tensor-core engine reference image (FP16)
     int n_rtiles_tc = 0, kc_tot = 0, tc_nstage = 0;
+    double tc_sigma = 1.0;         // power-of-two scale of both tensor-engine images
     bool tensor_ok = false;        // shape fits the tensor engine
     bool tensor_demoted = false;   // too many uncertified rows: fall back to the SIMT engine
 };
@@ -315,6 +554,12 @@ int sknnr_set_option(const char *name, int64_t value) {
     } else if (!strcmp(name, "host_slots")) {
         if (value < 1 || value > IndexBase::kSlots) return fail(SKNNR_EINVAL, "host_slots must be 1..8");
         g_opt.host_slots = value;
+    } else if (!strcmp(name, "host_threads")) {
+        if (value < 0 || value > 64) return fail(SKNNR_EINVAL, "host_threads must be 0..64");
+        g_opt.host_threads = value;   // read when the staging pool starts (first pageable call)
+    } else if (!strcmp(name, "stage_rows")) {
+        if (value < 1024) return fail(SKNNR_EINVAL, "stage_rows must be >= 1024");
+        g_opt.stage_rows = (value + 1023) / 1024 * 1024;
     } else if (!strcmp(name, "tc_seed_stride")) {
         if (value < 0 || value > 64) return fail(SKNNR_EINVAL, "tc_seed_stride must be 0..64");
         g_opt.tc_seed_stride = value;
@@ -331,6 +576,50 @@ int sknnr_host_alloc(void **ptr, int64_t bytes) {
 }
 int sknnr_host_free(void *ptr) {
     if (ptr) CK(cudaFreeHost(ptr));
+    return SKNNR_OK;
+}
+
+// ---- device buffers a multi-process caller shares over NVLink ---------------------------------
+int sknnr_device_alloc(int32_t device, void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(SKNNR_EINVAL, "bad arguments");
+    CK(cudaSetDevice(device));
+    CK(cudaMalloc(ptr, (size_t)bytes));
+    return SKNNR_OK;
+}
+int sknnr_device_free(int32_t device, void *ptr) {
+    CK(cudaSetDevice(device));
+    if (ptr) CK(cudaFree(ptr));
+    return SKNNR_OK;
+}
+int sknnr_ipc_export(int32_t device, void *ptr, void *handle64) {
+    if (!ptr || !handle64) return fail(SKNNR_EINVAL, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    CK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle64, &h, 64);
+    return SKNNR_OK;
+}
+int sknnr_ipc_open(int32_t device, const void *handle64, void **ptr) {
+    if (!ptr || !handle64) return fail(SKNNR_EINVAL, "NULL argument");
+    CK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SKNNR_OK;
+}
+int sknnr_ipc_close(int32_t device, void *ptr) {
+    CK(cudaSetDevice(device));
+    if (ptr) CK(cudaIpcCloseMemHandle(ptr));
+    return SKNNR_OK;
+}
+int sknnr_device_copy(int32_t device, void *dst, const void *src, int64_t bytes, int32_t kind, void *stream) {
+    if (!dst || !src || bytes < 0) return fail(SKNNR_EINVAL, "bad arguments");
+    CK(cudaSetDevice(device));
+    const cudaMemcpyKind kd = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost
+                                                                             : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, kd, (cudaStream_t)stream));
+    if (kind != 0 || !stream) CK(cudaStreamSynchronize((cudaStream_t)stream));
     return SKNNR_OK;
 }
 
@@ -402,50 +691,54 @@ int sknnr_index_create(const double *fit_z, int64_t n_ref, int32_t d_out, const 
     if (e == cudaSuccess)
         e = cudaMemcpy(ix->d_rimg, rimg.data(), rimg.size() * sizeof(float), cudaMemcpyHostToDevice);
 
-    // tensor-core engine image: tiles of 128 plots, [chunk][row][4] TF32 (round to nearest),
-    // K padded to dpad plus one extra block whose first chunk holds a 3-way TF32 split of |r|^2
-    // (+inf for padding plots) and whose second chunk is zero
-    ix->kc_tot = ix->dpad / 4 + 2;
+    // tensor-core engine image: tiles of 128 plots, [chunk][row][8] FP16 (round to nearest even) of
+    // sigma * (r - mu), K = d' + 3 padded to a multiple of 16: elements d' .. d'+2 hold a 3-way FP16
+    // split of sigma^2 |r - mu|^2 (+inf for padding plots), the rest is zero.  sigma = 2^e scales the
+    // plots so that sigma^2 max|r - mu|^2 lies in (2^12, 2^14]: FP16 then keeps its 11-bit significand
+    // (the precision of TF32) for every element above 2^-21 of the largest norm, and elements below
+    // that (FP16 subnormals, absolute error 2^-25) cannot matter at the certificate's 2^-10.
+    const int k_tot = round_up(d_out + 3, 16);
+    ix->kc_tot = k_tot / 8;
     ix->n_rtiles_tc = (int)((n_ref + TC_N - 1) / TC_N);
-    ix->tc_nstage = search_tc_pick_stages(ix->kc_tot);
-    ix->tensor_ok = ix->tc_nstage != 0;
+    ix->tc_nstage = search_tc_pick_config(ix->kc_tot);
+    ix->tensor_ok = ix->tc_nstage != 0 && std::isfinite(r2max);
     if (e == cudaSuccess && ix->tensor_ok) {
-        auto tf32 = [](float x) -> float {
-            uint32_t b;
-            memcpy(&b, &x, 4);
-            if ((b & 0x7f800000u) != 0x7f800000u) b = (b + 0x1000u) & 0xffffe000u;
-            float r;
-            memcpy(&r, &b, 4);
-            return r;
-        };
-        const size_t op_floats = (size_t)ix->kc_tot * TC_N * 4;
-        std::vector<float> timg((size_t)ix->n_rtiles_tc * op_floats, 0.0f);
+        int ex = 0;
+        if (r2max > 0.0) {
+            int fe;
+            std::frexp(16384.0 / r2max, &fe);          // 16384 / r2max = m * 2^fe, m in [0.5, 1)
+            ex = (fe - 1) >= 0 ? (fe - 1) / 2 : -((1 - (fe - 1)) / 2);   // floor((fe - 1) / 2)
+        }
+        ex = std::max(-500, std::min(500, ex));
+        ix->tc_sigma = std::ldexp(1.0, ex);
+        const double sg = ix->tc_sigma;
+        auto f16 = [](double x) -> double { return (double)__half2float(__float2half_rn((float)x)); };
+        const size_t op_halves = (size_t)ix->kc_tot * TC_N * 8;
+        std::vector<__half> timg((size_t)ix->n_rtiles_tc * op_halves, __float2half_rn(0.0f));
         for (int t = 0; t < ix->n_rtiles_tc; ++t) {
-            float *img = timg.data() + (size_t)t * op_floats;
+            __half *img = timg.data() + (size_t)t * op_halves;
+            auto at = [&](int k, int jj) -> __half & { return img[((size_t)(k / 8) * TC_N + jj) * 8 + (k % 8)]; };
             for (int jj = 0; jj < TC_N; ++jj) {
                 const int64_t j = (int64_t)t * TC_N + jj;
-                float *nrm = img + ((size_t)(ix->dpad / 4) * TC_N + jj) * 4;
                 if (j >= n_ref) {
-                    nrm[0] = INFINITY;
+                    at(d_out, jj) = __float2half_rn(INFINITY);
                     continue;
                 }
-                double n32 = 0.0;
+                double n16 = 0.0;
                 for (int k = 0; k < d_out; ++k) {
-                    const float f = tf32((float)(fit_z[j * d_out + k] - mu[k]));
-                    img[((size_t)(k / 4) * TC_N + jj) * 4 + (k % 4)] = f;
-                    n32 += (double)f * (double)f;
+                    const double f = f16((fit_z[j * d_out + k] - mu[k]) * sg);
+                    at(k, jj) = __float2half_rn((float)f);
+                    n16 += f * f;
                 }
-                const float hi = tf32((float)n32);
-                const float mid = tf32((float)(n32 - (double)hi));
-                const float lo = tf32((float)(n32 - (double)hi - (double)mid));
-                nrm[0] = hi;
-                nrm[1] = mid;
-                nrm[2] = lo;
+                const double hi = f16(n16), mid = f16(n16 - hi), lo = f16(n16 - hi - mid);
+                at(d_out, jj) = __float2half_rn((float)hi);
+                at(d_out + 1, jj) = __float2half_rn((float)mid);
+                at(d_out + 2, jj) = __float2half_rn((float)lo);
             }
         }
-        e = cudaMalloc(&ix->d_rimg_tc, timg.size() * sizeof(float));
+        e = cudaMalloc(&ix->d_rimg_tc, timg.size() * sizeof(__half));
         if (e == cudaSuccess)
-            e = cudaMemcpy(ix->d_rimg_tc, timg.data(), timg.size() * sizeof(float), cudaMemcpyHostToDevice);
+            e = cudaMemcpy(ix->d_rimg_tc, timg.data(), timg.size() * sizeof(__half), cudaMemcpyHostToDevice);
     }
     if (e != cudaSuccess) {
         sknnr_index_destroy(ix);
@@ -482,14 +775,15 @@ int sknnr_index_stats(sknnr_index *ix, sknnr_stats *out) {
 // With engine = SIMT stage 1 is skipped (L1 = all rows); with engine = EXACT only stage 3 runs.
 static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_t ldx, bool transformed,
                      int64_t rows, int64_t row0, int k, uint32_t flags, int decimals, int weights,
-                     double *o_dist, long long *o_idx, double *o_pred) {
+                     double *o_dist, long long *o_idx, double *o_pred, bool check_finite = false) {
     const bool excl = flags & SKNNR_EXCLUDE_SELF;
     const int kk = k + (excl ? 1 : 0);
     cudaStream_t st = s.stream;
     const int64_t prow = padded_rows(rows);
+    if (check_finite) CK(cudaMemsetAsync(s.nonfinite.p, 0, sizeof(int), st));
 
-    int kc = pick_kc(kk, 1);
-    if (g_opt.kc > kc) kc = (int)g_opt.kc;
+    int kc = pick_kc(kk, 1);   // 0: k (+1) is beyond the filtered engines' candidate lists -> exhaustive kernel
+    if (kc != 0 && g_opt.kc > kc) kc = (int)g_opt.kc;
     const bool simt_ok = kc != 0 && search_simt_pick_stages(ix->dpad, kc) != 0;
     const bool tensor_ok = ix->tensor_ok && !ix->tensor_demoted && kc != 0 && kc <= 16 && simt_ok;
     int engine = (int)g_opt.engine;
@@ -518,12 +812,17 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     const bool use_simt_first = engine == SKNNR_ENGINE_SIMT;
     CK(s.z64.reserve((size_t)rows * ix->d_out));
     if (engine != SKNNR_ENGINE_EXACT) CK(s.qimg.reserve((size_t)prow * ix->dpad));
-    if (use_tc) CK(s.qimg_tc.reserve((size_t)prow * ix->kc_tot * 4));
+    if (use_tc) CK(s.qimg_tc.reserve((size_t)prow * ix->kc_tot * 8));
     CK(launch_project(dX, x_f32, ldx, rows, transformed ? ix->d_out : ix->d_in, ix->d_out, ix->dpad,
                       transformed ? nullptr : ix->d_center, transformed ? nullptr : ix->d_scale,
                       transformed ? nullptr : ix->d_proj, ix->d_mu, s.z64.p,
-                      use_simt_first ? s.qimg.p : nullptr, use_tc ? s.qimg_tc.p : nullptr, 2, nullptr, st));
+                      use_simt_first ? s.qimg.p : nullptr, use_tc ? s.qimg_tc.p : nullptr, ix->kc_tot,
+                      ix->tc_sigma, nullptr, check_finite ? s.nonfinite.p : nullptr, st));
     ix->stats.kernel_launches++;
+    if (check_finite) {
+        CK(cudaMemcpyAsync(&s.h_fb[2], s.nonfinite.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        s.flag_pending = true;
+    }
 
     ExactArgs ea{};
     ea.metric = 0;
@@ -532,15 +831,13 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     ea.d = ix->d_out;
     ea.n_q = rows;
     ea.n_ref = (int)ix->n_ref;
-    ea.grid = (int)std::min<int64_t>(rows, (int64_t)ix->n_sm * 2);
-    CK(s.scratch.reserve((size_t)ix->n_sm * 2 * ix->n_ref));
-    ea.scratch = s.scratch.p;
+    ea.grid = ix->exact_ctas(rows);
 
     if (engine == SKNNR_ENGINE_EXACT) {
         ea.list = nullptr;
         ea.count = nullptr;
         if (g_opt.timing) CK(s.mark(st));
-        CK(launch_exact(ea, fp, st));
+        CK(ix->launch_exact_chained(ea, fp, kk, st));
         if (g_opt.timing) CK(s.mark(st));
         ix->stats.kernel_launches++;
         return SKNNR_OK;
@@ -564,15 +861,19 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     ra.r2max = ix->r2max;
     // |approx score - true score| <= eps_s * (|q|^2 + max|r|^2)   ("certificate")
     //   SIMT  : FP32 rounding of both operands and of |r|^2, plus dpad sequential FP32 FMAs
-    //   tensor: TF32 (round-to-nearest, 2^-11) operands, exact products, FP32 accumulation
+    //   tensor: FP16 (round-to-nearest, 2^-11 relative; subnormals 2^-25 absolute, < 2^-24 of the
+    //           bound's scale - see sknnr_index_create) operands, exact products, FP32 accumulation
     const double eps_simt = (2.0 * ix->dpad + 8.0) * std::ldexp(1.0, -24) * 1.01;
-    const double eps_tc = std::ldexp(1.0, -10) * 1.02 + (4.0 * ix->kc_tot) * std::ldexp(1.0, -20);
+    const double eps_tc = std::ldexp(1.0, -10) * 1.02 + (8.0 * ix->kc_tot) * std::ldexp(1.0, -20) +
+                          std::ldexp(1.0, -24);
+    ra.thr_scale = 1.0;
+    ra.qn_limit = INFINITY;
 
     const int *stage2_count = nullptr;  // null: stage 2 covers every row of the chunk
     if (use_tc) {
         if (g_opt.timing) CK(s.mark(st));
-        // two candidate streams of 8 per query while k (+1) <= 8 (twice the scanner warps), else one of 16
-        int ns = kk <= 8 ? 2 : 1;
+        // two candidate streams per query while k (+1) <= 7 (twice the scanner warps), else one
+        int ns = kk <= 7 ? 2 : 1;   // a stream's list keeps at most 7 (ns = 2) / 15 (ns = 1) candidates
         if (g_opt.tc_streams == 1) ns = 1;
         CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, ns, ix->tc_nstage,
                             (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, st));
@@ -582,6 +883,9 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
         ra.z64 = s.z64.p;
         ra.n_q = rows;
         ra.eps_s = eps_tc;
+        // the image holds -2 sigma (z - mu) in FP16: every element is finite while 2 sigma |z - mu| < 65504
+        ra.thr_scale = 1.0 / (ix->tc_sigma * ix->tc_sigma);
+        ra.qn_limit = 0.99 * (32752.0 / ix->tc_sigma) * (32752.0 / ix->tc_sigma);
         ra.fb_count = s.fb.p;
         ra.fb_list = s.fb.p + 1;
         ra.n_rows_dev = nullptr;
@@ -595,7 +899,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
         CK(s.z64c.reserve((size_t)rows * ix->d_out));
         CK(launch_gather_rows(s.z64.p, ix->d_out, s.fb.p + 1, s.fb.p, rows, s.z64c.p, st));
         CK(launch_project(s.z64c.p, 0, ix->d_out, rows, ix->d_out, ix->d_out, ix->dpad, nullptr, nullptr,
-                          nullptr, ix->d_mu, nullptr, s.qimg.p, nullptr, 0, s.fb.p, st));
+                          nullptr, ix->d_mu, nullptr, s.qimg.p, nullptr, 0, 1.0, s.fb.p, nullptr, st));
         ix->stats.kernel_launches += 4;
         stage2_count = s.fb.p;
     }
@@ -612,6 +916,8 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     ra.z64 = use_tc ? s.z64c.p : s.z64.p;
     ra.n_q = rows;
     ra.eps_s = eps_simt;
+    ra.thr_scale = 1.0;
+    ra.qn_limit = INFINITY;
     ra.fb_count = s.fb2.p;
     ra.fb_list = s.fb2.p + 1;
     ra.n_rows_dev = stage2_count;
@@ -622,7 +928,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     // stage 3: exhaustive float64 search of whatever is still uncertified (exact ties etc.)
     ea.list = s.fb2.p + 1;
     ea.count = s.fb2.p;
-    CK(launch_exact(ea, fp, st));
+    CK(ix->launch_exact_chained(ea, fp, kk, st));
     ix->stats.kernel_launches++;
     CK(cudaMemcpyAsync(&s.h_fb[0], use_tc ? s.fb.p : s.fb2.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&s.h_fb[1], s.fb2.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -663,16 +969,36 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     if (ldx < cols) return fail(SKNNR_EINVAL, "ldx smaller than the number of features");
     const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
 
-    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; }
+    cudaStream_t user_stream = dev_ptrs ? (cudaStream_t)stream : nullptr;
+    CallGuard guard(ix, user_stream);
+    // whatever an earlier call (possibly a device-pointer call on another stream) left running on
+    // the slots this call is going to use must be complete before their scratch is reused
+    if (dev_ptrs) {
+        for (int i = 0; i < 2; ++i) {
+            Slot &s = ix->slots[i];
+            if (s.last_pending) CK(cudaStreamWaitEvent(user_stream, s.ev_last, 0));
+        }
+    } else {
+        for (auto &s : ix->slots) CK(ix->finish_slot(s));
+    }
+    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; s.flag_pending = false; }
     ix->stats = sknnr_stats{};
     ix->stats.n_queries = n_q;
-    if (n_q == 0) return SKNNR_OK;
+    ix->saw_nonfinite = false;
+    if (n_q == 0) { guard.ok = true; return SKNNR_OK; }
 
-    cudaStream_t user_stream = (cudaStream_t)stream;
+    // ordinary NumPy buffers are staged through page-locked slot buffers by the host pool
+    const bool stage_in = !x_on_device && is_pageable(X);
+    const bool stage_dist = !dev_ptrs && out_dist && is_pageable(out_dist);
+    const bool stage_idx = !dev_ptrs && out_idx && is_pageable(out_idx);
+    const bool stage_pred = !dev_ptrs && weights != SKNNR_W_NONE && is_pageable(out_pred);
+    const bool staged = stage_in || stage_dist || stage_idx || stage_pred;
+    const bool check_finite = (flags & SKNNR_CHECK_FINITE) && !dev_ptrs && !excl;
     // device-resident queries have no copies to overlap: twice the chunk (fewer launches and cascade
     // tails; measured +1.8 %), while host buffers prefer the shorter pipeline ramp of the smaller one
-    const int64_t chunk = std::min<int64_t>(dev_ptrs ? 2 * g_opt.chunk_rows : g_opt.chunk_rows,
-                                            (n_q + 255) / 256 * 256);
+    int64_t chunk = dev_ptrs ? 2 * g_opt.chunk_rows : (staged ? std::min(g_opt.stage_rows, g_opt.chunk_rows) : g_opt.chunk_rows);
+    chunk = std::min<int64_t>(chunk, (n_q + 255) / 256 * 256);
+    const int n_slots = dev_ptrs ? 2 : (staged ? std::min<int>(4, (int)g_opt.host_slots) : (int)g_opt.host_slots);
     // Host buffers: the first chunk's H2D copy and the last chunk's D2H copy cannot overlap any
     // kernel, so the stream of chunks ramps up (1/4, 1/2, 1, ...) and down (..., 1/2, 1/4).
     const bool ramp = !dev_ptrs && n_q >= 4 * chunk && chunk % 1024 == 0;
@@ -689,21 +1015,18 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             else if (left > q4) rows = left - q4;
             else rows = left;
         }
-        // two slots alternate: the tail of chunk c (on its slot's tail stream) overlaps the first
+        // the slots alternate: the tail of chunk c (on its slot's tail stream) overlaps the first
         // stage of chunk c + 1 (other slot's buffers)
-        Slot &s = ix->slots[dev_ptrs ? (ci & 1) : (ci % (int)g_opt.host_slots)];
-        cudaStream_t saved = s.stream;
+        Slot &s = ix->slots[ci % n_slots];
+        StreamLoan loan(s, user_stream, dev_ptrs);
         if (dev_ptrs) {
-            s.stream = user_stream;
             if (s.tail_pending) {   // the slot's buffers are free once its previous tail is done
                 CK(cudaStreamWaitEvent(user_stream, s.ev_tail, 0));
                 s.tail_pending = false;
             }
         } else {
-            CK(cudaStreamSynchronize(s.stream));  // previous chunk on this slot is done
-            s.tail_pending = false;
-            ix->harvest(s);
-            // adaptive engine choice: if the TF32 filter cannot certify > 5 % of the rows
+            CK(ix->finish_slot(s));   // previous chunk on this slot is done, its results delivered
+            // adaptive engine choice: if the FP16 filter cannot certify > 5 % of the rows
             // (ill-conditioned features: huge norms relative to neighbour distances) the FP32
             // engine is the better first stage for this index
             if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen)
@@ -715,13 +1038,17 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             dX = (const unsigned char *)X + (size_t)r0 * ldx * esz;
         } else {
             CK(s.x.reserve((size_t)rows * cols * esz));
-            if (ldx == cols)
-                CK(cudaMemcpyAsync(s.x.p, (const unsigned char *)X + (size_t)r0 * ldx * esz,
-                                   (size_t)rows * cols * esz, cudaMemcpyHostToDevice, s.stream));
-            else
-                CK(cudaMemcpy2DAsync(s.x.p, (size_t)cols * esz,
-                                     (const unsigned char *)X + (size_t)r0 * ldx * esz, (size_t)ldx * esz,
-                                     (size_t)cols * esz, (size_t)rows, cudaMemcpyHostToDevice, s.stream));
+            const unsigned char *src = (const unsigned char *)X + (size_t)r0 * ldx * esz;
+            if (stage_in) {
+                CK(s.h_x.reserve((size_t)rows * cols * esz));
+                parallel_copy_rows(s.h_x.p, (size_t)cols * esz, src, (size_t)ldx * esz, (size_t)cols * esz, rows);
+                CK(cudaMemcpyAsync(s.x.p, s.h_x.p, (size_t)rows * cols * esz, cudaMemcpyHostToDevice, s.stream));
+            } else if (ldx == cols) {
+                CK(cudaMemcpyAsync(s.x.p, src, (size_t)rows * cols * esz, cudaMemcpyHostToDevice, s.stream));
+            } else {
+                CK(cudaMemcpy2DAsync(s.x.p, (size_t)cols * esz, src, (size_t)ldx * esz, (size_t)cols * esz,
+                                     (size_t)rows, cudaMemcpyHostToDevice, s.stream));
+            }
             ix->stats.h2d_bytes += rows * cols * (int64_t)esz;
             dX = s.x.p;
             dld = cols;
@@ -738,40 +1065,46 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             if (weights != SKNNR_W_NONE) { CK(s.o_pred.reserve((size_t)rows * ix->n_out)); o_pred = s.o_pred.p; }
         }
         rc = run_chunk(ix, s, dX, x_dtype == SKNNR_F32, dld, transformed, rows, row_offset + r0, k,
-                       flags, decimals, weights, o_dist, o_idx, o_pred);
-        if (rc != SKNNR_OK) { s.stream = saved; return rc; }
+                       flags, decimals, weights, o_dist, o_idx, o_pred, check_finite);
+        if (rc != SKNNR_OK) return rc;
         if (!dev_ptrs) {
             if (s.tail_pending) CK(cudaStreamWaitEvent(s.stream, s.ev_tail, 0));  // results complete
-            if (out_dist) {
-                CK(cudaMemcpyAsync(out_dist + r0 * k, o_dist, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, s.stream));
-                ix->stats.d2h_bytes += rows * k * 8;
-            }
-            if (out_idx) {
-                CK(cudaMemcpyAsync(out_idx + r0 * k, o_idx, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, s.stream));
-                ix->stats.d2h_bytes += rows * k * 8;
-            }
-            if (o_pred) {
-                CK(cudaMemcpyAsync(out_pred + r0 * ix->n_out, o_pred, (size_t)rows * ix->n_out * 8, cudaMemcpyDeviceToHost, s.stream));
-                ix->stats.d2h_bytes += rows * ix->n_out * 8;
-            }
+            // D2H straight into page-locked caller memory, else into the slot's staging buffer (the
+            // pool copies it out when the slot is next visited)
+            auto deliver = [&](void *dst, const void *src, size_t bytes, bool stage, PinBuf<unsigned char> &hb) -> cudaError_t {
+                void *to = dst;
+                if (stage) {
+                    cudaError_t e = hb.reserve(bytes);
+                    if (e != cudaSuccess) return e;
+                    to = hb.p;
+                    s.owed.push_back({dst, hb.p, bytes});
+                }
+                ix->stats.d2h_bytes += (int64_t)bytes;
+                return cudaMemcpyAsync(to, src, bytes, cudaMemcpyDeviceToHost, s.stream);
+            };
+            if (out_dist) CK(deliver(out_dist + r0 * k, o_dist, (size_t)rows * k * 8, stage_dist, s.h_dist));
+            if (out_idx) CK(deliver(out_idx + r0 * k, o_idx, (size_t)rows * k * 8, stage_idx, s.h_idx));
+            if (o_pred) CK(deliver(out_pred + r0 * ix->n_out, o_pred, (size_t)rows * ix->n_out * 8, stage_pred, s.h_pred));
+        } else {
+            CK(cudaEventRecord(s.ev_last, user_stream));
+            s.last_pending = true;
         }
-        s.stream = saved;
     }
     if (!dev_ptrs) {
-        for (auto &s : ix->slots) {
-            CK(cudaStreamSynchronize(s.stream));
-            s.tail_pending = false;
-            ix->harvest(s);
-        }
+        for (auto &s : ix->slots) CK(ix->finish_slot(s));
     } else {
         // results are complete on the caller's stream once both tails have joined it
         for (auto &s : ix->slots)
             if (s.tail_pending) {
                 CK(cudaStreamWaitEvent(user_stream, s.ev_tail, 0));
+                CK(cudaEventRecord(s.ev_last, user_stream));
                 s.tail_pending = false;
             }
     }
+    guard.ok = true;
     // a device-pointer call is not synchronised: its counters are harvested by the stats query
+    if (check_finite && ix->saw_nonfinite)
+        return fail(SKNNR_ENONFINITE, "Input X contains NaN or infinity.");
     return SKNNR_OK;
 }
 
@@ -798,10 +1131,12 @@ static int raster_impl(IX *ix, int d, const void *bands, int32_t x_dtype, int64_
     std::lock_guard<std::mutex> g(ix->lock);
     CK(cudaSetDevice(ix->device));
     const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
-    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; }
+    CallGuard guard(ix, nullptr);
+    for (auto &s : ix->slots) CK(ix->finish_slot(s));
+    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; s.flag_pending = false; }
     ix->stats = sknnr_stats{};
     if (n_valid_out) *n_valid_out = 0;
-    if (n_pix == 0) return SKNNR_OK;
+    if (n_pix == 0) { guard.ok = true; return SKNNR_OK; }
 
     const int64_t chunk = std::min<int64_t>(g_opt.chunk_rows, (n_pix + 1023) / 1024 * 1024);
     const int64_t n_blocks = (n_pix + chunk - 1) / chunk;
@@ -809,9 +1144,7 @@ static int raster_impl(IX *ix, int d, const void *bands, int32_t x_dtype, int64_
     auto stage_a = [&](int64_t b) -> int {
         Slot &s = ix->slots[b % IndexBase::kSlots];
         const int64_t p0 = b * chunk, rows = std::min(chunk, n_pix - p0);
-        CK(cudaStreamSynchronize(s.stream));   // the slot's previous block is complete
-        s.tail_pending = false;
-        ix->harvest(s);
+        CK(ix->finish_slot(s));   // the slot's previous block is complete
         CK(s.x.reserve((size_t)rows * d * esz));
         CK(s.r_pos.reserve((size_t)rows));
         CK(s.r_cnt.reserve((size_t)(rows + RASTER_GROUP - 1) / RASTER_GROUP + 2));
@@ -878,11 +1211,8 @@ static int raster_impl(IX *ix, int d, const void *bands, int32_t x_dtype, int64_
             ix->stats.kernel_launches++;
         }
     }
-    for (auto &s : ix->slots) {
-        CK(cudaStreamSynchronize(s.stream));
-        s.tail_pending = false;
-        ix->harvest(s);
-    }
+    for (auto &s : ix->slots) CK(ix->finish_slot(s));
+    guard.ok = true;
     if (n_valid_out) *n_valid_out = valid_before;
     return SKNNR_OK;
 }
@@ -923,7 +1253,7 @@ int sknnr_transform(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_q
                              (size_t)ldx * esz, (size_t)ix->d_in * esz, (size_t)rows,
                              cudaMemcpyHostToDevice, s.stream));
         CK(launch_project(s.x.p, x_dtype == SKNNR_F32, ix->d_in, rows, ix->d_in, ix->d_out, ix->dpad,
-                          ix->d_center, ix->d_scale, ix->d_proj, ix->d_mu, s.z64.p, nullptr, nullptr, 0, nullptr,
+                          ix->d_center, ix->d_scale, ix->d_proj, ix->d_mu, s.z64.p, nullptr, nullptr, 0, 1.0, nullptr, nullptr,
                           s.stream));
         CK(cudaMemcpyAsync(out_z + r0 * ix->d_out, s.z64.p, (size_t)rows * ix->d_out * 8,
                            cudaMemcpyDeviceToHost, s.stream));
@@ -1092,14 +1422,10 @@ static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *d
     ea.wsum = ix->wsum;
     ea.n_q = rows;
     ea.n_ref = (int)ix->n_ref;
-    ea.grid = (int)std::min<int64_t>(rows, (int64_t)ix->n_sm * 2);
-    if (!fast_u) {
-        CK(s.scratch.reserve((size_t)ix->n_sm * 2 * ix->n_ref));
-        ea.scratch = s.scratch.p;
-    }
+    ea.grid = ix->exact_ctas(rows);
     if (!fast_u && !fast_w) {
         if (g_opt.timing) CK(s.mark(st));
-        CK(launch_exact(ea, fp, st));
+        CK(ix->launch_exact_chained(ea, fp, kk, st));
         if (g_opt.timing) CK(s.mark(st));
         ix->stats.kernel_launches++;
         return SKNNR_OK;
@@ -1140,7 +1466,7 @@ static int run_hamming_chunk(sknnr_hamming_index *ix, Slot &s, const uint16_t *d
     // exhaustive float64 search of the uncertified rows
     ea.list = s.fb.p + 1;
     ea.count = s.fb.p;
-    CK(launch_exact(ea, fp, st));
+    CK(ix->launch_exact_chained(ea, fp, kk, st));
     CK(cudaMemcpyAsync(&s.h_fb[0], s.fb.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     s.h_fb[1] = 0;
     s.fb_pending = true;
@@ -1181,23 +1507,24 @@ static int hamming_kneighbors_impl(sknnr_hamming_index *ix, sknnr_forest *forest
     if (!forest && ldq < ix->n_trees) return fail(SKNNR_EINVAL, "ldq smaller than the number of trees");
     if (forest && ldq < forest->n_features) return fail(SKNNR_EINVAL, "ldx smaller than the number of features");
     const size_t xesz = x_dtype == SKNNR_F32 ? 4 : 8;
-    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; }
+    cudaStream_t user_stream = dev_ptrs ? (cudaStream_t)stream : nullptr;
+    CallGuard guard(ix, user_stream);
+    if (dev_ptrs) {
+        if (ix->slots[0].last_pending) CK(cudaStreamWaitEvent(user_stream, ix->slots[0].ev_last, 0));
+    } else {
+        for (auto &s : ix->slots) CK(ix->finish_slot(s));
+    }
+    for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; s.flag_pending = false; }
     ix->stats = sknnr_stats{};
     ix->stats.n_queries = n_q;
-    if (n_q == 0) return SKNNR_OK;
-    cudaStream_t user_stream = (cudaStream_t)stream;
+    if (n_q == 0) { guard.ok = true; return SKNNR_OK; }
     const int64_t chunk = std::min<int64_t>(g_opt.chunk_rows, (n_q + 255) / 256 * 256);
     int ci = 0;
     for (int64_t r0 = 0; r0 < n_q; r0 += chunk, ++ci) {
         const int64_t rows = std::min(chunk, n_q - r0);
         Slot &s = dev_ptrs ? ix->slots[0] : ix->slots[ci % IndexBase::kSlots];
-        cudaStream_t saved = s.stream;
-        if (dev_ptrs) {
-            s.stream = user_stream;
-        } else {
-            CK(cudaStreamSynchronize(s.stream));
-            ix->harvest(s);
-        }
+        StreamLoan loan(s, user_stream, dev_ptrs);
+        if (!dev_ptrs) CK(ix->finish_slot(s));
         const uint16_t *dq;
         int64_t dld = ldq;
         if (forest) {
@@ -1246,7 +1573,7 @@ static int hamming_kneighbors_impl(sknnr_hamming_index *ix, sknnr_forest *forest
         }
         rc = run_hamming_chunk(ix, s, dq, dld, rows, row_offset + r0, k, flags, decimals, weights,
                                o_dist, o_idx, o_pred);
-        if (rc != SKNNR_OK) { s.stream = saved; return rc; }
+        if (rc != SKNNR_OK) return rc;
         if (!dev_ptrs) {
             if (out_dist) {
                 CK(cudaMemcpyAsync(out_dist + r0 * k, o_dist, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, s.stream));
@@ -1260,15 +1587,14 @@ static int hamming_kneighbors_impl(sknnr_hamming_index *ix, sknnr_forest *forest
                 CK(cudaMemcpyAsync(out_pred + r0 * ix->n_out, o_pred, (size_t)rows * ix->n_out * 8, cudaMemcpyDeviceToHost, s.stream));
                 ix->stats.d2h_bytes += rows * ix->n_out * 8;
             }
-        }
-        s.stream = saved;
-    }
-    if (!dev_ptrs) {
-        for (auto &s : ix->slots) {
-            CK(cudaStreamSynchronize(s.stream));
-            ix->harvest(s);
+        } else {
+            CK(cudaEventRecord(s.ev_last, user_stream));
+            s.last_pending = true;
         }
     }
+    if (!dev_ptrs)
+        for (auto &s : ix->slots) CK(ix->finish_slot(s));
+    guard.ok = true;
     return SKNNR_OK;
 }
 

@@ -2,6 +2,7 @@
 // include/sknnr_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -12,8 +13,8 @@ struct FinishParams;
 // ---- project.cu: Z = ((X - center) / scale) @ proj  (S2, a1-a4) -----------------------
 // Writes Z as float64 rows (exact re-rank operand) and as the search kernel's query tile
 // image [n_qtiles][dpad][256] f32 = -2 * (Z - mu).
-// Also (optionally) the tensor-core engine's image [n_q/128][dpad/4+2][128][4] TF32 (two
-// consecutive 128-row operands form one CTA tile of the tensor kernel).
+// Also (optionally) the tensor-core engine's image [n_q/128][tc_kc][128][8] FP16 (two
+// consecutive 128-row operands form one CTA tile of the tensor kernel), scaled by tc_sigma.
 // Both images are zero-padded to a multiple of 1536 rows (padded_rows: every CTA tile size of
 // either engine - 256, 384, 512 - divides it).  n_rows_dev != null makes
 // the launch "compacted": only the first *n_rows_dev rows exist (device-side count).
@@ -21,7 +22,8 @@ inline long long padded_rows(long long n) { return (n + 1535) / 1536 * 1536; }
 cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long n_q, int d_in,
                            int d_out, int dpad, const double *center, const double *scale,
                            const double *proj, const double *mu, double *z64, float *qimg,
-                           float *qimg_tc, int tc_mt, const int *n_rows_dev, cudaStream_t st);
+                           __half *qimg_tc, int tc_kc, double tc_sigma, const int *n_rows_dev,
+                           int *nonfinite, cudaStream_t st);
 // z64c[i, :] = z64[list[i], :] for i < *count (rows whose certificate failed)
 cudaError_t launch_gather_rows(const double *z64, int d, const int *list, const int *count,
                                long long max_rows, double *z64c, cudaStream_t st);
@@ -34,16 +36,16 @@ cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, i
                                const int *n_rows_dev, cudaStream_t st);
 
 // ---- search_tc.cu (tcgen05 / TMEM engine) ------------------------------------------------
-// Two candidate-stream layouts: ns = 2 (two lists of 8 per query, k (+1) <= 8) and ns = 1 (one
-// list of 16).  cand_idx is [n_q][16], cand_thr [n_q][ns]; every reference outside a query's
+// Two candidate-stream layouts: ns = 2 (two lists of up to 7 per query, k (+1) <= 7) and ns = 1 (one
+// list of up to 15).  cand_idx is [n_q][16], cand_thr [n_q][ns]; every reference outside a query's
 // lists has an approximate score >= the minimum of its ns thresholds.
-size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns);
-int search_tc_pick_stages(int kc_tot);   // 0: the shape does not fit the engine
+size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns, int cape);
+int search_tc_pick_config(int kc_tot);   // ring stages | pending-queue depth << 8; 0: the shape does not fit
 int search_tc_seed_tiles(int n_rtiles, int seed_stride);
 extern int g_tc_debug;  // timing experiments: bit 0 = skip the hit path (wrong results)
 // seed_stride: one reference tile in seed_stride is pre-scanned to seed the thresholds (0 = off)
-cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int ns, int nstage, int seed_stride, int *cand_idx,
+cudaError_t launch_search_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles,
+                             long long n_q, int ns, int config, int seed_stride, int *cand_idx,
                              float *cand_thr, cudaStream_t st);
 
 // ---- refine.cu -------------------------------------------------------------------------
@@ -60,6 +62,8 @@ struct RefineArgs {
     int n_ref;
     double eps_s;           // relative error bound of the approximate score
     double r2max;           // max_j |ref_j - mu|^2
+    double thr_scale;       // cand_thr holds thresholds of scores scaled by 1 / thr_scale (tensor engine: sigma^2)
+    double qn_limit;        // rows with |q - mu|^2 >= qn_limit are never certified (FP16 range of the query image)
     int *fb_count;          // number of uncertified queries (device)
     int *fb_list;           // their row numbers (device, capacity n_q)
     const int *n_rows_dev;  // compacted launch: only the first *n_rows_dev rows exist
@@ -85,6 +89,7 @@ struct ExactArgs {
     const int *list;
     const int *count;
     double *scratch;        // [grid, n_ref]
+    double *big;            // [grid, 4 * (k + exclude_self)] - only read when k (+1) > 32
     int grid;
 };
 cudaError_t launch_exact(const ExactArgs &a, const FinishParams &fp, cudaStream_t st);

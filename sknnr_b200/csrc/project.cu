@@ -22,8 +22,9 @@ __global__ void __launch_bounds__(PROJ_THREADS)
 project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in, int d_out,
                int dpad, const double *__restrict__ center, const double *__restrict__ scale,
                const double *__restrict__ proj, const double *__restrict__ mu,
-               double *__restrict__ z64, float *__restrict__ qimg, float *__restrict__ qimg_tc,
-               int tc_mt, const int *__restrict__ n_rows_dev) {
+               double *__restrict__ z64, float *__restrict__ qimg, __half *__restrict__ qimg_tc,
+               int tc_kc, double tc_sigma, const int *__restrict__ n_rows_dev, int *__restrict__ nonfinite,
+               int xs_in_smem, int ps_in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int xs_ld = d_in | 1;  // odd row stride (in doubles): conflict-free row reads
     double *xs = reinterpret_cast<double *>(smem_raw);           // [128][xs_ld]
@@ -39,7 +40,10 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
     // coalesced load of the tile's rows, centring and scaling on the way in; (row, column) advance
     // incrementally (no integer division per element).  Without a projector the scaled value already
     // is z: it goes to z64 from here, where consecutive threads write consecutive addresses.
-    {
+    // (xs_in_smem == 0: more features than a 128-row tile can stage in shared memory - every thread
+    // then reads its own row from global memory in the loop below; ps_in_smem == 0: a projector too
+    // large for shared memory is read through the read-only cache instead)
+    if (xs_in_smem) {
         const int dr = PROJ_THREADS / d_in, dc = PROJ_THREADS - dr * d_in;
         int r = threadIdx.x / d_in, c = threadIdx.x - r * d_in;
         const bool z_here = !proj && z64 && d_out == d_in;
@@ -47,6 +51,8 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
             double v = 0.0;
             if (r < rows) {
                 v = (double)X[(q0 + r) * ldx + c];
+                // NaN / inf anywhere in the query block: the caller raises scikit-learn's ValueError
+                if (nonfinite && !isfinite(v)) *nonfinite = 1;
                 if (center) v -= center[c];
                 if (scale) v /= scale[c];
                 if (z_here) z64[(q0 + r) * d_out + c] = v;
@@ -60,32 +66,48 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
             }
         }
     }
-    const bool z_later = z64 && (proj || d_out != d_in);
-    if (proj)
+    const bool z_later = z64 && (proj || d_out != d_in || !xs_in_smem);
+    if (!xs_in_smem) ps = xs;   // nothing staged in front of the projector
+    if (proj && ps_in_smem)
         for (int e = threadIdx.x; e < d_in * d_out; e += PROJ_THREADS) ps[e] = proj[e];
     __syncthreads();
+    const double *pmat = ps_in_smem ? ps : proj;
 
     const int r = threadIdx.x;
     const double *xr = xs + r * xs_ld;
+    auto xval = [&](int i) -> double {
+        if (xs_in_smem) return xr[i];
+        double v = 0.0;
+        if (r < rows) {
+            v = (double)X[(q0 + r) * ldx + i];
+            if (nonfinite && !isfinite(v)) *nonfinite = 1;
+            if (center) v -= center[i];
+            if (scale) v /= scale[i];
+        }
+        return v;
+    };
     // row (q0 + r) lives in query tile (q0 + r) / QTILE at column (q0 + r) % QTILE
     const long long qrow = q0 + r;
     float *qt = qimg ? qimg + (size_t)(qrow / QTILE) * dpad * QTILE + (qrow % QTILE) : nullptr;
-    // tensor-core image: consecutive 128-row operands [chunk][row][4] TF32 (tc_mt of them form
-    // one CTA tile), with one extra K block (two chunks) that folds |r|^2 into the contraction:
-    // (1,1,1,0 | 0,0,0,0)
-    const int kc_tot = dpad / 4 + 2;
-    float4 *qc = nullptr;
+    // tensor-core image: consecutive 128-row operands [chunk][row][8] FP16 (two of them form one CTA
+    // tile of the tensor kernel): element k < d_out = -2 * sigma * (z_k - mu_k) (sigma = the index's
+    // power-of-two scale that brings the reference plots into FP16 range), elements d_out .. d_out+2
+    // = 1 (they meet the 3-way FP16 split of sigma^2 |r - mu|^2 on the reference side, which folds
+    // |r|^2 into the contraction), zero up to the padded depth 8 * tc_kc.
+    uint4 *qc = nullptr;
     if (qimg_tc) {
-        qc = reinterpret_cast<float4 *>(qimg_tc) + ((size_t)(qrow / TC_M) * kc_tot) * TC_M + (qrow % TC_M);
+        qc = reinterpret_cast<uint4 *>(qimg_tc) + ((size_t)(qrow / TC_M) * tc_kc) * TC_M + (qrow % TC_M);
     }
-    for (int k0 = 0; k0 < dpad; k0 += PROJ_KCHUNK) {
+    const int k_end = qc ? max(dpad, 8 * tc_kc) : dpad;
+    for (int k0 = 0; k0 < k_end; k0 += PROJ_KCHUNK) {
         double z[PROJ_KCHUNK];
 #pragma unroll
         for (int kk = 0; kk < PROJ_KCHUNK; ++kk) z[kk] = 0.0;
-        if (proj) {
+        if (k0 >= d_out) {
+        } else if (proj) {
             for (int i = 0; i < d_in; ++i) {
-                const double xv = xr[i];
-                const double *pr = ps + i * d_out + k0;
+                const double xv = xval(i);
+                const double *pr = pmat + (size_t)i * d_out + k0;
 #pragma unroll
                 for (int kk = 0; kk < PROJ_KCHUNK; ++kk)
                     if (k0 + kk < d_out) z[kk] += xv * pr[kk];
@@ -93,43 +115,51 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
         } else {
 #pragma unroll
             for (int kk = 0; kk < PROJ_KCHUNK; ++kk)
-                if (k0 + kk < d_out) z[kk] = xr[k0 + kk];
+                if (k0 + kk < d_out) z[kk] = xval(k0 + kk);
         }
-        float svs[PROJ_KCHUNK];
+        float hv[PROJ_KCHUNK];
 #pragma unroll
         for (int kk = 0; kk < PROJ_KCHUNK; ++kk) {
             const int k = k0 + kk;
-            float sv = 0.0f;
+            float sv = 0.0f, h = 0.0f;
             if (k < d_out && r < rows) {
                 if (z_later) z64[(q0 + r) * d_out + k] = z[kk];
-                sv = (float)(-2.0 * (z[kk] - mu[k]));
+                const double c2 = -2.0 * (z[kk] - mu[k]);
+                sv = (float)c2;
+                h = (float)(c2 * tc_sigma);
+            } else if (k >= d_out && k < d_out + 3 && r < rows) {
+                h = 1.0f;
             }
-            svs[kk] = sv;
-            if (qt) qt[(size_t)k * QTILE] = sv;
+            hv[kk] = h;
+            if (qt && k < dpad) qt[(size_t)k * QTILE] = sv;
         }
-        if (qc) {
-            qc[(size_t)(k0 / 4) * TC_M] =
-                make_float4(to_tf32(svs[0]), to_tf32(svs[1]), to_tf32(svs[2]), to_tf32(svs[3]));
-            qc[(size_t)(k0 / 4 + 1) * TC_M] =
-                make_float4(to_tf32(svs[4]), to_tf32(svs[5]), to_tf32(svs[6]), to_tf32(svs[7]));
+        if (qc && k0 < 8 * tc_kc) {
+            // round to nearest even; |h| >= 65520 becomes +-inf (such rows fail the certificate, refine.cu)
+            const __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
+            const __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<const uint32_t *>(&h01);
+            u.y = *reinterpret_cast<const uint32_t *>(&h23);
+            u.z = *reinterpret_cast<const uint32_t *>(&h45);
+            u.w = *reinterpret_cast<const uint32_t *>(&h67);
+            qc[(size_t)(k0 / 8) * TC_M] = u;
         }
-    }
-    if (qc) {
-        const float one = (r < rows) ? 1.0f : 0.0f;
-        qc[(size_t)(dpad / 4) * TC_M] = make_float4(one, one, one, 0.0f);
-        qc[(size_t)(dpad / 4 + 1) * TC_M] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
 cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long n_q, int d_in,
                            int d_out, int dpad, const double *center, const double *scale,
                            const double *proj, const double *mu, double *z64, float *qimg,
-                           float *qimg_tc, int tc_mt, const int *n_rows_dev, cudaStream_t st) {
-    (void)tc_mt;
+                           __half *qimg_tc, int tc_kc, double tc_sigma, const int *n_rows_dev,
+                           int *nonfinite, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
     const int xs_ld = d_in | 1;
-    const size_t smem = ((size_t)PROJ_THREADS * xs_ld + (proj ? (size_t)d_in * d_out : 0)) * 8;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    // what fits the 227 KB of shared memory is staged there: the 128-row tile first, then the projector
+    const size_t cap = 227 * 1024, xs_bytes = (size_t)PROJ_THREADS * xs_ld * 8;
+    const size_t ps_bytes = proj ? (size_t)d_in * d_out * 8 : 0;
+    const int xs_in_smem = xs_bytes <= cap ? 1 : 0;
+    const int ps_in_smem = (xs_in_smem ? xs_bytes : 0) + ps_bytes <= cap ? 1 : 0;
+    const size_t smem = (xs_in_smem ? xs_bytes : 0) + (ps_in_smem ? ps_bytes : 0);
     // cover whole query tiles so that padding columns of the last tile are zero-filled (every
     // CTA tile size of the search engines divides padded_rows, a multiple of PROJ_THREADS)
     const long long padded = padded_rows(n_q);
@@ -141,14 +171,14 @@ cudaError_t launch_project(const void *X, int x_is_f32, long long ldx, long long
         if (e != cudaSuccess) return e;
         project_kernel<float><<<(unsigned)grid, PROJ_THREADS, smem, st>>>(
             (const float *)X, ldx, n_q, d_in, d_out, dpad, center, scale, proj, mu, z64, qimg, qimg_tc,
-            tc_mt, n_rows_dev);
+            tc_kc, tc_sigma, n_rows_dev, nonfinite, xs_in_smem, ps_in_smem);
     } else {
         e = cudaFuncSetAttribute(project_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024);
         if (e != cudaSuccess) return e;
         project_kernel<double><<<(unsigned)grid, PROJ_THREADS, smem, st>>>(
             (const double *)X, ldx, n_q, d_in, d_out, dpad, center, scale, proj, mu, z64, qimg, qimg_tc,
-            tc_mt, n_rows_dev);
+            tc_kc, tc_sigma, n_rows_dev, nonfinite, xs_in_smem, ps_in_smem);
     }
     return cudaGetLastError();
 }

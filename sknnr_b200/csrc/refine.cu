@@ -152,8 +152,8 @@ refine_kernel(RefineArgs a, FinishParams fp) {
     if (thr == SK_INF_F) {
         ok = true;  // the list holds every reference
     } else {
-        const double bound = (double)thr + qn - a.eps_s * (qn + a.r2max);
-        ok = kth < bound;
+        const double bound = (double)thr * a.thr_scale + qn - a.eps_s * (qn + a.r2max);
+        ok = kth < bound && qn < a.qn_limit;
     }
     if (!ok) {
         if (lane == 0) {
@@ -213,7 +213,7 @@ refine2_kernel(RefineArgs a, FinishParams fp) {
     float thr = a.cand_thr[q * a.n_thr];
     for (int i = 1; i < a.n_thr; ++i) thr = fminf(thr, a.cand_thr[q * a.n_thr + i]);
     bool ok = true;                                 // thr = +inf: the list holds every reference
-    if (thr != SK_INF_F) ok = kth < (double)thr + qn - a.eps_s * (qn + a.r2max);
+    if (thr != SK_INF_F) ok = kth < (double)thr * a.thr_scale + qn - a.eps_s * (qn + a.r2max) && qn < a.qn_limit;
     if (live && !ok && hl == 0) {
         const int pos = atomicAdd(a.fb_count, 1);
         a.fb_list[pos] = a.row_map ? a.row_map[q] : (int)q;
@@ -264,17 +264,102 @@ __device__ __forceinline__ double exact_pair(const ExactArgs &a, long long q, in
     return num / a.wsum;
 }
 
+// finish_query for k (+1) > 32, by the whole CTA: the kk selected neighbours arrive ascending by
+// (distance, index) in sd / si (global scratch of the CTA, with room for the sort keys).  Same steps
+// as finish_query_w: self exclusion, sknnr's ordering key, outputs, weighted average.  Large k is
+// rare and rows reach this path one CTA at a time, so the sequential parts run on thread 0.
+__device__ void finish_query_block(const FinishParams &p, long long q, double *sd, int *si, double *key,
+                                   long long *sec, int kk) {
+    __shared__ double sh_denom;
+    __shared__ int sh_zero;
+    const long long row = p.row_offset + q;
+    if (threadIdx.x == 0) {
+        if (p.exclude_self) {
+            int pos = 0;
+            for (int c = 0; c < kk; ++c)
+                if ((long long)si[c] == row) { pos = c; break; }
+            for (int c = pos; c + 1 < kk; ++c) {
+                sd[c] = sd[c + 1];
+                si[c] = si[c + 1];
+            }
+        }
+        if (p.deterministic) {
+            const double scale = fmax(sd[p.k - 1], 1.0);
+            for (int c = 0; c < p.k; ++c) {
+                key[c] = rint((sd[c] / scale) * p.round_scale) / p.round_scale;
+                long long diff = (long long)si[c] - row;
+                if (diff < 0) diff = -diff;
+                sec[c] = (diff << 31) | (long long)si[c];
+            }
+            // the entries arrive sorted by distance and the key is monotone in it: an insertion sort
+            // only ever moves entries inside a run of equal rounded keys
+            for (int c = 1; c < p.k; ++c) {
+                const double kc = key[c], dc = sd[c];
+                const long long sc = sec[c];
+                int j = c - 1;
+                while (j >= 0 && (key[j] > kc || (key[j] == kc && sec[j] > sc))) {
+                    key[j + 1] = key[j];
+                    sec[j + 1] = sec[j];
+                    sd[j + 1] = sd[j];
+                    --j;
+                }
+                key[j + 1] = kc;
+                sec[j + 1] = sc;
+                sd[j + 1] = dc;
+            }
+            for (int c = 0; c < p.k; ++c) si[c] = (int)(sec[c] & 0x7fffffffLL);
+        }
+        int zero = 0;
+        double denom = 0.0;
+        if (p.weights == 2) {
+            for (int c = 0; c < p.k; ++c) zero |= (sd[c] == 0.0);
+            for (int c = 0; c < p.k; ++c) denom += zero ? (sd[c] == 0.0 ? 1.0 : 0.0) : 1.0 / sd[c];
+        }
+        sh_zero = zero;
+        sh_denom = denom;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.k; c += blockDim.x) {
+        if (p.out_dist) p.out_dist[q * p.k + c] = sd[c];
+        if (p.out_idx) p.out_idx[q * p.k + c] = (long long)si[c];
+    }
+    if (p.weights != 0 && p.out_pred != nullptr) {
+        for (int j = threadIdx.x; j < p.n_out; j += blockDim.x) {
+            double num = 0.0;
+            for (int c = 0; c < p.k; ++c) {
+                const int ic = si[c];
+                if (ic < 0 || ic >= p.n_ref) continue;
+                const double yv = p.y[(long long)ic * p.n_out + j];
+                if (p.weights == 1) {
+                    num += yv;
+                } else {
+                    const double w = sh_zero ? (sd[c] == 0.0 ? 1.0 : 0.0) : 1.0 / sd[c];
+                    num += yv * w;
+                }
+            }
+            p.out_pred[q * p.n_out + j] = (p.weights == 1) ? (num / (double)p.k) : (num / sh_denom);
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(EXACT_THREADS)
 exact_kernel(ExactArgs a, FinishParams fp) {
     __shared__ double red_d[EXACT_THREADS / 32];
     __shared__ int red_i[EXACT_THREADS / 32];
-    __shared__ double sel_d[MAXK];
-    __shared__ int sel_i[MAXK];
+    __shared__ double sel_d_s[MAXK];
+    __shared__ int sel_i_s[MAXK];
     // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
     const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long n_rows = a.list ? (long long)(*a.count) : a.n_q;
     double *scr = a.scratch + (size_t)blockIdx.x * a.n_ref;
     const int kk = fp.k + (fp.exclude_self ? 1 : 0);
+    // k (+1) > 32: the selection and the sort keys live in the CTA's slice of a.big
+    //   [kk] distances | [kk] keys | [kk] secondary keys | [kk] indices
+    const bool big = kk > MAXK;
+    double *bigp = big ? a.big + (size_t)blockIdx.x * 4 * kk : nullptr;
+    double *sel_d = big ? bigp : sel_d_s;
+    int *sel_i = big ? reinterpret_cast<int *>(bigp + 3 * (size_t)kk) : sel_i_s;
 
     for (long long it = blockIdx.x; it < n_rows; it += gridDim.x) {
         const long long q = a.list ? (long long)a.list[it] : it;
@@ -323,7 +408,12 @@ exact_kernel(ExactArgs a, FinishParams fp) {
             last_i = red_i[0];
             __syncthreads();
         }
-        if (warp == 0) {
+        if (big) {
+            if (a.metric == 0)
+                for (int c = threadIdx.x; c < kk; c += EXACT_THREADS) sel_d[c] = sqrt(sel_d[c]);
+            __syncthreads();
+            finish_query_block(fp, q, sel_d, sel_i, bigp + kk, reinterpret_cast<long long *>(bigp + 2 * (size_t)kk), kk);
+        } else if (warp == 0) {
             double d = (lane < kk) ? sel_d[lane] : SK_INF_D;
             const int id = (lane < kk) ? sel_i[lane] : 0x7fffffff;
             if (a.metric == 0) d = sqrt(d);

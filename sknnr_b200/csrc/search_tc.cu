@@ -65,8 +65,8 @@ constexpr int TC_GROUPS = 32;                   // seeding: group minima per que
 // MT M tiles (of 128 queries) per CTA; NS independent candidate streams per query: stream p owns
 // columns [p * 128 / NS, (p + 1) * 128 / NS) of every reference tile and has its own scanner
 // warps, candidate buffer and threshold; KCS candidates kept per stream, CAP buffer slots.
-template <int MT_, int NS_, int CAP_> struct TcCfg {
-    static constexpr int MT = MT_, NS = NS_, CAP = CAP_;
+template <int MT_, int NS_, int CAP_, int CAPE_> struct TcCfg {
+    static constexpr int MT = MT_, NS = NS_, CAP = CAP_, CAPE = CAPE_;
     static constexpr int QT = MT * TC_M;                  // queries per CTA
     static constexpr int EPI_WARPS = MT * 4 * NS;         // scanner warps: (stream, M tile, lane quarter)
     static constexpr int THREADS = (EPI_WARPS + MT + 1) * 32;  // + MT MMA issuer warps + TMA producer warp
@@ -78,6 +78,9 @@ template <int MT_, int NS_, int CAP_> struct TcCfg {
     static constexpr int SORT = CAP <= 16 ? 16 : 32;      // width of the register sorting network
     static_assert(CAP <= SORT && CAP % 2 == 0, "candidate buffer shape");
     static constexpr int CH = 4 / NS;                     // 32-column chunks a scanner warp reads per job
+    static constexpr int KCP = NS == 2 ? 8 : 0;           // published scores per thread (joint threshold)
+    // bytes of the selection state: candidates, pending queue (values + indices), published scores
+    static constexpr size_t SEL_BYTES = (size_t)LD * 4 * (2 * CAP + CAPE * 9 + KCP);
 };
 constexpr uint32_t TC_ROWB = 16;                // bytes of one row of one K chunk (4 TF32)
 static_assert(TC_N == 128, "epilogue assumes four 32-column chunks per tile");
@@ -118,13 +121,13 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
                      smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -177,9 +180,9 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                  : "memory");
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2,
-// B=TF32 [10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=F16 [7,10)=0,
+// B=F16 [10,13)=0, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                               ((uint32_t)(TC_M >> 4) << 24);
 
 // ---- thread-parallel register networks ---------------------------------------------------
@@ -220,20 +223,15 @@ __device__ __forceinline__ float tc_min32(const uint32_t (&r)[32]) {
     return fminf(fminf(b0, b1), fminf(b2, b3));
 }
 
-// diagnostics of the debug instantiation (tc_debug bit 3): chunk visits, events, hit lanes,
-// proactive compactions, cooperative fallbacks - printed by the last CTA
+// diagnostics of the debug instantiation (tc_debug bit 3): chunk visits, events, queued octets,
+// drains, compactions, dropped octets / values - printed by the last CTA
 __device__ unsigned long long g_tc_counters[8];
 
-struct ThrCnt {
+struct ThrPr {
     float thr;
-    int cnt;
+    uint32_t pr;
 };
 
-// Warp-wide compaction, thread-parallel: every thread reduces its OWN candidate buffer (column
-// cs0, slot stride LD) to the KC smallest scores and lowers its threshold to the
-// KC-th smallest.  Entries equal to the new threshold are kept only up to KC entries in total;
-// the dropped ones are >= the threshold, which is all the certificate needs.  Called by all 32
-// lanes (data-independent network, no divergence).
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -244,214 +242,207 @@ __device__ __forceinline__ int lds_s32(uint32_t addr) {
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// predicated dump of one octet of scores (+ the index of its first reference) into the calling
+// thread's next pending-queue entry: no branch, lanes whose predicate is off store nothing
+__device__ __forceinline__ void tc_dump8(bool on, uint32_t va, uint32_t ia, const float *w, int id) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %0, 0;\n"
+        "@p st.shared.v4.f32 [%1], {%3, %4, %5, %6};\n"
+        "@p st.shared.v4.f32 [%1+16], {%7, %8, %9, %10};\n"
+        "@p st.shared.b32 [%2], %11;\n"
+        "}\n" ::"r"((uint32_t)on),
+        "r"(va), "r"(ia), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]), "f"(w[4]), "f"(w[5]), "f"(w[6]),
+        "f"(w[7]), "r"(id)
+        : "memory");
+}
 
-// (the slow paths take 32-bit shared-memory addresses, not generic pointers: `cs0` = address of
-// slot 0 of the calling thread's score column; slot j lies j * LD * 4 bytes further and the index
-// column CAP * LD * 4 bytes behind the score column - nothing else has to stay live in the scanner
-// loop on their behalf)
-template <int KC, int CAP, int LD>
-__device__ __noinline__ ThrCnt tc_compact_all(uint32_t cs0, float thr, int cnt) {
+
+// J-th smallest score of the union of two ascending lists of KC scores each (1 <= J <= 2 KC): the
+// minimum over the splits i + j = J (i from `a`, j from `b`) of max(a[i - 1], b[j - 1]).
+template <int KC, int J, int NA>
+__device__ __forceinline__ float tc_union_rank(const float (&a)[NA], const float (&b)[KC]) {
+    static_assert(J >= 1 && J <= 2 * KC && NA >= KC, "rank out of range");
+    float best = SK_INF_F;
+#pragma unroll
+    for (int i = 0; i <= KC; ++i) {
+        const int j = J - i;
+        if (j < 0 || j > KC) continue;
+        float m;
+        if (i == 0) m = b[j - 1];
+        else if (j == 0) m = a[i - 1];
+        else m = fmaxf(a[i - 1], b[j - 1]);
+        best = fminf(best, m);
+    }
+    return best;
+}
+
+// rank (in the union of both streams' lists) of the score the joint threshold is set to: the k-th
+// neighbour must clear it by the certificate's error margin, so it sits a few ranks above k
+#ifndef SK_TC_JOINT
+#define SK_TC_JOINT 12
+#endif
+// parked octets of one lane that make the warp resolve its queues (room for CAPE - SK_TC_TRIG more)
+#ifndef SK_TC_TRIG
+#define SK_TC_TRIG 2
+#endif
+// > 0: the queues are resolved every SK_TC_DRAIN_EVERY jobs by all warps together instead
+#ifndef SK_TC_DRAIN_EVERY
+#define SK_TC_DRAIN_EVERY 0
+#endif
+
+// ---- per-thread selection state (thread <-> (query, stream) = column `col` of every array) ----
+//   candidates  buf_s / buf_i [CAP][LD]: unsorted (score, index) entries; the count lives in
+//               pr = 4 * col + count * LD * 4 (LD * 4 is a power of two above 4 * col), the offset of
+//               the next free score slot
+//   pending     pq_v [CAPE][LD][8] f32 + pq_i [CAPE][LD]: octets of raw scores that contained a value
+//               below the threshold, parked by the fast path and resolved later by the whole warp at
+//               once (tc_drain); count in pqo = 32 * col + count * LD * 32
+//   published   pub [KCP][LD]: the thread's KCP best scores (sorted) at its last compaction; the
+//               partner stream of the same query reads them to form a joint threshold
+// Dropping is always safe: a score that cannot be stored (queue or list full) lowers the thread's
+// threshold to that score instead - every reference outside the list then still has a score >=
+// the threshold, which is all the certificate needs (the row merely becomes harder to certify).
+
+// Warp-wide compaction, thread-parallel: every thread reduces its OWN candidate column to the
+// entries strictly below t = its KC-th smallest score and lowers its threshold to t (fewer than
+// KC entries: t = +inf, nothing changes).  NS = 2: the sorted best scores are published and the
+// threshold is further lowered to the KC-th smallest score of the union with the partner
+// stream's published list (stale or torn reads only see older = larger scores: still an upper
+// bound of the query's KC-th best).  Called by all 32 lanes.
+template <int KC, int CAP, int LD, int NS, int J>
+__device__ __forceinline__ ThrPr tc_compact(uint32_t bs0, uint32_t pub0, uint32_t c4, float thr, uint32_t pr) {
     static_assert(KC < CAP, "the buffer needs slack above KC");
     constexpr int SORT = CAP <= 16 ? 16 : 32;
     constexpr uint32_t IOFF = CAP * LD * 4, STEP = LD * 4;
-    __syncwarp();
+    const uint32_t cs0 = bs0 + c4;
+    const int cnt = (int)(pr / STEP);
     float s[SORT];
 #pragma unroll
     for (int j = 0; j < SORT; ++j) s[j] = (j < CAP && j < cnt) ? lds_f32(cs0 + j * STEP) : SK_INF_F;
     sort_regs<SORT>(s);
-    const float t = s[KC - 1];  // +inf while the buffer holds fewer than KC entries
-    int n_less = 0;
+    float t = s[KC - 1];
+    if constexpr (NS == 2) {
+        static_assert(LD == 512 || NS != 2, "partner column = column ^ 256");
+        const uint32_t mine = pub0 + c4, other = pub0 + (c4 ^ 1024u);
+        float o[KC];
 #pragma unroll
-    for (int j = 0; j < KC - 1; ++j) n_less += (s[j] < t) ? 1 : 0;
-    int quota = KC - n_less;    // entries equal to t that may stay
+        for (int i = 0; i < KC; ++i) {
+            st_shared_b32(mine + i * STEP, __float_as_uint(s[i]));
+            o[i] = lds_f32(other + i * STEP);
+        }
+        const float joint = tc_union_rank<KC, J, SORT>(s, o);
+        t = fminf(t, joint);
+    }
+    t = fminf(t, thr);
     uint32_t w = cs0;
-    int nw = 0;
 #pragma unroll 4
     for (int j = 0; j < CAP; ++j) {
         const float v = lds_f32(cs0 + j * STEP);
         const int id = lds_s32(cs0 + IOFF + j * STEP);
-        const bool valid = j < cnt;
-        const bool lt = valid && (v < t);
-        const bool eq = valid && (v == t) && quota > 0;
-        if (eq) --quota;
-        if (lt || eq) {
+        if (j < cnt && v < t) {
             st_shared_b32(w, __float_as_uint(v));
             st_shared_b32(w + IOFF, (uint32_t)id);
             w += STEP;
-            ++nw;
         }
     }
-    __syncwarp();
-    ThrCnt out;
-    out.thr = fminf(thr, t);
-    out.cnt = nw;
+    ThrPr out;
+    out.thr = t;
+    out.pr = w - bs0;
     return out;
 }
 
-// Cooperative (slow, always safe) hit path for ONE lane L whose 32 scores (references idb ..
-// idb+31) have been published to the warp's scratch line: the warp re-tests them one score per
-// lane and appends the survivors to lane L's candidate buffer, compacting the warp's buffers
-// whenever it would overflow.  Used when the in-lane path below ran out of buffer slots.
-template <int KC, int CAP, int LD>
-__device__ __noinline__ ThrCnt tc_process_coop(int L, int idb, uint32_t cs0, uint32_t scratch_a, int lane,
-                                               float thr, int cnt) {
-    constexpr uint32_t IOFF = CAP * LD * 4, STEP = LD * 4;
-    const float x = lds_f32(scratch_a + 4u * lane);   // score of lane L's query vs reference idb+lane
-    float thrL = __shfl_sync(SK_FULL, thr, L);
-    int cntL = __shfl_sync(SK_FULL, cnt, L);
-    unsigned pending = __ballot_sync(SK_FULL, x < thrL);
-    const uint32_t csL = cs0 + 4u * (uint32_t)(L - lane);   // lane L's column
-    while (pending) {
-        unsigned take = pending;
-        if (cntL + __popc(pending) > CAP) {
-            if (cntL > KC) {
-                if (lane == L) cnt = cntL;  // entries appended earlier in this loop
-                const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, cnt);
-                thr = tc.thr;
-                cnt = tc.cnt;
-                thrL = __shfl_sync(SK_FULL, thr, L);
-                cntL = __shfl_sync(SK_FULL, cnt, L);
-                pending &= __ballot_sync(SK_FULL, x < thrL);
-                continue;
-            }
-            // at most KC entries held but more hits than free slots: lowest hits first
-            const int room = CAP - cntL;
-            while (__popc(take) > room) take &= ~(0x80000000u >> __clz(take));
+// Resolve the warp's pending octets, all lanes at once: iteration `it` takes every lane's it-th
+// parked octet (lanes with fewer are passengers) and appends its values below the lane's
+// threshold to the lane's candidate column, branch-free (every value is stored at the next free
+// slot, the slot only advances for the values that qualify).  Compacts when a lane is down to
+// its last two free slots; a third qualifying value of one octet is dropped (see above).
+template <int KC, int CAP, int LD, int CAPE, int NS, int J, bool DBG>
+__device__ __noinline__ ThrPr tc_drain(uint32_t bs0, uint32_t pqv0, uint32_t pqi0, uint32_t pub0, uint32_t c4,
+                                       float thr, uint32_t pr, uint32_t pqo, int dbg) {
+    constexpr uint32_t IOFF = CAP * LD * 4, STEP = LD * 4, ES = LD * 32;
+    constexpr uint32_t FULL = (CAP - 2) * STEP, LAST = (CAP - 1) * STEP;
+    const int n_me = (int)(pqo / ES);
+    const int n_it = __reduce_max_sync(SK_FULL, n_me);
+    for (int it = 0; it < n_it; ++it) {   // warp-uniform
+        const bool act = it < n_me;
+        if (__any_sync(SK_FULL, act && pr >= FULL)) {
+            if (DBG && (dbg & 8) && (threadIdx.x & 31) == 0) atomicAdd(&g_tc_counters[4], 1ull);
+            const ThrPr c = tc_compact<KC, CAP, LD, NS, J>(bs0, pub0, c4, thr, pr);
+            thr = c.thr;
+            pr = c.pr;
         }
-        if ((take >> lane) & 1u) {
-            const int slot = cntL + __popc(take & ((1u << lane) - 1u));
-            st_shared_b32(csL + slot * STEP, __float_as_uint(x));
-            st_shared_b32(csL + IOFF + slot * STEP, (uint32_t)(idb + lane));
-        }
-        cntL += __popc(take);
-        pending &= ~take;
-    }
-    if (lane == L) cnt = cntL;
-    ThrCnt out;
-    out.thr = thr;
-    out.cnt = cnt;
-    return out;
-}
-
-// in-lane append of the values of v[0..N) below thr (references id0 ..), N <= 3: every value is
-// stored at the lane's next free slot and the slot only advances for the values that qualify, so
-// there is no branch per value.  The caller guarantees N free slots.
-// `ps` = shared-memory address of the lane's next free score slot (the index slot lies IOFF bytes
-// further); see the comment above for the protocol
-template <int N, int LD, int IOFF>
-__device__ __forceinline__ void tc_leaf(const float *v, int id0, float thr, uint32_t bs0, uint32_t &pr) {
-    // (three independent store groups: a "minimum first, others only if the median qualifies"
-    // variant has fewer instructions but a longer dependent chain and measured 8 % slower)
+        const uint32_t va = pqv0 + 8u * c4 + (uint32_t)it * ES;
+        const float4 x = lds_f32x4(va), y = lds_f32x4(va + 16);
+        const int id = lds_s32(pqi0 + c4 + (uint32_t)it * STEP);
+        const float vv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-        st_shared_b32(bs0 + pr, __float_as_uint(v[j]));
-        st_shared_b32(bs0 + pr + IOFF, (uint32_t)(id0 + j));
-        if (v[j] < thr) pr += LD * 4;
+        for (int j = 0; j < 8; ++j) {
+            st_shared_b32(bs0 + pr, __float_as_uint(vv[j]));
+            st_shared_b32(bs0 + pr + IOFF, (uint32_t)(id + j));
+            const bool q = act && vv[j] < thr;
+            if (q) {
+                if (pr < LAST) pr += STEP;
+                else thr = fminf(thr, vv[j]);
+            }
+        }
     }
+    ThrPr out;
+    out.thr = thr;
+    out.pr = pr;
+    return out;
 }
 
 // One 32-column chunk of the main pass.  `r` holds this thread's scores against references
-// idb .. idb+31.  Fast path: min3 tree + one vote.  Hit path, in the hit lanes only and without
-// any cross-lane traffic: the tree's intermediate minima (four groups of <= 9 values) locate the
-// values below the threshold, which the lane appends to its own candidate buffer column.
-// `cs0` = shared-memory address of slot 0 of this thread's candidate column.
-// The thread's candidate count lives in `pr`, the offset of its next free score slot from the
-// start `bs0` of the score buffer: pr = 4 * column + count * LD * 4 with LD * 4 a power of two above
-// 4 * column, so "fewer than three free slots" is one compare of pr with a constant and the hit
-// path only ever bumps that offset.
-template <int KC, int CAP, int LD, int EPI_WARPS, bool DBG>
-__device__ __forceinline__ void tc_process(const uint32_t (&r)[32], int idb, uint32_t bs0, int lane, float &thr,
-                                           uint32_t &pr, int dbg) {
-    constexpr uint32_t STEP = LD * 4, IOFF = CAP * LD * 4, FULL = (CAP - 2) * STEP;
-    static_assert((STEP & (STEP - 1)) == 0, "slot stride must be a power of two");
+// idb .. idb+31.  Fast path: min3 tree over four octets + one vote.  On a hit anywhere in the warp
+// every lane parks the octets whose minimum beats its threshold (predicated stores, no branch, no
+// cross-lane traffic); what the values are is sorted out later by tc_drain.
+template <int LD, int CAPE, bool DBG>
+__device__ __forceinline__ void tc_chunk(const uint32_t (&r)[32], int idb, uint32_t pqv0, uint32_t pqi0, float &thr,
+                                         uint32_t &pqo, int dbg) {
+    constexpr uint32_t ES = LD * 32, PQ_END = CAPE * ES;
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    // group minima b0..b3 over v[0..9), v[9..18), v[18..27), v[27..32).  The fast path reduces each
-    // group through STRIDED triples (v[g], v[g+3], v[g+6]); the hit path below re-derives the
-    // minima of the CONTIGUOUS triples it descends into, so that those eleven values are not kept
-    // live (and spilled) across the fast path.
-    float b[4];
+    float g[4];
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
-        const float *w = v + 9 * g;
-        b[g] = fminf(fminf(fminf(fminf(w[0], w[3]), w[6]), fminf(fminf(w[1], w[4]), w[7])),
-                     fminf(fminf(w[2], w[5]), w[8]));
+    for (int o = 0; o < 4; ++o) {
+        const float *w = v + 8 * o;
+        g[o] = fminf(fminf(fminf(fminf(w[0], w[1]), w[2]), fminf(fminf(w[3], w[4]), w[5])), fminf(w[6], w[7]));
     }
-    b[3] = fminf(fminf(fminf(v[27], v[29]), v[31]), fminf(v[28], v[30]));
-    const float b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3];
-    const float m = fminf(fminf(b0, b1), fminf(b2, b3));
-    bool hit = m < thr;
-    unsigned hits = 1u;
+    const float m = fminf(fminf(fminf(g[0], g[1]), g[2]), g[3]);
+    const bool hit = m < thr;
     if constexpr (DBG) {
-        hits = __ballot_sync(SK_FULL, hit);
-        if ((dbg & 8) && lane == 0) {
+        const unsigned hits = __ballot_sync(SK_FULL, hit);
+        if ((dbg & 8) && (threadIdx.x & 31) == 0) {
             atomicAdd(&g_tc_counters[0], 1ull);
             if (hits) atomicAdd(&g_tc_counters[1], 1ull);
-            atomicAdd(&g_tc_counters[2], (unsigned long long)__popc(hits));
         }
         if (hits == 0u) return;
+        if (dbg & 1) return;   // timing experiment: skip the hit path (results are wrong)
     } else {
         if (!__any_sync(SK_FULL, hit)) return;   // vote straight into a predicate
     }
-    if (DBG && (dbg & 1)) {  // timing experiment: count the hits, skip the hit path (results are wrong)
-        pr = (pr & (STEP - 1)) + (((pr / STEP) + __popc(hits)) & 7) * STEP;
-        return;
-    }
-    // a triple is appended only while three slots are free (pr < FULL); keep room for the usual one
-    // or two appends - compaction also refreshes the thresholds
-    if (__any_sync(SK_FULL, hit && pr >= FULL)) {
-        if (DBG && (dbg & 8) && lane == 0) atomicAdd(&g_tc_counters[3], 1ull);
-        const uint32_t c4 = pr & (STEP - 1);   // 4 * column
-        const ThrCnt tc = tc_compact_all<KC, CAP, LD>(bs0 + c4, thr, (int)(pr / STEP));
-        thr = tc.thr;
-        pr = c4 + (uint32_t)tc.cnt * STEP;
-        hit = m < thr;
-    }
-    const uint32_t pr0 = pr;
-    if (hit) {
-        // descend the tree: group of <= 9 values -> triple -> values.  Out of room: bit 0 of pr is set
-        // (offsets are multiples of 4) and pr >= FULL stays true
-#define SK_TC_TRIPLE(I, N)                                                      \
-        if (fminf(fminf(v[3 * (I)], v[3 * (I) + 1]), v[3 * (I) + ((N) == 3 ? 2 : 1)]) < thr) { \
-            if (pr >= FULL) pr |= 1u;                                           \
-            else tc_leaf<N, LD, IOFF>(v + 3 * (I), idb + 3 * (I), thr, bs0, pr); \
-        }
-        if (b0 < thr) { SK_TC_TRIPLE(0, 3) SK_TC_TRIPLE(1, 3) SK_TC_TRIPLE(2, 3) }
-        if (b1 < thr) { SK_TC_TRIPLE(3, 3) SK_TC_TRIPLE(4, 3) SK_TC_TRIPLE(5, 3) }
-        if (b2 < thr) { SK_TC_TRIPLE(6, 3) SK_TC_TRIPLE(7, 3) SK_TC_TRIPLE(8, 3) }
-        if (b3 < thr) { SK_TC_TRIPLE(9, 3) SK_TC_TRIPLE(10, 2) }
-#undef SK_TC_TRIPLE
-    }
-    // rare: a lane found more values than it had free slots -> undo its appends and redo the
-    // chunk for it through the cooperative path (which compacts as often as needed)
-    unsigned ovf = __ballot_sync(SK_FULL, (pr & 1u) != 0u);
-    if (ovf) {
-        if (DBG && (dbg & 8) && lane == 0) atomicAdd(&g_tc_counters[4], (unsigned long long)__popc(ovf));
-        if (pr & 1u) pr = pr0;
-        float thr2 = thr;
-        int cnt = (int)(pr / STEP);
-        const uint32_t c4 = pr & (STEP - 1), cs0 = bs0 + c4;
-        // the warp's scratch line lies in front of the candidate buffers: [EPI_WARPS][32] floats
-        const uint32_t scratch_a = bs0 - (uint32_t)EPI_WARPS * 128u + (c4 >> 7) * 128u;
-        while (ovf) {  // warp-uniform
-            const int L = __ffs(ovf) - 1;
-            ovf &= ovf - 1;
-            __syncwarp();
-            if (lane == L) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) st_shared_b32(scratch_a + 4u * i, __float_as_uint(v[i]));
-            }
-            __syncwarp();
-            const ThrCnt tc = tc_process_coop<KC, CAP, LD>(L, idb, cs0, scratch_a, lane, thr2, cnt);
-            thr2 = tc.thr;
-            cnt = tc.cnt;
-        }
-        thr = thr2;
-        pr = c4 + (uint32_t)cnt * STEP;
+    for (int o = 0; o < 4; ++o) {
+        const bool p = g[o] < thr;
+        const bool room = pqo < PQ_END;
+        tc_dump8(p && room, pqv0 + pqo, pqi0 + (pqo >> 3), v + 8 * o, idb + 8 * o);
+        if (p && !room) thr = fminf(thr, g[o]);
+        if (p && room) pqo += ES;
+        if (DBG && (dbg & 8) && p) atomicAdd(&g_tc_counters[room ? 2 : 5], 1ull);
     }
 }
 
@@ -487,22 +478,25 @@ __device__ __forceinline__ void tc_epi_job(uint32_t (&R)[CH][32], uint32_t tcol,
 
 // (register budget: the register file is allocated per 4 warps, so the 18-warp dual-stream CTA
 // gets 65536 / (20 * 32) = 102 -> 96 registers per thread and the 10-warp one 168)
-template <int KC, int MT, int NS, int CAP, bool DBG>
-__global__ void __launch_bounds__(TcCfg<MT, NS, CAP>::THREADS, 1)
-search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int kc_tot,
+template <int KC, int MT, int NS, int CAP, int CAPE, int J, bool DBG>
+__global__ void __launch_bounds__(TcCfg<MT, NS, CAP, CAPE>::THREADS, 1)
+search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rimg, int kc_tot,
                  int n_rtiles, int nstage, int n_seed, int seed_stride, long long n_q,
                  int *__restrict__ cand_idx, float *__restrict__ cand_thr, int dbg) {
-    using Cfg = TcCfg<MT, NS, CAP>;
-    constexpr int LD = Cfg::LD, EPI_WARPS = Cfg::EPI_WARPS;
+    using Cfg = TcCfg<MT, NS, CAP, CAPE>;
+    constexpr int LD = Cfg::LD, EPI_WARPS = Cfg::EPI_WARPS, KCP = Cfg::KCP;
+    static_assert(KCP == 0 || KCP == KC, "the joint threshold uses the KC best scores of both streams");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t a_bytes = (uint32_t)kc_tot * TC_M * TC_ROWB;  // one 128-query operand image
     const uint32_t b_bytes = (uint32_t)kc_tot * TC_N * TC_ROWB;  // one 128-plot operand image
     unsigned char *Qs = smem_raw;                                // MT operand images
     unsigned char *Rs = Qs + MT * a_bytes;                       // nstage operand images
-    float *scratch_all = reinterpret_cast<float *>(Rs + (size_t)nstage * b_bytes);  // [warps][32]
-    float *buf_s = scratch_all + EPI_WARPS * 32;
+    float *buf_s = reinterpret_cast<float *>(Rs + (size_t)nstage * b_bytes);   // candidates [CAP][LD]
     int *buf_i = reinterpret_cast<int *>(buf_s + CAP * LD);
-    uint64_t *full = reinterpret_cast<uint64_t *>(buf_i + CAP * LD);  // (CAP * LD * 4) % 8 == 0
+    float *pq_v = reinterpret_cast<float *>(buf_i + CAP * LD);                 // pending [CAPE][LD][8]
+    int *pq_i = reinterpret_cast<int *>(pq_v + CAPE * LD * 8);                 //         [CAPE][LD]
+    float *pub = reinterpret_cast<float *>(pq_i + CAPE * LD);                  // published [KCP][LD]
+    uint64_t *full = reinterpret_cast<uint64_t *>(pub + KCP * LD);             // (8-byte aligned: LD * 4 % 8 == 0)
     uint64_t *empty = full + nstage;
     uint64_t *afull = empty + nstage;       // [4] accumulator slot ready
     uint64_t *aempty = afull + TC_SLOTS;    // [4] accumulator slot drained
@@ -530,7 +524,7 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const long long qtile = blockIdx.x;
-    const int ksteps = kc_tot >> 1;  // MMA K = 8 TF32 = two 16-byte chunks
+    const int ksteps = kc_tot >> 1;  // MMA K = 16 FP16 = two 16-byte chunks
     const int n_seq = n_seed + n_rtiles;  // sampled tiles (seeding), then every tile
 
     if (warp == EPI_WARPS + MT) {
@@ -591,20 +585,20 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             if (elect_one()) {
                 if (DBG && (dbg & 16)) {   // timing experiment: the job's MMAs issued twice (same result)
                     uint32_t a2 = a_lo0, b2 = b_lo_s;
-                    tc_mma_tf32(d_tmem, desc_hi | a2, desc_hi | b2, TC_IDESC, 0u);
+                    tc_mma_f16(d_tmem, desc_hi | a2, desc_hi | b2, TC_IDESC, 0u);
                     for (int ks = 1; ks < ksteps; ++ks) {
                         a2 += a_kstep;
                         b2 += b_kstep;
-                        tc_mma_tf32(d_tmem, desc_hi | a2, desc_hi | b2, TC_IDESC, 1u);
+                        tc_mma_f16(d_tmem, desc_hi | a2, desc_hi | b2, TC_IDESC, 1u);
                     }
                 }
                 uint32_t a_lo = a_lo0, b_lo = b_lo_s;
-                tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 0u);
+                tc_mma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 0u);
 #pragma unroll 4
                 for (int ks = 1; ks < ksteps; ++ks) {
                     a_lo += a_kstep;
                     b_lo += b_kstep;
-                    tc_mma_tf32(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 1u);
+                    tc_mma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, 1u);
                 }
                 tc_commit(&afull[sl]);   // accumulators of job j complete
                 tc_commit(&empty[s]);    // one of the MT arrivals that free the smem slot
@@ -631,7 +625,17 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
         uint32_t R[CH][32];
         int t = 0;                            // position in the tile sequence; this warp's job = t * MT + h
         const uint32_t afull_a0 = smem_u32(afull), aempty_a0 = smem_u32(aempty);
-        const uint32_t cs0 = smem_u32(buf_s + col);
+
+        // shared-window addresses of the selection arrays, derived from the dynamic array's own shared
+        // address (no generic pointer round trip): uniform registers
+        const uint32_t bs0 = smem_u32(smem_raw) + MT * a_bytes + (uint32_t)nstage * b_bytes;
+        const uint32_t pqv0 = bs0 + 2u * CAP * LD * 4u, pqi0 = pqv0 + (uint32_t)CAPE * LD * 32u;
+        const uint32_t pub0 = pqi0 + (uint32_t)CAPE * LD * 4u;
+        const uint32_t c4 = 4u * (uint32_t)col;
+        if constexpr (KCP > 0) {
+#pragma unroll
+            for (int i = 0; i < KCP; ++i) st_shared_b32(pub0 + c4 + i * (LD * 4), __float_as_uint(SK_INF_F));
+        }
 
         // ---- seeding pass: group minima over the sampled tiles ----
         // (the 32 running minima live in the still unused candidate buffer column: slots of
@@ -657,31 +661,68 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
             for (int g = 0; g < TC_GROUPS; ++g) gm[g] = gcol[g * LD];
             sort_regs<TC_GROUPS>(gm);
             thr = gm[KC - 1];
+            if constexpr (KCP > 0) {
+                // joint seed: the KC-th smallest group minimum of BOTH streams of the query.  The two
+                // warps of a (M tile, lane quarter) pair meet on a named barrier so that each sees
+                // the other's minima.
+#pragma unroll
+                for (int i = 0; i < KC; ++i) st_shared_b32(pub0 + c4 + i * (LD * 4), __float_as_uint(gm[i]));
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & (MT * 4 - 1))) : "memory");
+                float o[KC];
+#pragma unroll
+                for (int i = 0; i < KC; ++i) o[i] = lds_f32(pub0 + (c4 ^ 1024u) + i * (LD * 4));
+                const float joint = tc_union_rank<KC, J, TC_GROUPS>(gm, o);
+                thr = fminf(thr, joint);
+            }
         }
 
         // ---- main pass ----
-        // shared-window address of buf_s, derived from the array's own shared address (no generic
-        // pointer round trip): uniform
-        const uint32_t bs0 = smem_u32(smem_raw) + MT * a_bytes + (uint32_t)nstage * b_bytes + EPI_WARPS * 128u;
-        uint32_t pr = 4u * (uint32_t)col;       // offset of this thread's next free slot (4 * col + count * LD * 4)
+        constexpr uint32_t ES = LD * 32;
+        uint32_t pr = c4;            // offset of this thread's next free candidate slot (4 * col + count * LD * 4)
+        uint32_t pqo = 8u * c4;      // offset of its next free pending-queue entry (32 * col + count * LD * 32)
+        int since_drain = 0;
         for (; t < n_seq; ++t) {
             const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
             const int idb = (t - n_seed) * TC_N + p * CH * 32;   // warp-uniform, like t and p
             tc_epi_job<CH>(R, tlane + (uint32_t)(sl * TC_N), afull_a0 + 8u * sl, (uint32_t)((j >> 2) & 1),
-                               aempty_a0 + 8u * sl, lane,
+                           aempty_a0 + 8u * sl, lane,
                            [&](const uint32_t (&r)[32], auto ic) {
                                constexpr int c = decltype(ic)::value;
-                               tc_process<KC, CAP, LD, EPI_WARPS, DBG>(r, idb + c * 32, bs0, lane, thr, pr, dbg);
+                               tc_chunk<LD, CAPE, DBG>(r, idb + c * 32, pqv0, pqi0, thr, pqo, dbg);
                            });
+            // resolve the parked octets once a lane has two or more of them (CAPE - 2 entries of room
+            // are left for the next job; beyond that an octet is dropped, which is safe)
+#if SK_TC_DRAIN_EVERY > 0
+            // every scanner warp of the CTA resolves its queues in the SAME jobs: a slot is only handed
+            // back when all eight warps of its M tile have read it, so a long operation costs the
+            // whole M tile its duration - once per period when the warps take it together, almost
+            // every job when each warp takes it whenever its own queues fill up
+            if (++since_drain == SK_TC_DRAIN_EVERY) {
+                since_drain = 0;
+#else
+            if (__any_sync(SK_FULL, pqo >= (uint32_t)(CAPE > 2 ? SK_TC_TRIG : 1) * ES)) {
+#endif
+                if (DBG && (dbg & 8) && lane == 0) atomicAdd(&g_tc_counters[3], 1ull);
+                if (DBG && (dbg & 32)) {   // timing experiment: park but never resolve (results are wrong)
+                    pqo = 8u * c4;
+                    continue;
+                }
+                const ThrPr d = tc_drain<KC, CAP, LD, CAPE, NS, J, DBG>(bs0, pqv0, pqi0, pub0, c4, thr, pr, pqo, dbg);
+                thr = d.thr;
+                pr = d.pr;
+                pqo = 8u * c4;
+            }
         }
 
-        // ---- final compaction, then every thread writes the candidates of its (query, stream) ----
-        int cnt;
+        // ---- flush the queue, final compaction, then every thread writes the candidates of its
+        //      (query, stream) ----
         {
-            const ThrCnt tc = tc_compact_all<KC, CAP, LD>(cs0, thr, (int)(pr / (uint32_t)(LD * 4)));
-            thr = tc.thr;
-            cnt = tc.cnt;
+            const ThrPr d = tc_drain<KC, CAP, LD, CAPE, NS, J, DBG>(bs0, pqv0, pqi0, pub0, c4, thr, pr, pqo, dbg);
+            const ThrPr c = tc_compact<KC, CAP, LD, NS, J>(bs0, pub0, c4, d.thr, d.pr);
+            thr = c.thr;
+            pr = c.pr;
         }
+        const int cnt = (int)(pr / (uint32_t)(LD * 4));
         const long long q = qtile * Cfg::QT + qslot;
         if (q < n_q) {
             constexpr int KOUT = 16 / NS;   // list slots per stream in the output (unused ones hold -1)
@@ -704,32 +745,36 @@ search_tc_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg,
     tc_fence_after();
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
     if (DBG && (dbg & 8) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
-        printf("tc counters (up to the last CTA): chunks %llu events %llu hit-lanes %llu compactions %llu coop %llu\n",
-               g_tc_counters[0], g_tc_counters[1], g_tc_counters[2], g_tc_counters[3], g_tc_counters[4]);
+        printf("tc counters (up to the last CTA): chunks %llu events %llu queued %llu drains %llu compactions %llu dropped %llu\n",
+               g_tc_counters[0], g_tc_counters[1], g_tc_counters[2], g_tc_counters[3], g_tc_counters[4],
+               g_tc_counters[5]);
 }
 
 int g_tc_debug = 0;  // timing experiments only (set through the "tc_debug" option)
 
-// Two configurations:
-//   ns = 2: two streams of KCS = 8 candidates (CAP 16) per query, 16 scanner warps -- k (+1) <= 8
-//   ns = 1: one stream of 16 candidates (CAP 32), 8 scanner warps              -- k (+1) <= 14
+// Two stream layouts:
+//   ns = 2: two streams of 8 candidates (CAP 16) per query, 16 scanner warps -- k (+1) <= 7
+//   ns = 1: one stream of 16 candidates (CAP 32), 8 scanner warps            -- k (+1) <= 15
+// (a list keeps the entries strictly below its KC-th best score, i.e. KC - 1 candidates)
+// and two pending-queue depths (4, or 2 when the operand images leave less shared memory).
 static constexpr int TC_MT = 2;
-#ifndef SK_TC_KCS
-#define SK_TC_KCS 8   // candidates kept per stream of the dual-stream layout (<= 8)
-#endif
 
-size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns) {
+size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns, int cape) {
     const size_t a = (size_t)kc_tot * TC_M * TC_ROWB, b = (size_t)kc_tot * TC_N * TC_ROWB;
-    const size_t ld = (size_t)TC_MT * TC_M * ns, cap = ns == 2 ? 16 : 32;
-    return TC_MT * a + nstage * b + (size_t)TC_MT * 4 * ns * 32 * 4 + 2 * cap * ld * 4 +
+    const size_t ld = (size_t)TC_MT * TC_M * ns, cap = ns == 2 ? 16 : 32, kcp = ns == 2 ? 8 : 0;
+    return TC_MT * a + nstage * b + ld * 4 * (2 * cap + (size_t)cape * 9 + kcp) +
            (size_t)(2 * nstage + 2 * TC_SLOTS + 1) * 8 + 16;
 }
 
-// ring stages for this contraction depth (0: the shape does not fit the engine)
-int search_tc_pick_stages(int kc_tot) {
-    for (int s = 4; s >= 2; --s)
-        if (search_tc_smem_bytes(kc_tot, s, 2) <= 227 * 1024 && search_tc_smem_bytes(kc_tot, s, 1) <= 227 * 1024)
-            return s;
+// ring stages (low byte) and pending-queue depth (next byte) for this contraction depth; 0: the
+// shape does not fit the engine
+int search_tc_pick_config(int kc_tot) {
+    const int capes[2] = {4, 2};
+    for (int ci = 0; ci < 2; ++ci)
+        for (int s = 4; s >= (ci == 0 ? 3 : 2); --s)
+            if (search_tc_smem_bytes(kc_tot, s, 2, capes[ci]) <= 227 * 1024 &&
+                search_tc_smem_bytes(kc_tot, s, 1, capes[ci]) <= 227 * 1024)
+                return s | (capes[ci] << 8);
     return 0;
 }
 
@@ -739,45 +784,58 @@ int search_tc_seed_tiles(int n_rtiles, int seed_stride) {
     return (n_rtiles + seed_stride - 1) / seed_stride;
 }
 
-template <int KC, int MT, int NS, int CAP, bool DBG>
-static cudaError_t launch_tc_dbg(const float *qimg, const float *rimg, int kc_tot, int n_rtiles, int nstage,
+template <int KC, int MT, int NS, int CAP, int CAPE, int J, bool DBG>
+static cudaError_t launch_tc_dbg(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles, int nstage,
                                  int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
                                  cudaStream_t st) {
-    using Cfg = TcCfg<MT, NS, CAP>;
-    const size_t smem = search_tc_smem_bytes(kc_tot, nstage, NS);
-    cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC, MT, NS, CAP, DBG>,
+    using Cfg = TcCfg<MT, NS, CAP, CAPE>;
+    const size_t smem = search_tc_smem_bytes(kc_tot, nstage, NS, CAPE);
+    cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC, MT, NS, CAP, CAPE, J, DBG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const long long n_qtiles = (n_q + Cfg::QT - 1) / Cfg::QT;
     const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride);
-    search_tc_kernel<KC, MT, NS, CAP, DBG><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
+    search_tc_kernel<KC, MT, NS, CAP, CAPE, J, DBG><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
         qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, seed_stride, n_q, cand_idx, cand_thr, g_tc_debug);
     return cudaGetLastError();
 }
 
 template <int KC, int MT, int NS, int CAP>
-static cudaError_t launch_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles, int nstage,
-                             int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
+static cudaError_t launch_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles, int nstage,
+                             int cape, int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
                              cudaStream_t st) {
+    // rank of the joint threshold: the certificate's margin grows with the contraction depth
+    // (eps * (|q|^2 + max|r|^2)), so deep spaces keep the streams' own KC-th best (rank 2 KC = off)
+    constexpr int JLO = NS == 2 ? SK_TC_JOINT : 1, JHI = NS == 2 ? 2 * KC : 1;
+    const bool deep = kc_tot > 6;   // more than 48 FP16 elements, i.e. d' > 45
     // the timing-experiment hooks ("tc_debug") live in a separate instantiation: none of their
     // tests is compiled into the product kernel
-    if (g_tc_debug)
-        return launch_tc_dbg<KC, MT, NS, CAP, true>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                    cand_idx, cand_thr, st);
-    return launch_tc_dbg<KC, MT, NS, CAP, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                 cand_idx, cand_thr, st);
+    if (g_tc_debug && cape == 4 && !deep)
+        return launch_tc_dbg<KC, MT, NS, CAP, 4, JLO, true>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
+                                                            cand_idx, cand_thr, st);
+    if (cape == 4 && !deep)
+        return launch_tc_dbg<KC, MT, NS, CAP, 4, JLO, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
+                                                             cand_idx, cand_thr, st);
+    if (cape == 4)
+        return launch_tc_dbg<KC, MT, NS, CAP, 4, JHI, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
+                                                             cand_idx, cand_thr, st);
+    if (cape == 2)
+        return launch_tc_dbg<KC, MT, NS, CAP, 2, JHI, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
+                                                             cand_idx, cand_thr, st);
+    return cudaErrorInvalidValue;
 }
 
-// cand_idx [n_q][16] (ns lists of 16 / ns entries), cand_thr [n_q][ns]
-cudaError_t launch_search_tc(const float *qimg, const float *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int ns, int nstage, int seed_stride, int *cand_idx,
+// cand_idx [n_q][16] (ns lists of 16 / ns entries), cand_thr [n_q][ns]; `config` from search_tc_pick_config
+cudaError_t launch_search_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles,
+                             long long n_q, int ns, int config, int seed_stride, int *cand_idx,
                              float *cand_thr, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
+    const int nstage = config & 0xff, cape = (config >> 8) & 0xff;
     if (ns == 2)
-        return launch_tc<SK_TC_KCS, TC_MT, 2, 16>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx,
+        return launch_tc<8, TC_MT, 2, 16>(qimg, rimg, kc_tot, n_rtiles, nstage, cape, seed_stride, n_q, cand_idx,
                                           cand_thr, st);
     if (ns == 1)
-        return launch_tc<16, TC_MT, 1, 32>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, cand_idx,
+        return launch_tc<16, TC_MT, 1, 32>(qimg, rimg, kc_tot, n_rtiles, nstage, cape, seed_stride, n_q, cand_idx,
                                            cand_thr, st);
     return cudaErrorInvalidValue;
 }

@@ -55,11 +55,11 @@ class StandardScalerWithDOF(DeviceProjectionMixin, StandardScaler):
         self.scale_ = np.std(X_arr, axis=0, ddof=self.ddof)
         return self
 
-    def _validate_query(self, X):
+    def _validate_query(self, X, finite=True):
         check_is_fitted(self)
         return validate_data(
             self, X, reset=False, accept_sparse=False, copy=False, dtype=FLOAT_DTYPES,
-            force_writeable=False, ensure_all_finite="allow-nan",
+            force_writeable=False, ensure_all_finite="allow-nan" if finite else False,
         )
 
     def _affine(self):

@@ -23,9 +23,9 @@ class MahalanobisTransformer(DeviceProjectionMixin, OneToOneFeatureMixin, Transf
         self.transform_ = np.linalg.inv(chol.T)
         return self
 
-    def _validate_query(self, X):
+    def _validate_query(self, X, finite=True):
         check_is_fitted(self)
-        return validate_data(self, X=X, ensure_all_finite="allow-nan", reset=False)
+        return validate_data(self, X=X, ensure_all_finite="allow-nan" if finite else False, reset=False)
 
     def _affine(self):
         return self.scaler_.mean_, self.scaler_.scale_, self.transform_, self.transform_.shape[1]
@@ -47,8 +47,8 @@ class CCATransformer(DeviceProjectionMixin, ComponentReducerMixin, TransformerMi
     ``(X - env_center_) @ projector_`` with no scaling
     (mirrors ref:src/sknnr/transformers/_cca_transformer.py:21-97)."""
 
-    def _checked(self, X, reset):
-        return validate_data(self, X=X, reset=reset, dtype=FLOAT_DTYPES, ensure_all_finite=True,
+    def _checked(self, X, reset, finite=True):
+        return validate_data(self, X=X, reset=reset, dtype=FLOAT_DTYPES, ensure_all_finite=finite,
                              ensure_min_features=2, ensure_min_samples=1)
 
     def fit(self, X, y):
@@ -67,9 +67,9 @@ class CCATransformer(DeviceProjectionMixin, ComponentReducerMixin, TransformerMi
         check_is_fitted(self, "n_components_")
         return np.asarray([f"cca{i}" for i in range(self.n_components_)], dtype=object)
 
-    def _validate_query(self, X):
+    def _validate_query(self, X, finite=True):
         check_is_fitted(self)
-        return self._checked(X, reset=False)
+        return self._checked(X, reset=False, finite=finite)
 
     def _affine(self):
         return self.env_center_, None, self.projector_, self.projector_.shape[1]
@@ -110,9 +110,9 @@ class CCorATransformer(DeviceProjectionMixin, ComponentReducerMixin, Transformer
         check_is_fitted(self, "n_components_")
         return np.asarray([f"ccora{i}" for i in range(self.n_components_)], dtype=object)
 
-    def _validate_query(self, X):
+    def _validate_query(self, X, finite=True):
         check_is_fitted(self)
-        return validate_data(self, X=X, reset=False, ensure_all_finite=True)
+        return validate_data(self, X=X, reset=False, ensure_all_finite=finite)
 
     def _affine(self):
         return self.scaler_.mean_, self.scaler_.scale_, self.projector_, self.projector_.shape[1]

@@ -215,10 +215,47 @@ def test_error_behaviour():
         ix.query(None, 10, exclude_self=True)
     with pytest.raises(ValueError, match="features"):
         ix.query(np.zeros((2, 4)), 2)
-    with pytest.raises(NotImplementedError):
-        KNNIndex(np.random.default_rng(0).standard_normal((100, 3))).query(np.zeros((2, 3)), 40)
     d, i, _ = ix.query(np.zeros((0, 3)), 2)
     assert d.shape == (0, 2) and i.shape == (0, 2)
+
+
+@pytest.mark.parametrize("k", [33, 40, 97, 300])
+def test_large_k_matches_oracle(k):
+    """ref:src/sknnr/_base.py:162-164 accepts any n_neighbors <= n_samples_fit: beyond 32 the
+    exhaustive float64 engine selects and finishes the row with a whole CTA."""
+    from sknnr_b200._engine import HammingIndex, KNNIndex
+
+    rng = np.random.default_rng(k)
+    n_ref = 301
+    R = rng.standard_normal((n_ref, 6))
+    R[200:230] = R[:30]                       # exact ties
+    y = rng.standard_normal((n_ref, 3))
+    Q = np.vstack([R[rng.integers(0, n_ref, 40)], rng.standard_normal((25, 6))])
+    st = orc.FittedState("euclidean", fit_Z=R, y=y)
+    ix = KNNIndex(R, None, None, None, y)
+    for off in (0, 1000):
+        d_o, i_o = orc.kneighbors(st, Q, k=k, row_offset=off, transformed=True)
+        d_g, i_g, p_g = ix.query(Q, k, transformed=True, weights="distance", with_pred=True, row_offset=off)
+        # (the reference's expansion |x|^2 - 2 x.y + |y|^2 returns ~1e-8 for a zero distance)
+        orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=1e-6, atol=1e-6)
+        same = (i_g == i_o).all(axis=1) & (d_o > 1e-6).all(axis=1)
+        p_o = orc.weighted_average(y, i_o, orc.get_weights(d_o, "distance"))
+        np.testing.assert_allclose(p_g[same], p_o[same], rtol=1e-6, atol=1e-9)
+    if k + 1 <= n_ref:
+        d_o, i_o = orc.kneighbors(st, None, k=k)
+        d_g, i_g, p_g = ix.query(None, k, exclude_self=True, weights="uniform", with_pred=True)
+        orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=1e-6, atol=1e-6)
+    # Hamming: bit-exact (count, index) ranking also for k > 32
+    T = 40
+    Rc = rng.integers(0, 6, size=(n_ref, T))
+    Qc = Rc[rng.integers(0, n_ref, 30)].copy()
+    Qc[rng.random(Qc.shape) < 0.3] = 7
+    w = np.full(T, 1.0 / T)
+    hs = orc.FittedState("hamming", fit_Z=Rc, y=y, hamming_w=w)
+    hd_o, hi_o = orc.kneighbors(hs, Qc, k=k)
+    hd, hi, _ = HammingIndex(Rc.astype(np.uint16), w, y).query(Qc.astype(np.uint16), k)
+    np.testing.assert_array_equal(hi, hi_o)
+    assert np.array_equal(hd, hd_o)
 
 
 # ---- Hamming / RFNN -------------------------------------------------------------------
