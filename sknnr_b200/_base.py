@@ -25,6 +25,7 @@ from sklearn.utils.validation import _is_arraylike, check_is_fitted, validate_da
 
 from . import _lib as L
 from ._engine import HammingIndex, KNNIndex
+from ._sharding import MultiDeviceIndex, devices_from_env
 
 
 class DFIndexCrosswalkMixin:
@@ -110,9 +111,11 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
         if ix is not None:
             return ix
         y = self._y
+        devices = devices_from_env()    # SKNNR_B200_DEVICES: the same fitted state on several GPUs
         if self._metric_kind() == "euclidean":
             center, scale, proj = self.__dict__.get("_projection", (None, None, None))
-            ix = KNNIndex(self._fit_X, center, scale, proj, y)
+            make = lambda dev: KNNIndex(self._fit_X, center, scale, proj, y, device=dev)  # noqa: E731
+            ix = MultiDeviceIndex(make, devices) if devices else make(None)
         else:
             ref_ids = np.asarray(self._fit_X)
             if not np.all(ref_ids == np.floor(ref_ids)):
@@ -123,7 +126,9 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
             w = (self.effective_metric_params_ or {}).get("w")
             if w is None:
                 w = np.full(ref_ids.shape[1], 1.0 / ref_ids.shape[1])
-            ix = HammingIndex(_encode_nodes(ref_ids, tables), w, y)
+            codes = _encode_nodes(ref_ids, tables)
+            make = lambda dev: HammingIndex(codes, w, y, device=dev)  # noqa: E731
+            ix = MultiDeviceIndex(make, devices) if devices else make(None)
         self.__dict__["_device_index"] = ix
         return ix
 
@@ -170,8 +175,9 @@ class RawKNNRegressor(DFIndexCrosswalkMixin, IndependentPredictorMixin, KNeighbo
             return ix.query(None, k, exclude_self=True, **kw)
         if forest is not None:
             k = self._check_k(n_neighbors, False, X.shape[0])
-            return ix.query_forest(forest._forest_index(self.__dict__.get("_node_tables")), X, k, **kw)
-        hamming = isinstance(ix, HammingIndex)
+            fx = forest._forest_index(self.__dict__.get("_node_tables"), devices=getattr(ix, "devices", None))
+            return ix.query_forest(fx, X, k, **kw)
+        hamming = hasattr(ix, "n_trees")
         if not raw:
             # (Euclidean searches: the finite check runs on the device, see below)
             X = validate_data(self, X, ensure_all_finite=hamming, accept_sparse=False, reset=False, order="C")

@@ -112,6 +112,21 @@ def _f64(a, ndim=None):
     return a
 
 
+def _outputs(out, n_q, k, n_out, return_distance, return_index, mode):
+    """Result arrays of a query: fresh ones, or the caller's (``out = (dist, idx, pred)``, C-contiguous
+    row blocks of the right dtype - a multi-device query hands every device a slice of shared arrays)."""
+    if out is None:
+        return (_result_empty((n_q, k), np.float64) if return_distance else None,
+                _result_empty((n_q, k), np.int64) if return_index else None,
+                _result_empty((n_q, n_out), np.float64) if mode != L.W_NONE else None)
+    dist, idx, pred = out
+    for a, want, width, dt in ((dist, return_distance, k, np.float64), (idx, return_index, k, np.int64),
+                               (pred, mode != L.W_NONE, n_out, np.float64)):
+        if want and (a is None or a.shape != (n_q, width) or a.dtype != dt or not a.flags.c_contiguous):
+            raise ValueError("`out` arrays must be C-contiguous, of the result's shape and dtype")
+    return (dist if return_distance else None, idx if return_index else None, pred if mode != L.W_NONE else None)
+
+
 def _weights_mode(weights, with_pred):
     if not with_pred:
         return L.W_NONE
@@ -233,7 +248,7 @@ class KNNIndex(_IndexBase):
     # -- host-buffer query (the drop-in call) ------------------------------------------
     def query(self, X, k, *, exclude_self=False, deterministic=True, decimals=10,
               row_offset=0, transformed=False, weights=None, with_pred=False,
-              return_distance=True, return_index=True, check_finite=False):
+              return_distance=True, return_index=True, check_finite=False, out=None):
         """kneighbors (+ optional predict) on host arrays.  ``X=None`` with
         ``exclude_self`` searches the reference set against itself.  ``check_finite``: the device
         looks for NaN / inf among the query values while it projects them and the call raises
@@ -255,9 +270,7 @@ class KNNIndex(_IndexBase):
                 raise ValueError(f"X has {X.shape[1]} features, but {want} are expected")
             Xp = _ptr(X)
         mode = _weights_mode(weights, with_pred)
-        dist = _result_empty((n_q, k), np.float64) if return_distance else None
-        idx = _result_empty((n_q, k), np.int64) if return_index else None
-        pred = _result_empty((n_q, self.n_out), np.float64) if mode != L.W_NONE else None
+        dist, idx, pred = _outputs(out, n_q, k, self.n_out, return_distance, return_index, mode)
         flags = self._flags(exclude_self, deterministic, transformed)
         if check_finite and not exclude_self:
             flags |= L.CHECK_FINITE
@@ -328,7 +341,7 @@ class HammingIndex(_IndexBase):
 
     def query(self, codes, k, *, exclude_self=False, deterministic=True, decimals=10,
               row_offset=0, weights=None, with_pred=False, return_distance=True,
-              return_index=True):
+              return_index=True, out=None):
         if exclude_self:
             n_q, cp, ldq = self.n_ref, None, 0
         else:
@@ -338,9 +351,7 @@ class HammingIndex(_IndexBase):
                 raise ValueError(f"X has {ldq} features, but {self.n_trees} are expected")
             cp = _ptr(codes)
         mode = _weights_mode(weights, with_pred)
-        dist = np.empty((n_q, k), dtype=np.float64) if return_distance else None
-        idx = np.empty((n_q, k), dtype=np.int64) if return_index else None
-        pred = np.empty((n_q, self.n_out), dtype=np.float64) if mode != L.W_NONE else None
+        dist, idx, pred = _outputs(out, n_q, k, self.n_out, return_distance, return_index, mode)
         L.check(self._lib.sknnr_hamming_kneighbors(
             self._h, cp, n_q, ldq, int(row_offset), int(k),
             self._flags(exclude_self, deterministic), int(decimals), _ptr(dist), _ptr(idx), mode,
@@ -348,7 +359,7 @@ class HammingIndex(_IndexBase):
         return dist, idx, pred
 
     def query_forest(self, forest, X, k, *, deterministic=True, decimals=10, row_offset=0,
-                     weights=None, with_pred=False, return_distance=True, return_index=True):
+                     weights=None, with_pred=False, return_distance=True, return_index=True, out=None):
         """kneighbors (+ predict) on RAW feature rows: forest walk -> node codes -> Hamming
         search in one device call (sknnr_hamming_kneighbors_forest)."""
         X = np.asarray(X)
@@ -360,9 +371,7 @@ class HammingIndex(_IndexBase):
                              f"{forest.n_features} are expected")
         n_q = X.shape[0]
         mode = _weights_mode(weights, with_pred)
-        dist = np.empty((n_q, k), dtype=np.float64) if return_distance else None
-        idx = np.empty((n_q, k), dtype=np.int64) if return_index else None
-        pred = np.empty((n_q, self.n_out), dtype=np.float64) if mode != L.W_NONE else None
+        dist, idx, pred = _outputs(out, n_q, k, self.n_out, return_distance, return_index, mode)
         L.check(self._lib.sknnr_hamming_kneighbors_forest(
             self._h, forest._h, _ptr(X), L.F32 if X.dtype == np.float32 else L.F64, n_q, X.shape[1],
             int(row_offset), int(k), self._flags(False, deterministic), int(decimals), _ptr(dist),

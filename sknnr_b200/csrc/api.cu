@@ -491,7 +491,11 @@ struct sknnr_index : IndexBase {
     int n_rtiles_tc = 0, kc_tot = 0, tc_nstage = 0;
     double tc_sigma = 1.0;         // power-of-two scale of both tensor-engine images
     bool tensor_ok = false;        // shape fits the tensor engine
-    bool tensor_demoted = false;   // too many uncertified rows: fall back to the SIMT engine
+    // too many uncertified rows: the SIMT engine is the better first stage.  Decided per stream layout
+    // (index = candidate streams per query: k (+1) <= 7 and larger k behave differently), from the
+    // chunks of host-buffer calls with that layout only.
+    bool tensor_demoted[3] = {false, false, false};
+    int ns_in_use = 2;
 };
 
 struct sknnr_hamming_index : IndexBase {
@@ -785,7 +789,9 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     int kc = pick_kc(kk, 1);   // 0: k (+1) is beyond the filtered engines' candidate lists -> exhaustive kernel
     if (kc != 0 && g_opt.kc > kc) kc = (int)g_opt.kc;
     const bool simt_ok = kc != 0 && search_simt_pick_stages(ix->dpad, kc) != 0;
-    const bool tensor_ok = ix->tensor_ok && !ix->tensor_demoted && kc != 0 && kc <= 16 && simt_ok;
+    const int ns_layout = g_opt.tc_streams == 1 ? 1 : (kk <= 7 ? 2 : 1);
+    ix->ns_in_use = ns_layout;
+    const bool tensor_ok = ix->tensor_ok && !ix->tensor_demoted[ns_layout] && kc != 0 && kc <= 16 && simt_ok;
     int engine = (int)g_opt.engine;
     if (engine == SKNNR_ENGINE_AUTO) engine = tensor_ok ? SKNNR_ENGINE_TENSOR : SKNNR_ENGINE_SIMT;
     if (engine == SKNNR_ENGINE_TENSOR && !(ix->tensor_ok && kc != 0 && kc <= 16 && simt_ok))
@@ -985,6 +991,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     ix->stats = sknnr_stats{};
     ix->stats.n_queries = n_q;
     ix->saw_nonfinite = false;
+    ix->chunk_rows_seen = ix->chunk_fb_seen = 0;   // the demotion rule looks at this call's chunks only
     if (n_q == 0) { guard.ok = true; return SKNNR_OK; }
 
     // ordinary NumPy buffers are staged through page-locked slot buffers by the host pool
@@ -1030,7 +1037,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             // (ill-conditioned features: huge norms relative to neighbour distances) the FP32
             // engine is the better first stage for this index
             if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen)
-                ix->tensor_demoted = true;
+                ix->tensor_demoted[ix->ns_in_use] = true;
         }
         const void *dX;
         int64_t dld = ldx;
@@ -1135,6 +1142,7 @@ static int raster_impl(IX *ix, int d, const void *bands, int32_t x_dtype, int64_
     for (auto &s : ix->slots) CK(ix->finish_slot(s));
     for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; s.flag_pending = false; }
     ix->stats = sknnr_stats{};
+    ix->chunk_rows_seen = ix->chunk_fb_seen = 0;
     if (n_valid_out) *n_valid_out = 0;
     if (n_pix == 0) { guard.ok = true; return SKNNR_OK; }
 
@@ -1230,7 +1238,7 @@ int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype,
                        [&](Slot &s, const void *xc, int64_t nv, int64_t row0, double *o_dist, long long *o_idx,
                            double *o_pred) -> int {
                            if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen)
-                               ix->tensor_demoted = true;
+                               ix->tensor_demoted[ix->ns_in_use] = true;
                            return run_chunk(ix, s, xc, x_dtype == SKNNR_F32, ix->d_in, false, nv, row0, k, flags,
                                             decimals, weights, o_dist, o_idx, o_pred);
                        });

@@ -5,10 +5,27 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdio.h>
 
 #define SK_FULL 0xffffffffu
 #define SK_INF_F __int_as_float(0x7f800000)
 #define SK_INF_D __longlong_as_double(0x7ff0000000000000LL)
+
+// Self-check build (python -m sknnr_b200._build --variant=checks -DSK_CHECKS): device-side bounds and
+// protocol assertions in the kernels that manage shared memory by hand.  compute-sanitizer is closed
+// on this pool, so the test suite is run against this build instead (profiles/r02_selfcheck.md).
+#ifdef SK_CHECKS
+#define SK_CHECK(cond)                                                                              \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            printf("SK_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__,   \
+                   (int)blockIdx.x, (int)threadIdx.x);                                              \
+            __trap();                                                                               \
+        }                                                                                           \
+    } while (0)
+#else
+#define SK_CHECK(cond) ((void)0)
+#endif
 
 namespace sk {
 

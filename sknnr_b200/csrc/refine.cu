@@ -190,6 +190,7 @@ refine2_kernel(RefineArgs a, FinishParams fp) {
 #pragma unroll 4
     for (int i = 0; i < a.kc; ++i) {
         const int c = __shfl_sync(SK_FULL, my_c, i, 16);
+        SK_CHECK(c >= -1 && c < a.n_ref);
         const bool have = c >= 0 && c < a.n_ref;
         double acc = 0.0;
         if (have) acc = dist2_lane_regs<DJ>(zr, a.ref64 + (long long)c * a.d, a.d, hl);

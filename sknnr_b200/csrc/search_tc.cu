@@ -78,9 +78,6 @@ template <int MT_, int NS_, int CAP_, int CAPE_> struct TcCfg {
     static constexpr int SORT = CAP <= 16 ? 16 : 32;      // width of the register sorting network
     static_assert(CAP <= SORT && CAP % 2 == 0, "candidate buffer shape");
     static constexpr int CH = 4 / NS;                     // 32-column chunks a scanner warp reads per job
-    static constexpr int KCP = NS == 2 ? 8 : 0;           // published scores per thread (joint threshold)
-    // bytes of the selection state: candidates, pending queue (values + indices), published scores
-    static constexpr size_t SEL_BYTES = (size_t)LD * 4 * (2 * CAP + CAPE * 9 + KCP);
 };
 constexpr uint32_t TC_ROWB = 16;                // bytes of one row of one K chunk (4 TF32)
 static_assert(TC_N == 128, "epilogue assumes four 32-column chunks per tile");
@@ -294,11 +291,7 @@ __device__ __forceinline__ float tc_union_rank(const float (&a)[NA], const float
 #ifndef SK_TC_JOINT
 #define SK_TC_JOINT 12
 #endif
-// parked octets of one lane that make the warp resolve its queues (room for CAPE - SK_TC_TRIG more)
-#ifndef SK_TC_TRIG
-#define SK_TC_TRIG 2
-#endif
-// > 0: the queues are resolved every SK_TC_DRAIN_EVERY jobs by all warps together instead
+// jobs between two resolutions of the pending queues (0 = 8 with queues of four octets, 2 with queues of two)
 #ifndef SK_TC_DRAIN_EVERY
 #define SK_TC_DRAIN_EVERY 0
 #endif
@@ -329,13 +322,14 @@ __device__ __forceinline__ ThrPr tc_compact(uint32_t bs0, uint32_t pub0, uint32_
     constexpr uint32_t IOFF = CAP * LD * 4, STEP = LD * 4;
     const uint32_t cs0 = bs0 + c4;
     const int cnt = (int)(pr / STEP);
+    SK_CHECK((pr & (STEP - 1)) == c4 && cnt <= CAP);
     float s[SORT];
 #pragma unroll
     for (int j = 0; j < SORT; ++j) s[j] = (j < CAP && j < cnt) ? lds_f32(cs0 + j * STEP) : SK_INF_F;
     sort_regs<SORT>(s);
     float t = s[KC - 1];
-    if constexpr (NS == 2) {
-        static_assert(LD == 512 || NS != 2, "partner column = column ^ 256");
+    if constexpr (NS == 2 && J < 2 * KC) {
+        static_assert(LD == 512, "partner column = column ^ 256");
         const uint32_t mine = pub0 + c4, other = pub0 + (c4 ^ 1024u);
         float o[KC];
 #pragma unroll
@@ -375,6 +369,7 @@ __device__ __noinline__ ThrPr tc_drain(uint32_t bs0, uint32_t pqv0, uint32_t pqi
     constexpr uint32_t IOFF = CAP * LD * 4, STEP = LD * 4, ES = LD * 32;
     constexpr uint32_t FULL = (CAP - 2) * STEP, LAST = (CAP - 1) * STEP;
     const int n_me = (int)(pqo / ES);
+    SK_CHECK((pqo & (ES - 1)) == 8u * c4 && n_me <= CAPE);
     const int n_it = __reduce_max_sync(SK_FULL, n_me);
     for (int it = 0; it < n_it; ++it) {   // warp-uniform
         const bool act = it < n_me;
@@ -387,6 +382,8 @@ __device__ __noinline__ ThrPr tc_drain(uint32_t bs0, uint32_t pqv0, uint32_t pqi
         const uint32_t va = pqv0 + 8u * c4 + (uint32_t)it * ES;
         const float4 x = lds_f32x4(va), y = lds_f32x4(va + 16);
         const int id = lds_s32(pqi0 + c4 + (uint32_t)it * STEP);
+        SK_CHECK(!act || (id >= 0 && (id & 7) == 0));
+        SK_CHECK(pr <= LAST + c4);
         const float vv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -439,6 +436,7 @@ __device__ __forceinline__ void tc_chunk(const uint32_t (&r)[32], int idb, uint3
     for (int o = 0; o < 4; ++o) {
         const bool p = g[o] < thr;
         const bool room = pqo < PQ_END;
+        SK_CHECK(pqo < PQ_END + ES);
         tc_dump8(p && room, pqv0 + pqo, pqi0 + (pqo >> 3), v + 8 * o, idb + 8 * o);
         if (p && !room) thr = fminf(thr, g[o]);
         if (p && room) pqo += ES;
@@ -484,8 +482,9 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
                  int n_rtiles, int nstage, int n_seed, int seed_stride, long long n_q,
                  int *__restrict__ cand_idx, float *__restrict__ cand_thr, int dbg) {
     using Cfg = TcCfg<MT, NS, CAP, CAPE>;
-    constexpr int LD = Cfg::LD, EPI_WARPS = Cfg::EPI_WARPS, KCP = Cfg::KCP;
-    static_assert(KCP == 0 || KCP == KC, "the joint threshold uses the KC best scores of both streams");
+    constexpr int LD = Cfg::LD, EPI_WARPS = Cfg::EPI_WARPS;
+    constexpr bool JOINT = NS == 2 && J < 2 * KC;     // J = 2 KC: every stream keeps its own KC-th best
+    constexpr int KCP = JOINT ? KC : 0;               // published scores per thread
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t a_bytes = (uint32_t)kc_tot * TC_M * TC_ROWB;  // one 128-query operand image
     const uint32_t b_bytes = (uint32_t)kc_tot * TC_N * TC_ROWB;  // one 128-plot operand image
@@ -582,6 +581,7 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
             if (j >= TC_SLOTS) mbar_wait(&aempty[sl], (uint32_t)(((j >> 2) - 1) & 1));
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + sl * TC_N;
+            SK_CHECK(s >= 0 && s < nstage && sl < TC_SLOTS);
             if (elect_one()) {
                 if (DBG && (dbg & 16)) {   // timing experiment: the job's MMAs issued twice (same result)
                     uint32_t a2 = a_lo0, b2 = b_lo_s;
@@ -690,18 +690,25 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
                                constexpr int c = decltype(ic)::value;
                                tc_chunk<LD, CAPE, DBG>(r, idb + c * 32, pqv0, pqi0, thr, pqo, dbg);
                            });
-            // resolve the parked octets once a lane has two or more of them (CAPE - 2 entries of room
-            // are left for the next job; beyond that an octet is dropped, which is safe)
-#if SK_TC_DRAIN_EVERY > 0
-            // every scanner warp of the CTA resolves its queues in the SAME jobs: a slot is only handed
+            // Every scanner warp of the CTA resolves its queues in the SAME jobs: a slot is only handed
             // back when all eight warps of its M tile have read it, so a long operation costs the
             // whole M tile its duration - once per period when the warps take it together, almost
-            // every job when each warp takes it whenever its own queues fill up
-            if (++since_drain == SK_TC_DRAIN_EVERY) {
+            // every job when each warp takes it whenever its own queues fill up (measured: 32.5 ->
+            // 30.1 ms per 4M rows).  A lane whose queue fills up inside a period drops octets, which
+            // only lowers its threshold.
+            constexpr int DRAIN_EVERY = SK_TC_DRAIN_EVERY > 0 ? SK_TC_DRAIN_EVERY : 8;
+            bool now;
+            if constexpr (CAPE >= 4 && NS == 2) {
+                // (... or earlier, when a lane is down to its last free entry: early in the pass, while
+                // the thresholds are still loose, the queues fill faster than the period)
+                now = (++since_drain == DRAIN_EVERY) | __any_sync(SK_FULL, pqo >= (uint32_t)(CAPE - 1) * ES);
+            } else {
+                // (one stream of four chunks per job, or queues of two octets: a period would overflow
+                // the queues, so a lane with a parked octet makes its warp resolve at once)
+                now = __any_sync(SK_FULL, pqo >= ES);
+            }
+            if (now) {
                 since_drain = 0;
-#else
-            if (__any_sync(SK_FULL, pqo >= (uint32_t)(CAPE > 2 ? SK_TC_TRIG : 1) * ES)) {
-#endif
                 if (DBG && (dbg & 8) && lane == 0) atomicAdd(&g_tc_counters[3], 1ull);
                 if (DBG && (dbg & 32)) {   // timing experiment: park but never resolve (results are wrong)
                     pqo = 8u * c4;
@@ -723,6 +730,7 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
             pr = c.pr;
         }
         const int cnt = (int)(pr / (uint32_t)(LD * 4));
+        SK_CHECK(cnt < KC && cnt <= 16 / NS);
         const long long q = qtile * Cfg::QT + qslot;
         if (q < n_q) {
             constexpr int KOUT = 16 / NS;   // list slots per stream in the output (unused ones hold -1)
@@ -761,7 +769,8 @@ static constexpr int TC_MT = 2;
 
 size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns, int cape) {
     const size_t a = (size_t)kc_tot * TC_M * TC_ROWB, b = (size_t)kc_tot * TC_N * TC_ROWB;
-    const size_t ld = (size_t)TC_MT * TC_M * ns, cap = ns == 2 ? 16 : 32, kcp = ns == 2 ? 8 : 0;
+    // (published scores only exist while the joint threshold is on: two streams, d' <= 45)
+    const size_t ld = (size_t)TC_MT * TC_M * ns, cap = ns == 2 ? 16 : 32, kcp = (ns == 2 && kc_tot <= 6) ? 8 : 0;
     return TC_MT * a + nstage * b + ld * 4 * (2 * cap + (size_t)cape * 9 + kcp) +
            (size_t)(2 * nstage + 2 * TC_SLOTS + 1) * 8 + 16;
 }
@@ -771,7 +780,7 @@ size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns, int cape) {
 int search_tc_pick_config(int kc_tot) {
     const int capes[2] = {4, 2};
     for (int ci = 0; ci < 2; ++ci)
-        for (int s = 4; s >= (ci == 0 ? 3 : 2); --s)
+        for (int s = 4; s >= 2; --s)
             if (search_tc_smem_bytes(kc_tot, s, 2, capes[ci]) <= 227 * 1024 &&
                 search_tc_smem_bytes(kc_tot, s, 1, capes[ci]) <= 227 * 1024)
                 return s | (capes[ci] << 8);
@@ -807,7 +816,7 @@ static cudaError_t launch_tc(const __half *qimg, const __half *rimg, int kc_tot,
     // rank of the joint threshold: the certificate's margin grows with the contraction depth
     // (eps * (|q|^2 + max|r|^2)), so deep spaces keep the streams' own KC-th best (rank 2 KC = off)
     constexpr int JLO = NS == 2 ? SK_TC_JOINT : 1, JHI = NS == 2 ? 2 * KC : 1;
-    const bool deep = kc_tot > 6;   // more than 48 FP16 elements, i.e. d' > 45
+    const bool deep = kc_tot > 6;   // more than 48 FP16 elements, i.e. d' > 45 (search_tc_smem_bytes knows the same rule)
     // the timing-experiment hooks ("tc_debug") live in a separate instantiation: none of their
     // tests is compiled into the product kernel
     if (g_tc_debug && cape == 4 && !deep)

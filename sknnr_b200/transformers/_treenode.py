@@ -125,19 +125,29 @@ class TreeNodeTransformer(TransformerMixin, BaseEstimator, ABC):
     def fit(self, X, y): ...
 
     # -- transform ----------------------------------------------------------------------
-    def _forest_index(self, node_code_tables=None):
+    def _forest_index(self, node_code_tables=None, devices=None):
         """Device copy of the trees (a cache outside ``__dict__``: never pickled, rebuilt on demand).
         A copy made with ``node_code_tables`` also serves the fused Hamming query of the estimator
-        that owns them."""
+        that owns them.  ``devices``: one copy per listed GPU (for a multi-device index)."""
         from .._engine import ForestIndex
 
-        key = "forest_coded" if node_code_tables is not None else "forest_plain"
+        if devices is not None:
+            from .._sharding import _PerDevice
+
+            return _PerDevice(self._forest_index_on(node_code_tables, d) for d in devices)
+        return self._forest_index_on(node_code_tables, None)
+
+    def _forest_index_on(self, node_code_tables, device):
+        from .._engine import ForestIndex
+
+        key = ("forest_coded" if node_code_tables is not None else "forest_plain") + ("" if device is None else f"@{device}")
+        coded = node_code_tables is not None
         fx = _cache.get(self, key)
-        if fx is not None and key == "forest_coded" and _cache.get(self, "tables_id") != id(node_code_tables):
+        if fx is not None and coded and _cache.get(self, "tables_id") != id(node_code_tables):
             fx = None   # the owning estimator rebuilt its code tables (refit)
         if fx is None:
-            fx = _cache.put(self, key, ForestIndex(self._trees(), self.n_features_in_, node_code_tables))
-            if key == "forest_coded":
+            fx = _cache.put(self, key, ForestIndex(self._trees(), self.n_features_in_, node_code_tables, device=device))
+            if coded:
                 _cache.put(self, "tables_id", id(node_code_tables))
         return fx
 

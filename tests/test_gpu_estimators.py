@@ -97,6 +97,23 @@ def test_config2_gnn_moscow_independent_score():
     np.testing.assert_array_equal(i, g["live_ref_nn"])
 
 
+def _same_forests_or_skip(g, ids_te, key, what):
+    """The golden node IDs come from forests grown by a recorded scikit-learn / NumPy: with the same
+    versions different forests are a FAILURE (the seeded training is deterministic), with other
+    versions the end-to-end comparison cannot be made and the test says so loudly."""
+    import numpy
+    import sklearn
+
+    if np.array_equal(ids_te, g[key].astype(np.int64)):
+        return
+    have = {"sklearn": sklearn.__version__, "numpy": numpy.__version__}
+    rec = dict(v.split("=", 1) for v in g["versions"].tolist())
+    same = all(rec.get(k) == v for k, v in have.items())
+    assert not same, f"{what}: different trees although the versions equal the golden generator's ({rec})"
+    pytest.skip(f"{what}: scikit-learn {have['sklearn']} / NumPy {have['numpy']} grew different trees than the "
+                f"golden generator's ({rec.get('sklearn')} / {rec.get('numpy')})")
+
+
 def test_rfnn_end_to_end_matches_live_reference():
     """Same scikit-learn version and seed grow the same forests, so the whole RFNN path
     (forest apply on the host, Hamming search on the device) must reproduce the live
@@ -108,8 +125,7 @@ def test_rfnn_end_to_end_matches_live_reference():
     Xtr, Xte, ytr, yte, _ = _split()
     est = S.RFNNRegressor(n_neighbors=5, random_state=42).fit(Xtr, ytr)
     ids_te = est.transformer_.transform(Xte)
-    if not np.array_equal(ids_te, g["ids_test"].astype(np.int64)):
-        pytest.skip("scikit-learn grew different forests than the golden generator's")
+    _same_forests_or_skip(g, ids_te, "ids_test", "RFNN end to end")
     np.testing.assert_array_equal(est.hamming_weights_, g["hamming_w"])
     d, i = est.kneighbors(Xte)
     assert np.array_equal(d, g["live_tgt_dist"])
@@ -146,8 +162,7 @@ def test_gbnn_end_to_end_matches_live_reference():
             warnings.simplefilter("ignore", FutureWarning)
             est = S.GBNNRegressor(n_neighbors=5, random_state=42).fit(Xtr, ytr, y_fit=y_fit)
         ids_te = est.transformer_.transform(Xte)
-        if not np.array_equal(ids_te, g[tag + "ids_test"].astype(np.int64)):
-            pytest.skip("scikit-learn grew different boosted trees than the golden generator's")
+        _same_forests_or_skip(g, ids_te, tag + "ids_test", "GBNN end to end")
         np.testing.assert_allclose(est.hamming_weights_, g[tag + "hamming_w"], rtol=1e-12)
         if not np.array_equal(est.hamming_weights_, g[tag + "hamming_w"]):
             continue   # weights differ in the last bit: distances cannot be bit-equal

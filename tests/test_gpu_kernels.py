@@ -762,3 +762,156 @@ def test_c4_shape_hamming_properties():
         d_b, i_b, _ = ix.query(Qc[h:], k, row_offset=h, deterministic=False)
         assert np.array_equal(i_b, idx[h:]) and np.array_equal(d_b, dist[h:])
         ix.close()
+
+
+# ---- round 2: host staging, device-side finite check, large shapes, non-integer node IDs -----
+from sknnr_b200 import _lib as L  # noqa: E402
+
+
+def test_pageable_and_page_locked_buffers_give_identical_results():
+    """Ordinary NumPy arrays are staged through page-locked slot buffers by the library's host
+    threads (csrc/api.cu); many small staged chunks, strided rows and caller-supplied result
+    arrays must reproduce the page-locked path bit for bit."""
+    from sknnr_b200._engine import KNNIndex, pinned_empty
+
+    rng = np.random.default_rng(5)
+    R = rng.standard_normal((700, 9))
+    y = rng.standard_normal((700, 2))
+    n_q = 20_000
+    X = rng.standard_normal((n_q, 9))
+    Xs = np.ascontiguousarray(np.hstack([X, rng.standard_normal((n_q, 3))]))[:, :9]   # row stride 12
+    Xp = pinned_empty((n_q, 9))
+    Xp[:] = X
+    ix = KNNIndex(R, None, None, None, y)
+    L.set_option("stage_rows", 1024)
+    L.set_option("chunk_rows", 4096)
+    try:
+        ref = ix.query(Xp, 5, transformed=True, weights="distance", with_pred=True,
+                       out=(pinned_empty((n_q, 5)), pinned_empty((n_q, 5), np.int64), pinned_empty((n_q, 2))))
+        for Xin in (X, Xs, X.astype(np.float32).astype(np.float64)):
+            got = ix.query(Xin, 5, transformed=True, weights="distance", with_pred=True)
+            own = (np.empty((n_q, 5)), np.empty((n_q, 5), dtype=np.int64), np.empty((n_q, 2)))
+            got2 = ix.query(Xin, 5, transformed=True, weights="distance", with_pred=True, out=own)
+            if Xin is not X and Xin is not Xs:
+                continue   # (the float32 round trip changes the values: only exercised, not compared)
+            for a, b, c in zip(ref, got, got2):
+                assert np.array_equal(a, b) and np.array_equal(a, c)
+        with pytest.raises(ValueError, match="out"):
+            ix.query(X, 5, transformed=True, out=(np.empty((n_q, 4)), np.empty((n_q, 5), dtype=np.int64), None))
+    finally:
+        L.set_option("stage_rows", 1 << 19)
+        L.set_option("chunk_rows", 1 << 20)
+
+
+def test_device_side_finite_check_raises_like_the_reference():
+    from sknnr_b200 import EuclideanKNNRegressor, MSNRegressor, RawKNNRegressor
+    from sknnr_b200._engine import KNNIndex
+
+    rng = np.random.default_rng(6)
+    R = rng.standard_normal((300, 6))
+    y = rng.standard_normal((300, 3))
+    X = rng.standard_normal((5000, 6))
+    ix = KNNIndex(R, None, None, None, y)
+    ok = ix.query(X, 3, transformed=True, check_finite=True)
+    assert np.isfinite(ok[0]).all()
+    for bad, where in ((np.nan, (4321, 2)), (np.inf, (0, 0)), (-np.inf, (4999, 5))):
+        Xb = X.copy()
+        Xb[where] = bad
+        with pytest.raises(L.NonFiniteInput):
+            ix.query(Xb, 3, transformed=True, check_finite=True)
+        ix.query(Xb, 3, transformed=True)                 # without the flag the call does not judge
+        for est in (EuclideanKNNRegressor(n_neighbors=3).fit(R, y), MSNRegressor(n_neighbors=3).fit(R, y),
+                    RawKNNRegressor(n_neighbors=3).fit(R, y)):
+            with pytest.raises(ValueError, match="NaN|infinity"):
+                est.predict(Xb)
+            with pytest.raises(ValueError, match="NaN|infinity"):
+                est.kneighbors(Xb)
+        assert np.isfinite(EuclideanKNNRegressor(n_neighbors=3).fit(R, y).predict(X)).all()
+
+
+@pytest.mark.parametrize(("d_in", "d_out"), [(300, 20), (200, 200), (230, 230)])
+def test_projection_of_shapes_beyond_shared_memory(d_in, d_out):
+    """More raw features than a 128-row tile can stage (d_in > 225) and projectors beyond 227 KB
+    (ADVICE round 1): the projection falls back to global-memory operands, same numbers."""
+    from sknnr_b200._engine import KNNIndex
+
+    rng = np.random.default_rng(d_in)
+    n_ref = 400
+    Xr = rng.standard_normal((n_ref, d_in)) * 3.0 + 10.0
+    center, scale = Xr.mean(0), Xr.std(0, ddof=1)
+    proj = rng.standard_normal((d_in, d_out)) / np.sqrt(d_in)
+    Z = ((Xr - center) / scale) @ proj
+    y = rng.standard_normal((n_ref, 2))
+    ix = KNNIndex(Z, center, scale, proj, y)
+    Q = rng.standard_normal((333, d_in)) * 3.0 + 10.0
+    np.testing.assert_allclose(ix.transform(Q), ((Q - center) / scale) @ proj, rtol=1e-11, atol=1e-11)
+    st = orc.FittedState("euclidean", fit_Z=Z, y=y, center=center, scale=scale, proj=proj)
+    d_o, i_o = orc.kneighbors(st, Q, k=4)
+    d_g, i_g, _ = ix.query(Q, 4)
+    orc.assert_tie_aware_equal(d_g, i_g, d_o, i_o, rtol=1e-5, atol=1e-7 * float(np.sqrt((Z ** 2).sum(1).max())))
+    Qb = Q.copy()
+    Qb[17, d_in - 1] = np.nan
+    with pytest.raises(L.NonFiniteInput):
+        ix.query(Qb, 4, check_finite=True)
+
+
+def test_hamming_non_integer_query_values_match_nothing():
+    """scipy's hamming compares values ($SP/scipy/spatial/distance.py:1718-1723): a query value such as
+    3.5 equals no node ID (the int64 cast used to truncate it onto node 3)."""
+    from sklearn.neighbors import KNeighborsRegressor
+
+    from sknnr_b200 import RawKNNRegressor
+
+    rng = np.random.default_rng(8)
+    Rc = rng.integers(0, 6, size=(200, 12)).astype(np.float64)
+    y = rng.standard_normal((200, 2))
+    Q = Rc[rng.integers(0, 200, 50)].copy()
+    Q[rng.random(Q.shape) < 0.25] += 0.5
+    w = np.full(12, 1.0 / 12)            # (as RFNN passes them, ref:src/sknnr/_weighted_trees.py:139-140)
+    ours = RawKNNRegressor(n_neighbors=4, metric="hamming", algorithm="brute", metric_params={"w": w}).fit(Rc, y)
+    d_g, i_g = ours.kneighbors(Q, use_deterministic_ordering=False)
+    ref = KNeighborsRegressor(n_neighbors=200, metric="hamming", algorithm="brute", metric_params={"w": w}).fit(Rc, y)
+    d_all, i_all = ref.kneighbors(Q)
+    full = np.empty_like(d_all)
+    np.put_along_axis(full, i_all, d_all, axis=1)          # full[q, j] = scipy distance of plot j
+    assert np.array_equal(d_g, np.take_along_axis(full, i_g, axis=1))
+    order = np.lexsort((np.broadcast_to(np.arange(200), full.shape), full), axis=1)[:, :4]
+    assert np.array_equal(i_g, order)
+
+
+def test_raster_nodata_is_compared_in_the_band_dtype():
+    """A float32 raster whose nodata literal is not representable in float32."""
+    from sknnr_b200._engine import KNNIndex
+
+    rng = np.random.default_rng(9)
+    R = rng.standard_normal((300, 4))
+    y = rng.standard_normal((300, 2))
+    ix = KNNIndex(R, None, None, None, y)
+    img = rng.standard_normal((4, 1000)).astype(np.float32)
+    nodata = -9999.9
+    img[2, ::7] = nodata                       # stored as float32(-9999.9) != -9999.9
+    _, idx, _, n_valid = ix.query_raster(img, 3, nodata=nodata)
+    masked = (img == np.float32(nodata)).any(axis=0)
+    assert n_valid == int((~masked).sum()) and masked.sum() > 0
+    assert (idx[:, masked] == -1).all() and (idx[:, ~masked] >= 0).all()
+
+
+@pytest.mark.parametrize("k", [7, 10])
+def test_tensor_engine_certifies_nearly_every_row_and_stays_selected(k):
+    """Both stream layouts of the tensor engine (k <= 7: two streams, larger k: one) must certify
+    all but a few per cent of the rows of an ordinary workload - otherwise the library demotes the
+    index to the 10x slower FP32 engine - and a self-query (k + 1) must not spoil later calls."""
+    from sknnr_b200._engine import KNNIndex
+
+    rng = np.random.default_rng(12)
+    R = rng.standard_normal((20_000, 32))
+    y = rng.standard_normal((20_000, 2))
+    Q = rng.standard_normal((40_000, 32))
+    ix = KNNIndex(R, None, None, None, y)
+    ix.query(None, k, exclude_self=True)
+    st = ix.stats()
+    assert st["engine"] == L.ENGINE_TENSOR and st["n_fallback"] < 0.05 * st["n_queries"], st
+    for _ in range(2):
+        ix.query(Q, k, transformed=True, weights="distance", with_pred=True)
+        st = ix.stats()
+        assert st["engine"] == L.ENGINE_TENSOR and st["n_fallback"] < 0.03 * st["n_queries"], st

@@ -74,3 +74,50 @@ def test_sharded_query_equals_single_call_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0] and res[1] and res[2] and res[3] == (15, 3)
+
+
+def test_devices_from_env_and_multi_device_fan_out(monkeypatch):
+    """Host logic of the in-process multi-device index with stub parts (no GPU): contiguous blocks,
+    global row offsets, disjoint slices of shared result arrays."""
+    from sknnr_b200 import _sharding as S
+
+    monkeypatch.delenv("SKNNR_B200_DEVICES", raising=False)
+    assert S.devices_from_env() is None
+    monkeypatch.setenv("SKNNR_B200_DEVICES", "3")
+    assert S.devices_from_env() is None
+    monkeypatch.setenv("SKNNR_B200_DEVICES", "0, 2,5")
+    assert S.devices_from_env() == [0, 2, 5]
+
+    calls = []
+
+    class Part:
+        n_ref, n_out, d_in, d_out = 10, 2, 3, 3
+
+        def __init__(self, dev):
+            self.dev = dev
+
+        def query(self, X, k, row_offset=0, out=None, **kw):
+            calls.append((self.dev, row_offset, X.shape[0]))
+            if out is None:
+                out = (np.empty((X.shape[0], k)), np.empty((X.shape[0], k), dtype=np.int64), np.empty((X.shape[0], 2)))
+            d, i, p = out
+            rows = np.arange(row_offset, row_offset + X.shape[0])
+            d[:] = rows[:, None] + 0.5
+            i[:] = rows[:, None] * 10 + np.arange(k)
+            if p is not None:
+                p[:] = X[:, :2] * (self.dev + 1)
+            return d, i, p
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(S.MultiDeviceIndex, "min_rows_per_device", 4)
+    m = S.MultiDeviceIndex(Part, [0, 1, 2])
+    X = np.arange(33, dtype=float)[:, None] * np.ones((1, 3))
+    d, i, p = m.query(X, 2, row_offset=100, weights="uniform", with_pred=True)
+    assert sorted(calls) == [(0, 100, 11), (1, 111, 11), (2, 122, 11)]
+    assert np.array_equal(d[:, 0], np.arange(100, 133) + 0.5) and np.array_equal(i[:, 1], np.arange(100, 133) * 10 + 1)
+    assert np.array_equal(p[:11], X[:11, :2]) and np.array_equal(p[22:], X[22:, :2] * 3)
+    calls.clear()
+    d, i, p = m.query(X[:5], 2)            # too few rows for a second device: one call, own outputs
+    assert calls == [(0, 0, 5)] and d.shape == (5, 2)
