@@ -102,7 +102,7 @@ int sknnr_device_count(int *count);
  *   "tc_seed_stride" 0..64: the tensor engine pre-scans one reference tile in n to seed its
  *                 thresholds (default 4; 0 = off)
  *   "host_threads" workers that stage pageable caller buffers through page-locked slot buffers
- *                 (default 0 = min(8, cores / 2); read when the first pageable call starts them)
+ *                 (default 0 = min(16, cores / 2); read when the first pageable call starts them)
  *   "stage_rows"  rows per chunk of a call with pageable buffers (default 1<<19)
  *   "tc_debug"    timing experiments only (bit 0 skips the hit path, bit 2 skips the tile
  *                 loads: results are wrong)                                             */

@@ -89,7 +89,7 @@ public:
             int n = (int)g_opt.host_threads;
             if (n <= 0) {
                 const unsigned hw = std::thread::hardware_concurrency();
-                n = (int)std::min(8u, std::max(1u, hw / 2));
+                n = (int)std::min(16u, std::max(2u, hw / 2));
             }
             return new HostPool(n - 1);   // the calling thread takes a share as well
         }();

@@ -699,9 +699,11 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
             constexpr int DRAIN_EVERY = SK_TC_DRAIN_EVERY > 0 ? SK_TC_DRAIN_EVERY : 8;
             bool now;
             if constexpr (CAPE >= 4 && NS == 2) {
-                // (... or earlier, when a lane is down to its last free entry: early in the pass, while
-                // the thresholds are still loose, the queues fill faster than the period)
-                now = (++since_drain == DRAIN_EVERY) | __any_sync(SK_FULL, pqo >= (uint32_t)(CAPE - 1) * ES);
+                // (early in the pass, while the thresholds are still loose, the queues fill faster: the first
+                // eighth of the tiles uses a period of two jobs - a schedule again, not a vote, so that
+                // the warps still resolve together and the fast path pays nothing for it)
+                const int period = (t - n_seed) < (n_rtiles >> 3) ? 2 : DRAIN_EVERY;
+                now = ++since_drain >= period;
             } else {
                 // (one stream of four chunks per job, or queues of two octets: a period would overflow
                 // the queues, so a lane with a parked octet makes its warp resolve at once)
