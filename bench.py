@@ -76,7 +76,12 @@ def parse_args():
     ap.add_argument("--tc-debug", type=int, default=0)
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--host-slots", type=int, default=0)
+    ap.add_argument("--gather", default="auto", choices=["auto", "fused", "copy"],
+                    help="N > 1: how a rank's rows reach rank 0's arrays - fused = the finishing kernels store "
+                         "over NVLink; copy = per-chunk copy-engine peer copies on the chunk's stream")
     a = ap.parse_args()
+    if a.gather == "auto":
+        a.gather = "fused"
     if a.only:
         a.no_c4 = a.no_c4 or a.only != "c4"
         a.no_c5 = a.no_c5 or a.only != "c5"
@@ -448,6 +453,7 @@ def run_ours(a, rank, world, local_rank):
     lib = L.load()
     L.set_option("timing", 1)
     for name, v in (("engine", a.engine), ("kc", a.kc), ("tc_streams", a.tc_streams), ("tc_debug", a.tc_debug),
+
                     ("chunk_rows", a.chunk_rows), ("host_slots", a.host_slots)):
         if v:
             L.set_option(name, v)
@@ -535,13 +541,21 @@ def bench_c3(a, rank, world, local_rank, dev, stream, lib, L, KNNIndex, barrier,
                            pred_ptr=shared.ptr(2), weights="distance", row_offset=rank * n_q,
                            stream=stream.cuda_stream)
 
+    def step_copy():
+        # synchronous call on device pointers: chunks pipeline over the library's slot streams and every
+        # chunk's results travel to rank 0's arrays as copy-engine peer copies under the next chunks' kernels
+        L.check(lib.sknnr_kneighbors(index._h, C.c_void_p(X_dev.data_ptr()), L.F64, n_q, d, rank * n_q, k,
+                                     L.DETERMINISTIC, 10, C.c_void_p(shared.ptr(0)), C.c_void_p(shared.ptr(1)),
+                                     L.W_DISTANCE, C.c_void_p(shared.ptr(2)), None))
+
+    step_timed = step_copy if (world > 1 and a.gather == "copy") else step_device
     for _ in range(a.warmup):
-        step_device()
+        step_timed()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total = timed(step_device, a.steps)
+    ms_total = timed(step_timed, a.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = world * n_q * a.steps / (ms_total * 1e-3)
 
@@ -672,6 +686,7 @@ def bench_c3(a, rank, world, local_rank, dev, stream, lib, L, KNNIndex, barrier,
         "hbm": hbm, "cpu_baseline": cpu, "e2e": e2e, "e2e_estimator": e2e_est,
         "gpu_launches": int(dev_stats["kernel_launches"] * a.steps),
         "fallback_rows_per_step": int(dev_stats["n_fallback"]), "fused_gather_verified": gather_ok,
+        "gather": (a.gather if world > 1 else None),
         "clocks": clocks,
     }
     return line

@@ -139,7 +139,11 @@ int sknnr_index_destroy(sknnr_index *index);
  *   decimals   RawKNNRegressor.DISTANCE_PRECISION_DECIMALS (ref:src/sknnr/_base.py:102).
  *   out_dist   [n_q, k] f64 or NULL;  out_idx [n_q, k] i64 or NULL
  *   weights    SKNNR_W_*; out_pred [n_q, n_out] f64 (required unless SKNNR_W_NONE)
- *   stream     cudaStream_t as void* (only with SKNNR_DEVICE_PTRS; else ignored)          */
+ *   stream     cudaStream_t as void* (only with SKNNR_DEVICE_PTRS; else ignored)
+ * Without SKNNR_DEVICE_PTRS the call is synchronous and every pointer may be a pageable host,
+ * page-locked host or device pointer (unified addressing; a peer GPU's memory mapped with
+ * sknnr_ipc_open included): device-resident X is read in place, results bound for device memory
+ * leave each chunk as one copy-engine transfer on the chunk's stream.                          */
 int sknnr_kneighbors(sknnr_index *index, const void *X, int32_t x_dtype, int64_t n_q,
                      int64_t ldx, int64_t row_offset, int32_t k, uint32_t flags,
                      int32_t decimals, double *out_dist, int64_t *out_idx, int32_t weights,

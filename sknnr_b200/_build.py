@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libsknnr_b200.so"
 SOURCES = ["api.cu", "search_simt.cu", "search_tc.cu", "refine.cu", "project.cu", "hamming.cu", "forest.cu", "raster.cu", "misc.cu"]
-HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "sknnr_b200.h")]
+HEADERS = ["common.cuh", "kernels.h", "tc_common.cuh", os.path.join("..", "..", "include", "sknnr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas=-v", *os.environ.get("SK_NVCC_EXTRA", "").split(),

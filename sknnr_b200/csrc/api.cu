@@ -156,6 +156,18 @@ bool is_pageable(const void *p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
+// true for device (or managed) memory: such an X needs no copy in, such outputs are reached by a
+// device-to-device (possibly peer, over NVLink) copy
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
 template <typename T>
 struct PinBuf {
     T *p = nullptr;
@@ -974,6 +986,11 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     const int cols = transformed ? ix->d_out : ix->d_in;
     if (ldx < cols) return fail(SKNNR_EINVAL, "ldx smaller than the number of features");
     const size_t esz = x_dtype == SKNNR_F32 ? 4 : 8;
+    // A synchronous call takes any mix of host and device pointers (unified addressing): device
+    // resident X is read in place, and results bound for device memory - this GPU's or a peer's
+    // mapped through sknnr_ipc_open - leave each chunk as one copy-engine transfer on the chunk's
+    // slot stream, under the kernels of the following chunks.
+    if (!dev_ptrs && !x_on_device && is_device_ptr(X)) x_on_device = true;
 
     cudaStream_t user_stream = dev_ptrs ? (cudaStream_t)stream : nullptr;
     CallGuard guard(ix, user_stream);
@@ -1049,12 +1066,12 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             if (stage_in) {
                 CK(s.h_x.reserve((size_t)rows * cols * esz));
                 parallel_copy_rows(s.h_x.p, (size_t)cols * esz, src, (size_t)ldx * esz, (size_t)cols * esz, rows);
-                CK(cudaMemcpyAsync(s.x.p, s.h_x.p, (size_t)rows * cols * esz, cudaMemcpyHostToDevice, s.stream));
+                CK(cudaMemcpyAsync(s.x.p, s.h_x.p, (size_t)rows * cols * esz, cudaMemcpyDefault, s.stream));
             } else if (ldx == cols) {
-                CK(cudaMemcpyAsync(s.x.p, src, (size_t)rows * cols * esz, cudaMemcpyHostToDevice, s.stream));
+                CK(cudaMemcpyAsync(s.x.p, src, (size_t)rows * cols * esz, cudaMemcpyDefault, s.stream));
             } else {
                 CK(cudaMemcpy2DAsync(s.x.p, (size_t)cols * esz, src, (size_t)ldx * esz, (size_t)cols * esz,
-                                     (size_t)rows, cudaMemcpyHostToDevice, s.stream));
+                                     (size_t)rows, cudaMemcpyDefault, s.stream));
             }
             ix->stats.h2d_bytes += rows * cols * (int64_t)esz;
             dX = s.x.p;
@@ -1087,7 +1104,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
                     s.owed.push_back({dst, hb.p, bytes});
                 }
                 ix->stats.d2h_bytes += (int64_t)bytes;
-                return cudaMemcpyAsync(to, src, bytes, cudaMemcpyDeviceToHost, s.stream);
+                return cudaMemcpyAsync(to, src, bytes, cudaMemcpyDefault, s.stream);
             };
             if (out_dist) CK(deliver(out_dist + r0 * k, o_dist, (size_t)rows * k * 8, stage_dist, s.h_dist));
             if (out_idx) CK(deliver(out_idx + r0 * k, o_idx, (size_t)rows * k * 8, stage_idx, s.h_idx));
