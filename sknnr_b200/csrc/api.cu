@@ -47,7 +47,7 @@ struct Options {
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
     int64_t tc_streams = 0;     // tensor engine: candidate streams per query (0 = automatic, else 1 or 2)
     int64_t host_slots = 8;     // chunks of a host-buffer call in flight (1..8)
-    int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = off)
+    int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = default)
     int64_t host_threads = 0;   // workers that stage pageable host buffers (0 = automatic)
     int64_t stage_rows = 1 << 19; // rows per chunk of a call whose buffers are pageable
 } g_opt;
@@ -717,7 +717,8 @@ int sknnr_index_create(const double *fit_z, int64_t n_ref, int32_t d_out, const 
     ix->kc_tot = k_tot / 8;
     ix->n_rtiles_tc = (int)((n_ref + TC_N - 1) / TC_N);
     ix->tc_nstage = search_tc_pick_config(ix->kc_tot);
-    ix->tensor_ok = ix->tc_nstage != 0 && std::isfinite(r2max);
+    // (below a thousand plots a tile pass is a handful of jobs: the FP32 engine is the better filter)
+    ix->tensor_ok = ix->tc_nstage != 0 && std::isfinite(r2max) && n_ref >= 1024;
     if (e == cudaSuccess && ix->tensor_ok) {
         int ex = 0;
         if (r2max > 0.0) {

@@ -443,6 +443,9 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
             float *gcol = buf_s + col;
 #pragma unroll
             for (int g = 0; g < TC_GROUPS; ++g) gcol[g * LD] = SK_INF_F;   // buf_i follows buf_s
+            // (few sampled tiles: a group is an octet of columns instead of a chunk, so that even a
+            // reference set of a few hundred plots fills more than KC groups)
+            const bool fine = n_seed * CH < TC_GROUPS;
             for (; t < n_seed; ++t) {
                 const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
                 const int g0 = (t * CH) & (TC_GROUPS - 1);
@@ -450,8 +453,19 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
                                aempty_a0 + 8u * sl, lane,
                                [&](const uint32_t (&r)[32], auto ic) {
                                    constexpr int c = decltype(ic)::value;
-                                   float *g = gcol + (g0 + c) * LD;
-                                   *g = fminf(*g, tc_min32(r));
+                                   if (!fine) {
+                                       float *g = gcol + (g0 + c) * LD;
+                                       *g = fminf(*g, tc_min32(r));
+                                   } else {
+#pragma unroll
+                                       for (int o = 0; o < 4; ++o) {
+                                           float m = __uint_as_float(r[8 * o]);
+#pragma unroll
+                                           for (int e = 1; e < 8; ++e) m = fminf(m, __uint_as_float(r[8 * o + e]));
+                                           float *g = gcol + (((t * CH + c) * 4 + o) & (TC_GROUPS - 1)) * LD;
+                                           *g = fminf(*g, m);
+                                       }
+                                   }
                                });
             }
             float gm[TC_GROUPS];
@@ -478,7 +492,8 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
         constexpr uint32_t ES = LD * 32;
         uint32_t pr = c4;            // offset of this thread's next free candidate slot (4 * col + count * LD * 4)
         uint32_t pqo = 8u * c4;      // offset of its next free pending-queue entry (32 * col + count * LD * 32)
-        int since_drain = 2;   // countdown to an extra resolution (the first one comes early)
+        int since_drain = 1;   // countdown to an extra resolution (the first one right after the first job)
+        const int early_tiles = max(64, n_rtiles >> 3);
         for (; t < n_seq; ++t) {
             const int j = t * MT + h, sl = j & (TC_SLOTS - 1);
             const int idb = (t - n_seed) * TC_N + p * CH * 32;   // warp-uniform, like t and p
@@ -503,6 +518,10 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
             bool now;
             if constexpr (CAPE >= 4 && NS == 2) {
                 now = (((t - n_seed) & (DRAIN_EVERY - 1)) == DRAIN_EVERY - 1) | (--since_drain == 0);
+                // (the first tiles of the main pass - all of them on a small reference set - also look
+                // at the queues themselves: there the thresholds move fast and a warp-wide vote per job,
+                // 3.6 % of the kernel when it is paid on every tile, buys 5 - 10x fewer uncertified rows)
+                if ((t - n_seed) < early_tiles) now |= __any_sync(SK_FULL, pqo >= (uint32_t)(CAPE - 1) * ES);
             } else {
                 // (one stream of four chunks per job, or queues of two octets: a period would overflow
                 // the queues, so a lane with a parked octet makes its warp resolve at once)
@@ -590,9 +609,18 @@ int search_tc_pick_config(int kc_tot) {
 }
 
 // sampled tiles of the seeding pass (0 = no seeding: too few references for it to pay)
+// The kernel starts with infinite thresholds, and a pass that starts cold parks far more octets than
+// its queues hold (dropped octets cost certificates), so the sample is never switched off: small
+// reference sets are pre-scanned completely (they are cheap), mid-sized ones every second tile.
+int search_tc_seed_stride(int n_rtiles, int seed_stride) {
+    if (seed_stride <= 0) seed_stride = 4;
+    if (n_rtiles < 64) return 1;
+    if (n_rtiles < 192) return seed_stride < 2 ? seed_stride : 2;
+    return seed_stride;
+}
 int search_tc_seed_tiles(int n_rtiles, int seed_stride) {
-    if (seed_stride <= 0 || n_rtiles < 64) return 0;
-    return (n_rtiles + seed_stride - 1) / seed_stride;
+    const int st = search_tc_seed_stride(n_rtiles, seed_stride);
+    return (n_rtiles + st - 1) / st;
 }
 
 template <int KC, int MT, int NS, int CAP, int CAPE, int J, bool DBG>
@@ -607,7 +635,8 @@ static cudaError_t launch_tc_dbg(const __half *qimg, const __half *rimg, int kc_
     const long long n_qtiles = (n_q + Cfg::QT - 1) / Cfg::QT;
     const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride);
     search_tc_kernel<KC, MT, NS, CAP, CAPE, J, DBG><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
-        qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, seed_stride, n_q, cand_idx, cand_thr, g_tc_debug);
+        qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, search_tc_seed_stride(n_rtiles, seed_stride), n_q, cand_idx,
+        cand_thr, g_tc_debug);
     return cudaGetLastError();
 }
 

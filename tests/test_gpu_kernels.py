@@ -896,16 +896,16 @@ def test_raster_nodata_is_compared_in_the_band_dtype():
     assert (idx[:, masked] == -1).all() and (idx[:, ~masked] >= 0).all()
 
 
-@pytest.mark.parametrize("k", [7, 10])
-def test_tensor_engine_certifies_nearly_every_row_and_stays_selected(k):
+@pytest.mark.parametrize(("k", "n_ref"), [(7, 20_000), (10, 20_000), (7, 2_000), (7, 5_000), (7, 9_000)])
+def test_tensor_engine_certifies_nearly_every_row_and_stays_selected(k, n_ref):
     """Both stream layouts of the tensor engine (k <= 7: two streams, larger k: one) must certify
     all but a few per cent of the rows of an ordinary workload - otherwise the library demotes the
     index to the 10x slower FP32 engine - and a self-query (k + 1) must not spoil later calls."""
     from sknnr_b200._engine import KNNIndex
 
     rng = np.random.default_rng(12)
-    R = rng.standard_normal((20_000, 32))
-    y = rng.standard_normal((20_000, 2))
+    R = rng.standard_normal((n_ref, 32))
+    y = rng.standard_normal((n_ref, 2))
     Q = rng.standard_normal((40_000, 32))
     ix = KNNIndex(R, None, None, None, y)
     ix.query(None, k, exclude_self=True)
