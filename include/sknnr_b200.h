@@ -100,7 +100,8 @@ int sknnr_device_count(int *count);
  *   "tc_streams"  0/1/2 candidate streams per query of the tensor engine (default 0 = two
  *                 streams of 8 while k (+1) <= 8, else one of 16)
  *   "tc_seed_stride" 0..64: the tensor engine pre-scans one reference tile in n to seed its
- *                 thresholds (default 4; 0 = off)
+ *                 thresholds (default 4; 0 = the default too: the engine never starts cold, and
+ *                 reference sets below 192 / 64 tiles are pre-scanned at stride <= 2 / 1)
  *   "host_threads" workers that stage pageable caller buffers through page-locked slot buffers
  *                 (default 0 = min(16, cores / 2); read when the first pageable call starts them)
  *   "stage_rows"  rows per chunk of a call with pageable buffers (default 1<<19)

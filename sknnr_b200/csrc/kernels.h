@@ -43,7 +43,8 @@ size_t search_tc_smem_bytes(int kc_tot, int nstage, int ns, int cape);
 int search_tc_pick_config(int kc_tot);   // ring stages | pending-queue depth << 8; 0: the shape does not fit
 int search_tc_seed_tiles(int n_rtiles, int seed_stride);
 extern int g_tc_debug;  // timing experiments: bit 0 = skip the hit path (wrong results)
-// seed_stride: one reference tile in seed_stride is pre-scanned to seed the thresholds (0 = off)
+// seed_stride: one reference tile in seed_stride is pre-scanned to seed the thresholds (0 = the
+// default, 4; small reference sets use a denser stride, see search_tc_seed_stride)
 cudaError_t launch_search_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles,
                              long long n_q, int ns, int config, int seed_stride, int *cand_idx,
                              float *cand_thr, cudaStream_t st);

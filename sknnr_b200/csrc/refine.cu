@@ -187,8 +187,7 @@ refine2_kernel(RefineArgs a, FinishParams fp) {
     const int my_c = hl < a.kc ? a.cand_idx[q * a.kc + hl] : -1;
     int id = 0x7fffffff;
     double d2 = SK_INF_D;
-#pragma unroll 4
-    for (int i = 0; i < a.kc; ++i) {
+    auto take = [&](int i) {
         const int c = __shfl_sync(SK_FULL, my_c, i, 16);
         SK_CHECK(c >= -1 && c < a.n_ref);
         const bool have = c >= 0 && c < a.n_ref;
@@ -199,6 +198,30 @@ refine2_kernel(RefineArgs a, FinishParams fp) {
             id = c;
             d2 = acc;
         }
+    };
+    // The tensor engine hands over two half lists of 8 slots, each filled from its first slot and
+    // padded with -1 (typically 4 + 4 entries under the joint threshold): only the occupied prefix
+    // of the two halves is visited, slot i and slot 8 + i per step.  Anything else: all slots.
+    const unsigned vm = __ballot_sync(SK_FULL, my_c >= 0);
+    int n_step = 8;
+    if (a.kc == 16) {
+        int worst = 0;
+        bool prefix = true;
+#pragma unroll
+        for (int hlf = 0; hlf < 4; ++hlf) {
+            const unsigned m = (vm >> (8 * hlf)) & 0xffu;
+            const int n = __popc(m);
+            prefix = prefix && (m == ((1u << n) - 1u));
+            worst = max(worst, n);
+        }
+        if (prefix) n_step = worst;
+        for (int i = 0; i < n_step; ++i) {
+            take(i);
+            take(8 + i);
+        }
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < a.kc; ++i) take(i);
     }
     double qn = 0.0;
     for (int k = hl; k < a.d; k += 16) {
