@@ -76,6 +76,8 @@ def parse_args():
     ap.add_argument("--tc-debug", type=int, default=0)
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--host-slots", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library option for an experiment (sknnr_set_option), repeatable")
     ap.add_argument("--gather", default="auto", choices=["auto", "fused", "copy"],
                     help="N > 1: how a rank's rows reach rank 0's arrays - fused = the finishing kernels store "
                          "over NVLink; copy = per-chunk copy-engine peer copies on the chunk's stream")
@@ -459,6 +461,9 @@ def run_ours(a, rank, world, local_rank):
             L.set_option(name, v)
     if a.tc_seed_stride >= 0:
         L.set_option("tc_seed_stride", a.tc_seed_stride)
+    for item in a.opt:
+        name, _, v = item.partition("=")
+        L.set_option(name, int(v))
     stream = torch.cuda.current_stream(dev)
 
     def barrier():

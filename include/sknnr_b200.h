@@ -102,6 +102,8 @@ int sknnr_device_count(int *count);
  *   "tc_seed_stride" 0..64: the tensor engine pre-scans one reference tile in n to seed its
  *                 thresholds (default 4; 0 = the default too: the engine never starts cold, and
  *                 reference sets below 192 / 64 tiles are pre-scanned at stride <= 2 / 1)
+ *   "tail_spread" 0/1 the second (FP32) stage of the cascade deals its few rows out over all SMs,
+ *                 one warp of 32 rows at a time (default 1; 0 = one CTA per 384 rows)
  *   "host_threads" workers that stage pageable caller buffers through page-locked slot buffers
  *                 (default 0 = min(16, cores / 2); read when the first pageable call starts them)
  *   "stage_rows"  rows per chunk of a call with pageable buffers (default 1<<19)

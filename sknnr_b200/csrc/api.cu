@@ -47,6 +47,7 @@ struct Options {
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
     int64_t tc_streams = 0;     // tensor engine: candidate streams per query (0 = automatic, else 1 or 2)
     int64_t host_slots = 8;     // chunks of a host-buffer call in flight (1..8)
+    int64_t tail_spread = 1;    // second stage: deal the uncertified rows out over all SMs (0: one CTA per 384 rows)
     int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = default)
     int64_t host_threads = 0;   // workers that stage pageable host buffers (0 = automatic)
     int64_t stage_rows = 1 << 19; // rows per chunk of a call whose buffers are pageable
@@ -315,6 +316,7 @@ struct IndexBase {
     int exact_grid = 0;
     sknnr_stats stats{};
     int n_sm = 148;
+    bool spread_tail = true;   // run_chunk: deal the second stage's rows out over all SMs (set per chunk by the caller)
     long long n_exact_rows = 0;     // rows that reached the exhaustive kernel (last call)
     long long chunk_rows_seen = 0;  // adaptive engine choice: rows / first-stage failures seen
     long long chunk_fb_seen = 0;
@@ -576,6 +578,8 @@ int sknnr_set_option(const char *name, int64_t value) {
     } else if (!strcmp(name, "stage_rows")) {
         if (value < 1024) return fail(SKNNR_EINVAL, "stage_rows must be >= 1024");
         g_opt.stage_rows = (value + 1023) / 1024 * 1024;
+    } else if (!strcmp(name, "tail_spread")) {
+        g_opt.tail_spread = value ? 1 : 0;
     } else if (!strcmp(name, "tc_seed_stride")) {
         if (value < 0 || value > 64) return fail(SKNNR_EINVAL, "tc_seed_stride must be 0..64");
         g_opt.tc_seed_stride = value;
@@ -926,7 +930,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     // stage 2 (or the only fast stage): FP32 SIMT engine
     if (g_opt.timing && !use_tc) CK(s.mark(st));
     CK(launch_search_simt(s.qimg.p, ix->d_rimg, ix->dpad, ix->n_rtiles, rows, kc, s.cand_idx.p,
-                          s.cand_thr.p, stage2_count, st));
+                          s.cand_thr.p, stage2_count, g_opt.tail_spread && ix->spread_tail ? ix->n_sm : 0, st));
     if (g_opt.timing && !use_tc) CK(s.mark(st));
     FinishParams fp2 = fp;
     fp2.row_map = use_tc ? s.fb.p + 1 : nullptr;
@@ -1089,6 +1093,9 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             if (out_idx) { CK(s.o_idx.reserve((size_t)rows * k)); o_idx = s.o_idx.p; }
             if (weights != SKNNR_W_NONE) { CK(s.o_pred.reserve((size_t)rows * ix->n_out)); o_pred = s.o_pred.p; }
         }
+        // the last chunk's second stage has nothing to hide under: it is dealt out over all SMs; the
+        // others keep to a few SMs, which costs the following chunk's tensor kernel less
+        ix->spread_tail = r0 + rows >= n_q;
         rc = run_chunk(ix, s, dX, x_dtype == SKNNR_F32, dld, transformed, rows, row_offset + r0, k,
                        flags, decimals, weights, o_dist, o_idx, o_pred, check_finite);
         if (rc != SKNNR_OK) return rc;
@@ -1257,6 +1264,7 @@ int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype,
                            double *o_pred) -> int {
                            if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen)
                                ix->tensor_demoted[ix->ns_in_use] = true;
+                           ix->spread_tail = false;
                            return run_chunk(ix, s, xc, x_dtype == SKNNR_F32, ix->d_in, false, nv, row0, k, flags,
                                             decimals, weights, o_dist, o_idx, o_pred);
                        });

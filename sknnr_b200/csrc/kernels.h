@@ -33,7 +33,9 @@ size_t search_simt_smem_bytes(int dpad, int kc, int nstage);
 int search_simt_pick_stages(int dpad, int kc);
 cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, int n_rtiles,
                                long long n_q, int kc, int *cand_idx, float *cand_thr,
-                               const int *n_rows_dev, cudaStream_t st);
+                               const int *n_rows_dev, int spread_ctas, cudaStream_t st);
+// n_rows_dev != null: compacted launch, the row count is read on the device; spread_ctas > 0 then
+// deals the rows out over up to that many CTAs in units of one warp (0: one CTA per 384 rows)
 
 // ---- search_tc.cu (tcgen05 / TMEM engine) ------------------------------------------------
 // Two candidate-stream layouts: ns = 2 (two lists of up to 7 per query, k (+1) <= 7) and ns = 1 (one

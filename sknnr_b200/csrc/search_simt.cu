@@ -33,11 +33,24 @@ template <int KC>
 __global__ void __launch_bounds__(SEARCH_THREADS, 1)
 search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int dpad,
                    int n_rtiles, int nstage, long long n_q, int *__restrict__ cand_idx,
-                   float *__restrict__ cand_thr, const int *__restrict__ n_rows_dev) {
-    if (n_rows_dev) {  // compacted launch: CTAs beyond the device-side row count have no work
+                   float *__restrict__ cand_thr, const int *__restrict__ n_rows_dev, int spread_ctas) {
+    long long qtile = blockIdx.x;
+    int wpc = NCOMPUTE_WARPS, woff = 0;   // warps of this CTA that have rows, first warp slot of the tile it serves
+    if (n_rows_dev) {
+        // Compacted launch (second stage of the cascade): the row count is only known on the device and is
+        // usually a fraction of a percent of the chunk.  One CTA per 384 rows would leave most SMs idle for
+        // a full scan of the reference set, so the rows are dealt out in units of one warp (32 rows) over
+        // up to spread_ctas CTAs: CTA b serves wpc consecutive warp slots of a query tile, wpc the smallest
+        // divisor of 12 that covers the rows, and its other warps retire at once.
         const long long n_dev = *n_rows_dev;
-        if ((long long)blockIdx.x * QTILE >= n_dev) return;
         n_q = min(n_q, n_dev);
+        const long long n_w = (n_q + 31) / 32;
+        const long long per = spread_ctas > 0 ? (n_w + spread_ctas - 1) / spread_ctas : NCOMPUTE_WARPS;
+        wpc = per <= 1 ? 1 : per <= 2 ? 2 : per <= 3 ? 3 : per <= 4 ? 4 : per <= 6 ? 6 : NCOMPUTE_WARPS;
+        const long long w0 = (long long)blockIdx.x * wpc;
+        if (w0 >= n_w) return;
+        qtile = w0 / NCOMPUTE_WARPS;
+        woff = (int)(w0 - qtile * NCOMPUTE_WARPS);
     }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int rtile_floats = (dpad + 1) * RTILE;
@@ -53,13 +66,14 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
     uint64_t *qbar = empty + nstage;
 
     // (shuffle: the compiler then knows `warp` is warp-uniform and keeps what derives from it in uniform registers)
-    const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0);
+    const int warp0 = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0);
+    const int warp = warp0 + woff;   // warp slot of the query tile
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NCOMPUTE_WARPS);
+            mbar_init(&empty[s], wpc);
         }
         mbar_init(qbar, 1);
         fence_mbar_init();
@@ -69,8 +83,7 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
         list_i[e] = -1;
     }
     __syncthreads();
-
-    const long long qtile = blockIdx.x;
+    if (warp0 >= wpc) return;
 
     // ---------------- TMA producer: lane 0 of warp 0, inline ----------------
     // Tile t+nstage-2 is requested at the top of iteration t, so the slot it overwrites was
@@ -238,7 +251,7 @@ int search_simt_pick_stages(int dpad, int kc) {
 template <int KC>
 static cudaError_t launch_kc(const float *qimg, const float *rimg, int dpad, int n_rtiles,
                              long long n_q, int *cand_idx, float *cand_thr, const int *n_rows_dev,
-                             cudaStream_t st) {
+                             int spread_ctas, cudaStream_t st) {
     const int nstage = search_simt_pick_stages(dpad, KC);
     if (nstage == 0) return cudaErrorInvalidValue;
     const size_t smem = search_simt_smem_bytes(dpad, KC, nstage);
@@ -246,19 +259,20 @@ static cudaError_t launch_kc(const float *qimg, const float *rimg, int dpad, int
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const long long n_qtiles = (n_q + QTILE - 1) / QTILE;
-    search_simt_kernel<KC><<<(unsigned)n_qtiles, SEARCH_THREADS, smem, st>>>(
-        qimg, rimg, dpad, n_rtiles, nstage, n_q, cand_idx, cand_thr, n_rows_dev);
+    const long long grid = n_rows_dev && spread_ctas > n_qtiles ? spread_ctas : n_qtiles;
+    search_simt_kernel<KC><<<(unsigned)grid, SEARCH_THREADS, smem, st>>>(
+        qimg, rimg, dpad, n_rtiles, nstage, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas);
     return cudaGetLastError();
 }
 
 cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, int n_rtiles,
                                long long n_q, int kc, int *cand_idx, float *cand_thr,
-                               const int *n_rows_dev, cudaStream_t st) {
+                               const int *n_rows_dev, int spread_ctas, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
     switch (kc) {
-        case 8: return launch_kc<8>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, st);
-        case 16: return launch_kc<16>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, st);
-        case 32: return launch_kc<32>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, st);
+        case 8: return launch_kc<8>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, st);
+        case 16: return launch_kc<16>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, st);
+        case 32: return launch_kc<32>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, st);
         default: return cudaErrorInvalidValue;
     }
 }
