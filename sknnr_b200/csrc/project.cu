@@ -47,22 +47,37 @@ project_kernel(const TX *__restrict__ X, long long ldx, long long n_q, int d_in,
         const int dr = PROJ_THREADS / d_in, dc = PROJ_THREADS - dr * d_in;
         int r = threadIdx.x / d_in, c = threadIdx.x - r * d_in;
         const bool z_here = !proj && z64 && d_out == d_in;
-        for (int e = threadIdx.x; e < PROJ_THREADS * d_in; e += PROJ_THREADS) {
-            double v = 0.0;
-            if (r < rows) {
-                v = (double)X[(q0 + r) * ldx + c];
-                // NaN / inf anywhere in the query block: the caller raises scikit-learn's ValueError
-                if (nonfinite && !isfinite(v)) *nonfinite = 1;
-                if (center) v -= center[c];
-                if (scale) v /= scale[c];
-                if (z_here) z64[(q0 + r) * d_out + c] = v;
+        // (every thread makes exactly d_in passes; the loads of eight passes are issued together, ahead
+        // of the divisions, so that eight rows' worth of HBM requests are in flight per thread)
+        constexpr int UNR = 8;
+        for (int e0 = 0; e0 < d_in; e0 += UNR) {
+            double v[UNR];
+            int rr[UNR], cc[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                rr[u] = r;
+                cc[u] = c;
+                const bool have = e0 + u < d_in && r < rows;
+                v[u] = have ? (double)X[(q0 + r) * ldx + c] : 0.0;
+                r += dr;
+                c += dc;
+                if (c >= d_in) {
+                    c -= d_in;
+                    ++r;
+                }
             }
-            xs[r * xs_ld + c] = v;
-            r += dr;
-            c += dc;
-            if (c >= d_in) {
-                c -= d_in;
-                ++r;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (e0 + u >= d_in) break;
+                double w = v[u];
+                if (rr[u] < rows) {
+                    // NaN / inf anywhere in the query block: the caller raises scikit-learn's ValueError
+                    if (nonfinite && !isfinite(w)) *nonfinite = 1;
+                    if (center) w -= center[cc[u]];
+                    if (scale) w /= scale[cc[u]];
+                    if (z_here) z64[(q0 + rr[u]) * d_out + cc[u]] = w;
+                }
+                xs[rr[u] * xs_ld + cc[u]] = w;
             }
         }
     }
