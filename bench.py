@@ -571,6 +571,7 @@ def bench_c3(a, rank, world, local_rank, dev, stream, lib, L, KNNIndex, barrier,
     step_device()
     barrier()
     dev_stats = index.stats()
+    cascade = index.cascade_counts()
     search_ms = dev_stats["search_ms"]
 
     # out-of-band verification of the fused gather: every rank repeats its block into local memory and
@@ -690,7 +691,8 @@ def bench_c3(a, rank, world, local_rank, dev, stream, lib, L, KNNIndex, barrier,
                       note=TC_NOTE),
         "hbm": hbm, "cpu_baseline": cpu, "e2e": e2e, "e2e_estimator": e2e_est,
         "gpu_launches": int(dev_stats["kernel_launches"] * a.steps),
-        "fallback_rows_per_step": int(dev_stats["n_fallback"]), "fused_gather_verified": gather_ok,
+        "fallback_rows_per_step": int(dev_stats["n_fallback"]), "cascade_rows_per_step": cascade,
+        "fused_gather_verified": gather_ok,
         "gather": (a.gather if world > 1 else None),
         "clocks": clocks,
     }
@@ -737,6 +739,7 @@ def bench_c5(a, rank, world, local_rank, dev, stream, lib, L, barrier, timed, pe
     step()
     barrier()
     st = index.stats()
+    cascade = index.cascade_counts()
     rec = None
     if rank == 0:
         # parity on a sample, outside the timed region: the first rows of rank 0 against the oracle
@@ -764,7 +767,8 @@ def bench_c5(a, rank, world, local_rank, dev, stream, lib, L, barrier, timed, pe
                "ms_per_step": ms / steps, "scaling": "strong", "rows_per_gpu": per,
                "roofline": tensor_roofline(flops, st["search_ms"], n_chunks, peaks, gemm, None, n_q / n_chunks,
                                            TC_NOTE + " (rank 0's launches)"),
-               "fallback_rows_per_step_rank0": int(st["n_fallback"]), "parity_sample_rows": m,
+               "fallback_rows_per_step_rank0": int(st["n_fallback"]), "cascade_rows_per_step_rank0": cascade,
+               "parity_sample_rows": m,
                "gpu_launches": int(st["kernel_launches"] * steps)}
         if not a.no_cpu_baseline and world == 1:
             rec["cpu_baseline"] = cpu_c5(a, Rraw, y, A, k)

@@ -102,6 +102,10 @@ int sknnr_device_count(int *count);
  *   "tc_seed_stride" 0..64: the tensor engine pre-scans one reference tile in n to seed its
  *                 thresholds (default 4; 0 = the default too: the engine never starts cold, and
  *                 reference sets below 192 / 64 tiles are pre-scanned at stride <= 2 / 1)
+ *   "tc_retry"    0/1 after its two-stream layout (k (+1) <= 7) the tensor engine runs a second pass,
+ *                 one stream of 16, over the rows the first pass could not certify, each from the
+ *                 threshold the first pass proved sufficient, before the FP32 engine sees what is
+ *                 left (default 1)
  *   "tail_spread" 0/1 the second (FP32) stage of the cascade deals its few rows out over all SMs,
  *                 one warp of 32 rows at a time (default 1; 0 = one CTA per 384 rows)
  *   "host_threads" workers that stage pageable caller buffers through page-locked slot buffers
@@ -163,6 +167,10 @@ int sknnr_weighted_average(sknnr_index *index, const int64_t *idx, const double 
                            int64_t n_q, int32_t k, double *out_pred);
 
 int sknnr_index_stats(sknnr_index *index, sknnr_stats *out);
+/* Rows of the last call that left each stage of the engine cascade uncertified:
+ * out3[0] after the tensor engine's first pass (= stats.n_fallback), out3[1] rows that reached the
+ * FP32 engine, out3[2] rows that reached the exhaustive float64 kernel.                      */
+int sknnr_index_cascade_counts(sknnr_index *index, int64_t *out3);
 
 /* ---- Hamming index: RFNNRegressor (metric="hamming" over terminal-node IDs) -------------
  * Replaces sklearn's brute Hamming branch + scipy cdist_hamming

@@ -222,6 +222,13 @@ class KNNIndex(_IndexBase):
     _destroy = "sknnr_index_destroy"
     _stats = "sknnr_index_stats"
 
+    def cascade_counts(self) -> dict:
+        """Rows of the last call left uncertified by the tensor engine's first pass, rows that reached the
+        FP32 engine and rows that reached the exhaustive float64 kernel."""
+        out = (C.c_int64 * 3)()
+        L.check(self._lib.sknnr_index_cascade_counts(self._h, out))
+        return {"after_tensor": out[0], "to_fp32": out[1], "to_exact": out[2]}
+
     def __init__(self, fit_z, center=None, scale=None, proj=None, y=None, device=None):
         super().__init__()
         fit_z = _f64(fit_z)

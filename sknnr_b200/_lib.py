@@ -23,7 +23,7 @@ MAX_CODE = 31743
 EXPORTS = [
     "sknnr_last_error", "sknnr_abi_version", "sknnr_device_count", "sknnr_set_option",
     "sknnr_index_create", "sknnr_index_destroy", "sknnr_kneighbors", "sknnr_transform",
-    "sknnr_weighted_average", "sknnr_index_stats", "sknnr_hamming_index_create",
+    "sknnr_weighted_average", "sknnr_index_stats", "sknnr_index_cascade_counts", "sknnr_hamming_index_create",
     "sknnr_hamming_index_destroy", "sknnr_hamming_kneighbors",
     "sknnr_hamming_weighted_average", "sknnr_hamming_index_stats", "sknnr_host_alloc",
     "sknnr_host_free", "sknnr_measure_fp32_peak", "sknnr_forest_create", "sknnr_forest_destroy",
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.sknnr_transform.argtypes = [vp, vp, i32, i64, i64, vp]
     lib.sknnr_weighted_average.argtypes = [vp, vp, vp, i64, i32, vp]
     lib.sknnr_index_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.sknnr_index_cascade_counts.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.sknnr_hamming_index_create.argtypes = [vp, i64, i32, vp, vp, i32, i32, C.POINTER(vp)]
     lib.sknnr_hamming_index_destroy.argtypes = [vp]
     lib.sknnr_hamming_kneighbors.argtypes = [vp, vp, i64, i64, i64, i32, u32, i32, vp, vp, i32, vp, vp]

@@ -47,6 +47,7 @@ struct Options {
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
     int64_t tc_streams = 0;     // tensor engine: candidate streams per query (0 = automatic, else 1 or 2)
     int64_t host_slots = 8;     // chunks of a host-buffer call in flight (1..8)
+    int64_t tc_retry = 1;       // tensor engine: second pass over the uncertified rows before the FP32 stage
     int64_t tail_spread = 1;    // second stage: deal the uncertified rows out over all SMs (0: one CTA per 384 rows)
     int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = default)
     int64_t host_threads = 0;   // workers that stage pageable host buffers (0 = automatic)
@@ -234,6 +235,8 @@ struct Slot {
     DevBuf<__half> qimg_tc;        // tensor-core engine query image (FP16)
     DevBuf<double> z64c;           // compacted rows of the cascade's second stage
     DevBuf<int> fb2;               // second-stage failures: [0] = count, [1..] = list
+    DevBuf<int> fbm;               // failures of the tensor engine's second pass (stage 1b), same layout
+    DevBuf<float> fb_thr;          // second-pass thresholds of the first-stage failures (order of fb's list)
     DevBuf<uint16_t> codes;        // node codes produced by the device forest walk
     DevBuf<int> ids32;             // node IDs of sknnr_forest_apply
     DevBuf<uint32_t> qimg_h;       // Hamming query image
@@ -253,7 +256,7 @@ struct Slot {
     cudaEvent_t ev_cnt = nullptr;
     std::vector<cudaEvent_t> evs;  // pooled (start, stop) pairs around the search kernels
     size_t ev_used = 0;            // events handed out since the last harvest
-    int *h_fb = nullptr;           // pinned: [0] first-stage, [1] second-stage failures, [2] non-finite flag
+    int *h_fb = nullptr;           // pinned: [0] first-stage, [1] second-stage failures, [2] non-finite flag, [3] rows of the FP32 stage
     bool fb_pending = false;
     long long rows_in_flight = 0;
     DevBuf<int> nonfinite;         // [0] != 0: a query value of the chunk in flight is NaN / inf
@@ -267,7 +270,7 @@ struct Slot {
     struct CopyOut { void *dst; const void *src; size_t bytes; };
     std::vector<CopyOut> owed;
     void release() {
-        x.release(); z64.release(); qimg.release(); qimg_tc.release(); z64c.release(); fb2.release();
+        x.release(); z64.release(); qimg.release(); qimg_tc.release(); z64c.release(); fb2.release(); fbm.release(); fb_thr.release();
         codes.release(); ids32.release(); qimg_h.release(); cand_idx.release();
         cand_thr.release(); cand_cnt.release(); fb.release(); o_dist.release();
         o_idx.release(); o_pred.release();
@@ -318,6 +321,7 @@ struct IndexBase {
     int n_sm = 148;
     bool spread_tail = true;   // run_chunk: deal the second stage's rows out over all SMs (set per chunk by the caller)
     long long n_exact_rows = 0;     // rows that reached the exhaustive kernel (last call)
+    long long n_simt_rows = 0;      // rows that reached the FP32 stage after the tensor engine (last call)
     long long chunk_rows_seen = 0;  // adaptive engine choice: rows / first-stage failures seen
     long long chunk_fb_seen = 0;
 
@@ -346,7 +350,7 @@ struct IndexBase {
             CK(cudaEventCreateWithFlags(&s.ev_stage1, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
             CK(cudaHostAlloc((void **)&s.h_fb, 4 * sizeof(int), cudaHostAllocDefault));
-            s.h_fb[0] = s.h_fb[1] = s.h_fb[2] = 0;
+            s.h_fb[0] = s.h_fb[1] = s.h_fb[2] = s.h_fb[3] = 0;
             CK(s.nonfinite.reserve(1));
             CK(cudaEventCreateWithFlags(&s.ev_last, cudaEventDisableTiming));
             CK(cudaHostAlloc((void **)&s.h_cnt, sizeof(int), cudaHostAllocDefault));
@@ -375,6 +379,7 @@ struct IndexBase {
         if (s.fb_pending) {
             stats.n_fallback += s.h_fb[0];
             n_exact_rows += s.h_fb[1];
+            n_simt_rows += s.h_fb[3];
             chunk_rows_seen += s.rows_in_flight;
             chunk_fb_seen += s.h_fb[0];
             s.fb_pending = false;
@@ -578,6 +583,8 @@ int sknnr_set_option(const char *name, int64_t value) {
     } else if (!strcmp(name, "stage_rows")) {
         if (value < 1024) return fail(SKNNR_EINVAL, "stage_rows must be >= 1024");
         g_opt.stage_rows = (value + 1023) / 1024 * 1024;
+    } else if (!strcmp(name, "tc_retry")) {
+        g_opt.tc_retry = value ? 1 : 0;
     } else if (!strcmp(name, "tail_spread")) {
         g_opt.tail_spread = value ? 1 : 0;
     } else if (!strcmp(name, "tc_seed_stride")) {
@@ -787,11 +794,24 @@ int sknnr_index_stats(sknnr_index *ix, sknnr_stats *out) {
     return SKNNR_OK;
 }
 
+int sknnr_index_cascade_counts(sknnr_index *ix, int64_t *out3) {
+    if (!ix || !out3) return fail(SKNNR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(ix->lock);
+    cudaSetDevice(ix->device);
+    for (auto &s : ix->slots) ix->harvest(s);
+    out3[0] = ix->stats.n_fallback;
+    out3[1] = ix->n_simt_rows;
+    out3[2] = ix->n_exact_rows;
+    return SKNNR_OK;
+}
+
 // one chunk of a Euclidean-space query, everything enqueued on s.stream.
 //
 // Engine cascade (every stage is a filter whose result the float64 refine kernel certifies):
-//   1. tensor (tcgen05, TF32 scores, eps 2^-10)        -> refine -> uncertified rows list L1
-//   2. SIMT   (FP32 FFMA2 scores, eps ~(2d+8) 2^-24) on the compacted rows of L1 -> refine -> L2
+//   1. tensor (tcgen05, FP16 operands, eps 2^-10)      -> refine -> uncertified rows list L1
+//   1b. tensor again on the compacted rows of L1, each row from the threshold its first pass proved
+//       sufficient (no seeding, nothing dropped)       -> refine -> L1b
+//   2. SIMT   (FP32 FFMA2 scores, eps ~(2d+8) 2^-24) on the compacted rows of L1b -> refine -> L2
 //   3. exact  (float64, exhaustive) on L2
 // With engine = SIMT stage 1 is skipped (L1 = all rows); with engine = EXACT only stage 3 runs.
 static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_t ldx, bool transformed,
@@ -893,14 +913,23 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     ra.qn_limit = INFINITY;
 
     const int *stage2_count = nullptr;  // null: stage 2 covers every row of the chunk
+    const int *stage2_list = nullptr;   // chunk rows of the compacted stage-2 rows
     if (use_tc) {
         if (g_opt.timing) CK(s.mark(st));
         // two candidate streams per query while k (+1) <= 7 (twice the scanner warps), else one
         int ns = kk <= 7 ? 2 : 1;   // a stream's list keeps at most 7 (ns = 2) / 15 (ns = 1) candidates
         if (g_opt.tc_streams == 1) ns = 1;
         CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, ns, ix->tc_nstage,
-                            (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, st));
+                            (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, nullptr, nullptr, st));
         if (g_opt.timing) CK(s.mark(st));
+        // (a second pass only pays after the two-stream layout: its joint list holds 11 candidates, the
+        // second pass's single stream 15 - the one-stream layout would meet the same 15 again)
+        const bool retry = g_opt.tc_retry != 0 && ns == 2;
+        if (retry) {
+            CK(s.fb_thr.reserve((size_t)rows));
+            CK(s.fbm.reserve((size_t)rows + 1));
+            CK(cudaMemsetAsync(s.fbm.p, 0, sizeof(int), st));
+        }
         ra.kc = 16;
         ra.n_thr = ns;
         ra.z64 = s.z64.p;
@@ -911,6 +940,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
         ra.qn_limit = 0.99 * (32752.0 / ix->tc_sigma) * (32752.0 / ix->tc_sigma);
         ra.fb_count = s.fb.p;
         ra.fb_list = s.fb.p + 1;
+        ra.fb_thr = retry ? s.fb_thr.p : nullptr;
         ra.n_rows_dev = nullptr;
         ra.row_map = nullptr;
         CK(launch_refine(ra, fp, st));
@@ -918,13 +948,44 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
         CK(cudaEventRecord(s.ev_stage1, st));
         CK(cudaStreamWaitEvent(s.tail_stream, s.ev_stage1, 0));
         st = s.tail_stream;
-        // stage 2 input: gather the uncertified rows and rebuild their FP32 query image
         CK(s.z64c.reserve((size_t)rows * ix->d_out));
-        CK(launch_gather_rows(s.z64.p, ix->d_out, s.fb.p + 1, s.fb.p, rows, s.z64c.p, st));
+        const int *list = s.fb.p + 1, *count = s.fb.p;
+        if (retry) {
+            // stage 1b: the same engine once more over the uncertified rows alone, every row starting from
+            // the threshold its first pass proved sufficient (retry_threshold): nothing is parked or
+            // dropped on the way, the pass costs a few CTAs, and the FP32 engine is left with the rows
+            // that have more than 15 references inside the FP16 error margin of their k-th neighbour.
+            CK(launch_gather_rows(s.z64.p, ix->d_out, list, count, rows, s.z64c.p, st));
+            CK(launch_project(s.z64c.p, 0, ix->d_out, rows, ix->d_out, ix->d_out, ix->dpad, nullptr, nullptr,
+                              nullptr, ix->d_mu, nullptr, nullptr, s.qimg_tc.p, ix->kc_tot, ix->tc_sigma, count,
+                              nullptr, st));
+            // (one stream of 16 whatever the first pass used: what the two-stream layout cannot certify
+            // is mostly rows with more references inside the error margin of the k-th neighbour than
+            // its joint list of 11 holds)
+            CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, 1, ix->tc_nstage,
+                                (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, s.fb_thr.p, count, st));
+            FinishParams fpb = fp;
+            fpb.row_map = list;
+            RefineArgs rb = ra;
+            rb.z64 = s.z64c.p;
+            rb.n_thr = 1;
+            rb.fb_count = s.fbm.p;
+            rb.fb_list = s.fbm.p + 1;
+            rb.fb_thr = nullptr;
+            rb.n_rows_dev = count;
+            rb.row_map = list;
+            CK(launch_refine(rb, fpb, st));
+            ix->stats.kernel_launches += 4;
+            list = s.fbm.p + 1;
+            count = s.fbm.p;
+        }
+        // stage 2 input: gather the uncertified rows and rebuild their FP32 query image
+        CK(launch_gather_rows(s.z64.p, ix->d_out, list, count, rows, s.z64c.p, st));
         CK(launch_project(s.z64c.p, 0, ix->d_out, rows, ix->d_out, ix->d_out, ix->dpad, nullptr, nullptr,
-                          nullptr, ix->d_mu, nullptr, s.qimg.p, nullptr, 0, 1.0, s.fb.p, nullptr, st));
+                          nullptr, ix->d_mu, nullptr, s.qimg.p, nullptr, 0, 1.0, count, nullptr, st));
         ix->stats.kernel_launches += 4;
-        stage2_count = s.fb.p;
+        stage2_count = count;
+        stage2_list = list;
     }
 
     // stage 2 (or the only fast stage): FP32 SIMT engine
@@ -933,7 +994,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
                           s.cand_thr.p, stage2_count, g_opt.tail_spread && ix->spread_tail ? ix->n_sm : 0, st));
     if (g_opt.timing && !use_tc) CK(s.mark(st));
     FinishParams fp2 = fp;
-    fp2.row_map = use_tc ? s.fb.p + 1 : nullptr;
+    fp2.row_map = stage2_list;
     ra.kc = kc;
     ra.n_thr = 1;
     ra.z64 = use_tc ? s.z64c.p : s.z64.p;
@@ -943,6 +1004,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     ra.qn_limit = INFINITY;
     ra.fb_count = s.fb2.p;
     ra.fb_list = s.fb2.p + 1;
+    ra.fb_thr = nullptr;
     ra.n_rows_dev = stage2_count;
     ra.row_map = fp2.row_map;
     CK(launch_refine(ra, fp2, st));
@@ -955,6 +1017,8 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     ix->stats.kernel_launches++;
     CK(cudaMemcpyAsync(&s.h_fb[0], use_tc ? s.fb.p : s.fb2.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&s.h_fb[1], s.fb2.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (stage2_count) CK(cudaMemcpyAsync(&s.h_fb[3], stage2_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    else s.h_fb[3] = 0;
     s.fb_pending = true;
     s.rows_in_flight = use_tc ? rows : 0;
     if (use_tc) {
@@ -1011,6 +1075,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     }
     for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; s.flag_pending = false; }
     ix->stats = sknnr_stats{};
+    ix->n_simt_rows = ix->n_exact_rows = 0;
     ix->stats.n_queries = n_q;
     ix->saw_nonfinite = false;
     ix->chunk_rows_seen = ix->chunk_fb_seen = 0;   // the demotion rule looks at this call's chunks only
@@ -1167,6 +1232,7 @@ static int raster_impl(IX *ix, int d, const void *bands, int32_t x_dtype, int64_
     for (auto &s : ix->slots) CK(ix->finish_slot(s));
     for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; s.flag_pending = false; }
     ix->stats = sknnr_stats{};
+    ix->n_simt_rows = ix->n_exact_rows = 0;
     ix->chunk_rows_seen = ix->chunk_fb_seen = 0;
     if (n_valid_out) *n_valid_out = 0;
     if (n_pix == 0) { guard.ok = true; return SKNNR_OK; }

@@ -396,7 +396,10 @@ __device__ __forceinline__ void finish_query_w(const FinishParams &p, long long 
         // row_scale = max(rowmax, 1); rounded = rint(dist / row_scale * 10^dec) / 10^dec
         double rowmax = __shfl_sync(SK_FULL, dist, p.k - 1, W);  // ascending -> last is max
         double scale = fmax(rowmax, 1.0);
-        double key = (lane < p.k) ? rint((dist / scale) * p.round_scale) / p.round_scale : SK_INF_D;
+        // (lanes past k hold +inf: they divide 1.0 instead, which keeps the whole warp on the division's
+        // fast path - an infinite operand sends all 32 lanes through the slow one)
+        const double dsafe = (lane < p.k) ? dist : 1.0;
+        double key = (lane < p.k) ? rint((dsafe / scale) * p.round_scale) / p.round_scale : SK_INF_D;
         long long diff = (long long)id - row;
         if (diff < 0) diff = -diff;
         // sort by (key, diff, id): fold (diff, id) into one 64-bit secondary key.  ids and
@@ -430,7 +433,7 @@ __device__ __forceinline__ void finish_query_w(const FinishParams &p, long long 
             if (zm)
                 w = (dist == 0.0) ? 1.0 : 0.0;
             else
-                w = 1.0 / dist;
+                w = 1.0 / ((lane < p.k) ? dist : 1.0);   // (padding lanes: fast-path operand, see above)
         }
         if (lane >= p.k) w = 0.0;
         double denom = 0.0;

@@ -49,7 +49,9 @@ extern int g_tc_debug;  // timing experiments: bit 0 = skip the hit path (wrong 
 // default, 4; small reference sets use a denser stride, see search_tc_seed_stride)
 cudaError_t launch_search_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles,
                              long long n_q, int ns, int config, int seed_stride, int *cand_idx,
-                             float *cand_thr, cudaStream_t st);
+                             float *cand_thr, const float *init_thr, const int *n_rows_dev, cudaStream_t st);
+// init_thr != null: second pass - no seeding, row q starts from threshold init_thr[q]; n_rows_dev != null:
+// compacted launch, the row count is read on the device
 
 // ---- refine.cu -------------------------------------------------------------------------
 struct RefineArgs {
@@ -69,6 +71,8 @@ struct RefineArgs {
     double qn_limit;        // rows with |q - mu|^2 >= qn_limit are never certified (FP16 range of the query image)
     int *fb_count;          // number of uncertified queries (device)
     int *fb_list;           // their row numbers (device, capacity n_q)
+    float *fb_thr;          // null, or [capacity n_q]: per uncertified row, the score threshold under which a
+                            // second pass of the same engine has to list every reference (retry_threshold)
     const int *n_rows_dev;  // compacted launch: only the first *n_rows_dev rows exist
     const int *row_map;     // compacted launch: row of the original chunk (goes into fb_list)
 };

@@ -82,6 +82,36 @@ __device__ __forceinline__ double dist2_serial(const double *__restrict__ zq, co
     return p[0];
 }
 
+// sqrt of the sorted squared distances: the padding lanes (+inf) take sqrt(1) instead, which keeps the
+// warp on the square root's fast path; every other value, NaN included, goes through unchanged
+__device__ __forceinline__ double sqrt_padded(double d2) {
+    const bool pad = d2 == SK_INF_D;
+    const double s = sqrt(pad ? 1.0 : d2);
+    return pad ? SK_INF_D : s;
+}
+
+// Threshold (in the engine's scaled approximate-score units) for a second pass of the tensor engine over a
+// row whose first-pass list was not certified.  `kth` is the exact k-th squared distance among the row's
+// first-pass candidates, hence an upper bound of the true one: every reference that can still belong to the
+// top k has approximate score <= (kth - |q|^2 + E) / thr_scale, E = eps_s (|q|^2 + max|r|^2).  A second pass
+// that lists everything below a threshold a hair above that (rounded up to float) finds all of them, and
+// its own certificate  kth' < thr * thr_scale + |q|^2 - E  then holds because kth' <= kth.
+#ifdef SK_RETRY_STATS
+__device__ unsigned long long g_retry_stats[4];
+#endif
+__device__ __forceinline__ float retry_threshold(double kth, double qn, const RefineArgs &a) {
+#ifdef SK_RETRY_STATS
+    atomicAdd(&g_retry_stats[0], 1ull);
+    if (!(kth < SK_INF_D)) atomicAdd(&g_retry_stats[1], 1ull);
+    if (!(qn < a.qn_limit)) atomicAdd(&g_retry_stats[2], 1ull);
+#endif
+    if (!(kth < SK_INF_D)) return SK_INF_F;   // fewer than k candidates so far (or NaN): start cold
+    const double span = qn + a.r2max;
+    double t = (kth - qn + a.eps_s * span) / a.thr_scale;
+    t += 1e-6 * fabs(t) + 1e-9 * span / a.thr_scale;
+    return __double2float_ru(t);
+}
+
 // DJ = ceil(d / 16) for d <= 64 (the query row lives in DJ registers per lane), 0 = any d
 template <int DJ>
 __global__ void __launch_bounds__(REFINE_WARPS * 32)
@@ -159,10 +189,11 @@ refine_kernel(RefineArgs a, FinishParams fp) {
         if (lane == 0) {
             const int pos = atomicAdd(a.fb_count, 1);
             a.fb_list[pos] = a.row_map ? a.row_map[q] : (int)q;
+            if (a.fb_thr) a.fb_thr[pos] = retry_threshold(kth, qn, a);
         }
         return;
     }
-    finish_query(fp, q, sqrt(d2), id, lane);
+    finish_query(fp, q, sqrt_padded(d2), id, lane);
 }
 
 // Two queries per warp, one per 16-lane segment, for lists of <= 16 candidates and d <= 64 (the
@@ -241,10 +272,17 @@ refine2_kernel(RefineArgs a, FinishParams fp) {
     if (live && !ok && hl == 0) {
         const int pos = atomicAdd(a.fb_count, 1);
         a.fb_list[pos] = a.row_map ? a.row_map[q] : (int)q;
+        if (a.fb_thr) a.fb_thr[pos] = retry_threshold(kth, qn, a);
     }
-    finish_query_w<16>(fp, q, sqrt(d2), id, hl, live && ok);
+    finish_query_w<16>(fp, q, sqrt_padded(d2), id, hl, live && ok);
 }
 
+#ifdef SK_RETRY_STATS
+extern "C" void sk_retry_stats(unsigned long long *out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_retry_stats, sizeof(g_retry_stats));
+}
+#endif
 cudaError_t launch_refine(const RefineArgs &a, const FinishParams &fp, cudaStream_t st) {
     if (a.n_q <= 0) return cudaSuccess;
     if (a.kc <= 16 && a.d <= 64) {

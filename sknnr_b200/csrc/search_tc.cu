@@ -278,8 +278,14 @@ template <int KC, int MT, int NS, int CAP, int CAPE, int J, bool DBG>
 __global__ void __launch_bounds__(TcCfg<MT, NS, CAP, CAPE>::THREADS, 1)
 search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rimg, int kc_tot,
                  int n_rtiles, int nstage, int n_seed, int seed_stride, long long n_q,
-                 int *__restrict__ cand_idx, float *__restrict__ cand_thr, int dbg) {
+                 int *__restrict__ cand_idx, float *__restrict__ cand_thr, int dbg,
+                 const float *__restrict__ init_thr, const int *__restrict__ n_rows_dev) {
     using Cfg = TcCfg<MT, NS, CAP, CAPE>;
+    if (n_rows_dev) {   // compacted launch (second pass): only the first *n_rows_dev rows exist
+        const long long n_dev = *n_rows_dev;
+        if ((long long)blockIdx.x * Cfg::QT >= n_dev) return;
+        n_q = min(n_q, n_dev);
+    }
     constexpr int LD = Cfg::LD, EPI_WARPS = Cfg::EPI_WARPS;
     constexpr bool JOINT = NS == 2 && J < 2 * KC;     // J = 2 KC: every stream keeps its own KC-th best
     constexpr int KCP = JOINT ? KC : 0;               // published scores per thread
@@ -419,7 +425,15 @@ search_tc_kernel(const __half *__restrict__ qimg, const __half *__restrict__ rim
         const int h = (warp >> 2) % MT;
         const int qslot = h * TC_M + (warp & 3) * 32 + lane;   // query within the CTA = TMEM lane of M tile h
         const uint32_t tlane = tmem_base + (((uint32_t)((warp & 3) * 32)) << 16) + (uint32_t)(p * CH * 32);
+        // Second pass over the rows the first one could not certify: every row comes with a threshold
+        // just above what its top k needs (refine.cu, retry_threshold), so the lists end up holding
+        // exactly the references below it and nothing is dropped on the way.  No seeding then; rows
+        // past the end take -inf (no hits).
         float thr = SK_INF_F;
+        if (init_thr) {
+            const long long q_me = qtile * Cfg::QT + qslot;
+            thr = q_me < n_q ? init_thr[q_me] : -SK_INF_F;
+        }
         uint32_t R[CH][32];
         int t = 0;                            // position in the tile sequence; this warp's job = t * MT + h
         const uint32_t afull_a0 = smem_u32(afull), aempty_a0 = smem_u32(aempty);
@@ -626,24 +640,24 @@ int search_tc_seed_tiles(int n_rtiles, int seed_stride) {
 template <int KC, int MT, int NS, int CAP, int CAPE, int J, bool DBG>
 static cudaError_t launch_tc_dbg(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles, int nstage,
                                  int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
-                                 cudaStream_t st) {
+                                 const float *init_thr, const int *n_rows_dev, cudaStream_t st) {
     using Cfg = TcCfg<MT, NS, CAP, CAPE>;
     const size_t smem = search_tc_smem_bytes(kc_tot, nstage, NS, CAPE);
     cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<KC, MT, NS, CAP, CAPE, J, DBG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const long long n_qtiles = (n_q + Cfg::QT - 1) / Cfg::QT;
-    const int n_seed = search_tc_seed_tiles(n_rtiles, seed_stride);
+    const int n_seed = init_thr ? 0 : search_tc_seed_tiles(n_rtiles, seed_stride);
     search_tc_kernel<KC, MT, NS, CAP, CAPE, J, DBG><<<(unsigned)n_qtiles, Cfg::THREADS, smem, st>>>(
         qimg, rimg, kc_tot, n_rtiles, nstage, n_seed, search_tc_seed_stride(n_rtiles, seed_stride), n_q, cand_idx,
-        cand_thr, g_tc_debug);
+        cand_thr, g_tc_debug, init_thr, n_rows_dev);
     return cudaGetLastError();
 }
 
 template <int KC, int MT, int NS, int CAP>
 static cudaError_t launch_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles, int nstage,
                              int cape, int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
-                             cudaStream_t st) {
+                             const float *init_thr, const int *n_rows_dev, cudaStream_t st) {
     // rank of the joint threshold: the certificate's margin grows with the contraction depth
     // (eps * (|q|^2 + max|r|^2)), so deep spaces keep the streams' own KC-th best (rank 2 KC = off)
     constexpr int JLO = NS == 2 ? SK_TC_JOINT : 1, JHI = NS == 2 ? 2 * KC : 1;
@@ -652,31 +666,31 @@ static cudaError_t launch_tc(const __half *qimg, const __half *rimg, int kc_tot,
     // tests is compiled into the product kernel
     if (g_tc_debug && cape == 4 && !deep)
         return launch_tc_dbg<KC, MT, NS, CAP, 4, JLO, true>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                            cand_idx, cand_thr, st);
+                                                            cand_idx, cand_thr, init_thr, n_rows_dev, st);
     if (cape == 4 && !deep)
         return launch_tc_dbg<KC, MT, NS, CAP, 4, JLO, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                             cand_idx, cand_thr, st);
+                                                             cand_idx, cand_thr, init_thr, n_rows_dev, st);
     if (cape == 4)
         return launch_tc_dbg<KC, MT, NS, CAP, 4, JHI, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                             cand_idx, cand_thr, st);
+                                                             cand_idx, cand_thr, init_thr, n_rows_dev, st);
     if (cape == 2)
         return launch_tc_dbg<KC, MT, NS, CAP, 2, JHI, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                             cand_idx, cand_thr, st);
+                                                             cand_idx, cand_thr, init_thr, n_rows_dev, st);
     return cudaErrorInvalidValue;
 }
 
 // cand_idx [n_q][16] (ns lists of 16 / ns entries), cand_thr [n_q][ns]; `config` from search_tc_pick_config
 cudaError_t launch_search_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles,
                              long long n_q, int ns, int config, int seed_stride, int *cand_idx,
-                             float *cand_thr, cudaStream_t st) {
+                             float *cand_thr, const float *init_thr, const int *n_rows_dev, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
     const int nstage = config & 0xff, cape = (config >> 8) & 0xff;
     if (ns == 2)
         return launch_tc<8, TC_MT, 2, 16>(qimg, rimg, kc_tot, n_rtiles, nstage, cape, seed_stride, n_q, cand_idx,
-                                          cand_thr, st);
+                                          cand_thr, init_thr, n_rows_dev, st);
     if (ns == 1)
         return launch_tc<16, TC_MT, 1, 32>(qimg, rimg, kc_tot, n_rtiles, nstage, cape, seed_stride, n_q, cand_idx,
-                                           cand_thr, st);
+                                           cand_thr, init_thr, n_rows_dev, st);
     return cudaErrorInvalidValue;
 }
 

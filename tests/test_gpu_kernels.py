@@ -915,3 +915,40 @@ def test_tensor_engine_certifies_nearly_every_row_and_stays_selected(k, n_ref):
         ix.query(Q, k, transformed=True, weights="distance", with_pred=True)
         st = ix.stats()
         assert st["engine"] == L.ENGINE_TENSOR and st["n_fallback"] < 0.03 * st["n_queries"], st
+
+
+@pytest.mark.parametrize(("k", "n_ref", "exclude_self"), [(5, 30_000, False), (7, 30_000, False), (12, 30_000, False),
+                                                           (6, 8_000, True)])
+def test_tensor_second_pass_equals_fp32_stage_and_takes_most_of_its_rows(k, n_ref, exclude_self):
+    """Stage 1b of the cascade (the tensor engine once more over its uncertified rows, each from the
+    threshold the first pass proved sufficient) must change nothing but who certifies a row: results
+    are bit-equal with and without it, and it leaves the FP32 engine fewer rows than the first pass did."""
+    from sknnr_b200._engine import KNNIndex
+
+    rng = np.random.default_rng(31)
+    R = rng.standard_normal((n_ref, 32))
+    y = rng.standard_normal((n_ref, 3))
+    Q = None if exclude_self else rng.standard_normal((150_000, 32))
+    ix = KNNIndex(R, None, None, None, y)
+    kw = dict(exclude_self=True) if exclude_self else dict(transformed=True)
+    try:
+        L.set_option("tc_retry", 0)
+        d0, i0, p0 = ix.query(Q, k, weights="distance", with_pred=True, **kw)
+        c0 = ix.cascade_counts()
+        L.set_option("tc_retry", 1)
+        d1, i1, p1 = ix.query(Q, k, weights="distance", with_pred=True, **kw)
+        c1 = ix.cascade_counts()
+    finally:
+        L.set_option("tc_retry", 1)
+    assert ix.stats()["engine"] == L.ENGINE_TENSOR
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1) and np.array_equal(p0, p1)
+    # (which rows the first pass certifies depends a little on when its two streams see each other's
+    # published scores, so its count moves by a row or two between runs)
+    assert c0["after_tensor"] == c0["to_fp32"], (c0, c1)
+    assert abs(c1["after_tensor"] - c0["after_tensor"]) <= max(3, 0.02 * c0["after_tensor"]), (c0, c1)
+    assert c1["to_fp32"] <= c1["after_tensor"]
+    if k + int(exclude_self) > 7:
+        # one stream of 16 in the first pass already: a second pass would meet the same list, so there is none
+        assert c1["to_fp32"] == c1["after_tensor"], (c0, c1)
+    elif c1["after_tensor"] >= 50:
+        assert c1["to_fp32"] < 0.2 * c1["after_tensor"], (c0, c1)
