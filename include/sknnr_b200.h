@@ -102,6 +102,9 @@ int sknnr_device_count(int *count);
  *   "tc_seed_stride" 0..64: the tensor engine pre-scans one reference tile in n to seed its
  *                 thresholds (default 4; 0 = the default too: the engine never starts cold, and
  *                 reference sets below 192 / 64 tiles are pre-scanned at stride <= 2 / 1)
+ *   "simt_min_rows" 0..2^20: when fewer rows than this are still uncertified after the tensor engine,
+ *                 they skip the FP32 engine (one warp would scan the whole reference set for them)
+ *                 and go to the exhaustive float64 kernel (default 256)
  *   "tc_retry"    0/1 after its two-stream layout (k (+1) <= 7) the tensor engine runs a second pass,
  *                 one stream of 16, over the rows the first pass could not certify, each from the
  *                 threshold the first pass proved sufficient, before the FP32 engine sees what is

@@ -47,6 +47,7 @@ struct Options {
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
     int64_t tc_streams = 0;     // tensor engine: candidate streams per query (0 = automatic, else 1 or 2)
     int64_t host_slots = 8;     // chunks of a host-buffer call in flight (1..8)
+    int64_t simt_min_rows = 256; // cascade: fewer uncertified rows than this skip the FP32 engine (exhaustive kernel instead)
     int64_t tc_retry = 1;       // tensor engine: second pass over the uncertified rows before the FP32 stage
     int64_t tail_spread = 1;    // second stage: deal the uncertified rows out over all SMs (0: one CTA per 384 rows)
     int64_t tc_seed_stride = 4; // tensor engine: pre-scan every n-th reference tile to seed thresholds (0 = default)
@@ -322,8 +323,10 @@ struct IndexBase {
     bool spread_tail = true;   // run_chunk: deal the second stage's rows out over all SMs (set per chunk by the caller)
     long long n_exact_rows = 0;     // rows that reached the exhaustive kernel (last call)
     long long n_simt_rows = 0;      // rows that reached the FP32 stage after the tensor engine (last call)
-    long long chunk_rows_seen = 0;  // adaptive engine choice: rows / first-stage failures seen
+    long long chunk_rows_seen = 0;  // adaptive engine choice: rows / cost-weighted first-stage failures seen
     long long chunk_fb_seen = 0;
+    long long chunk_fail_seen = 0;  // plain count of first-pass failures (same window)
+    bool tc_wide_joint = false;     // tensor engine, two streams: joint threshold at rank 12 instead of 10
 
     int init_common(int dev, const double *y, int64_t nref, int nout) {
         int count = 0;
@@ -381,7 +384,14 @@ struct IndexBase {
             n_exact_rows += s.h_fb[1];
             n_simt_rows += s.h_fb[3];
             chunk_rows_seen += s.rows_in_flight;
-            chunk_fb_seen += s.h_fb[0];
+            // what a first-pass failure costs: about a third of a row's first pass when the second pass
+            // certifies it, twenty times that when it goes on to the FP32 engine
+            chunk_fb_seen += s.h_fb[3] * 6LL + s.h_fb[0];
+            chunk_fail_seen += s.h_fb[0];
+            // the two-stream layout's joint threshold sits at rank 10 of the query's candidates; data whose
+            // neighbours crowd inside the FP16 error margin (few features, many plots) fail that more
+            // than the second pass is worth: such an index moves to rank 12 for good
+            if (chunk_rows_seen >= 4096 && chunk_fail_seen * 25 > chunk_rows_seen) tc_wide_joint = true;
             s.fb_pending = false;
         }
         if (s.flag_pending) {
@@ -583,6 +593,9 @@ int sknnr_set_option(const char *name, int64_t value) {
     } else if (!strcmp(name, "stage_rows")) {
         if (value < 1024) return fail(SKNNR_EINVAL, "stage_rows must be >= 1024");
         g_opt.stage_rows = (value + 1023) / 1024 * 1024;
+    } else if (!strcmp(name, "simt_min_rows")) {
+        if (value < 0 || value > (1 << 20)) return fail(SKNNR_EINVAL, "simt_min_rows must be 0..2^20");
+        g_opt.simt_min_rows = value;
     } else if (!strcmp(name, "tc_retry")) {
         g_opt.tc_retry = value ? 1 : 0;
     } else if (!strcmp(name, "tail_spread")) {
@@ -920,7 +933,8 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
         int ns = kk <= 7 ? 2 : 1;   // a stream's list keeps at most 7 (ns = 2) / 15 (ns = 1) candidates
         if (g_opt.tc_streams == 1) ns = 1;
         CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, ns, ix->tc_nstage,
-                            (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, nullptr, nullptr, st));
+                            (int)g_opt.tc_seed_stride, ix->tc_wide_joint || g_opt.tc_retry == 0, s.cand_idx.p,
+                            s.cand_thr.p, nullptr, nullptr, st));
         if (g_opt.timing) CK(s.mark(st));
         // (a second pass only pays after the two-stream layout: its joint list holds 11 candidates, the
         // second pass's single stream 15 - the one-stream layout would meet the same 15 again)
@@ -963,7 +977,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
             // is mostly rows with more references inside the error margin of the k-th neighbour than
             // its joint list of 11 holds)
             CK(launch_search_tc(s.qimg_tc.p, ix->d_rimg_tc, ix->kc_tot, ix->n_rtiles_tc, rows, 1, ix->tc_nstage,
-                                (int)g_opt.tc_seed_stride, s.cand_idx.p, s.cand_thr.p, s.fb_thr.p, count, st));
+                                (int)g_opt.tc_seed_stride, 0, s.cand_idx.p, s.cand_thr.p, s.fb_thr.p, count, st));
             FinishParams fpb = fp;
             fpb.row_map = list;
             RefineArgs rb = ra;
@@ -990,8 +1004,11 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
 
     // stage 2 (or the only fast stage): FP32 SIMT engine
     if (g_opt.timing && !use_tc) CK(s.mark(st));
+    // (a handful of rows is not worth a scan of the whole reference set by one warp per row block: below
+    // simt_min_rows the stage passes its rows straight on to the exhaustive kernel)
+    const int bypass = stage2_count ? (int)g_opt.simt_min_rows : 0;
     CK(launch_search_simt(s.qimg.p, ix->d_rimg, ix->dpad, ix->n_rtiles, rows, kc, s.cand_idx.p,
-                          s.cand_thr.p, stage2_count, g_opt.tail_spread && ix->spread_tail ? ix->n_sm : 0, st));
+                          s.cand_thr.p, stage2_count, g_opt.tail_spread && ix->spread_tail ? ix->n_sm : 0, bypass, st));
     if (g_opt.timing && !use_tc) CK(s.mark(st));
     FinishParams fp2 = fp;
     fp2.row_map = stage2_list;
@@ -1005,6 +1022,7 @@ static int run_chunk(sknnr_index *ix, Slot &s, const void *dX, int x_f32, int64_
     ra.fb_count = s.fb2.p;
     ra.fb_list = s.fb2.p + 1;
     ra.fb_thr = nullptr;
+    ra.bypass_rows = bypass;
     ra.n_rows_dev = stage2_count;
     ra.row_map = fp2.row_map;
     CK(launch_refine(ra, fp2, st));
@@ -1078,7 +1096,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     ix->n_simt_rows = ix->n_exact_rows = 0;
     ix->stats.n_queries = n_q;
     ix->saw_nonfinite = false;
-    ix->chunk_rows_seen = ix->chunk_fb_seen = 0;   // the demotion rule looks at this call's chunks only
+    ix->chunk_rows_seen = ix->chunk_fb_seen = ix->chunk_fail_seen = 0;   // the demotion rule looks at this call's chunks only
     if (n_q == 0) { guard.ok = true; return SKNNR_OK; }
 
     // ordinary NumPy buffers are staged through page-locked slot buffers by the host pool
@@ -1123,7 +1141,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             // adaptive engine choice: if the FP16 filter cannot certify > 5 % of the rows
             // (ill-conditioned features: huge norms relative to neighbour distances) the FP32
             // engine is the better first stage for this index
-            if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen)
+            if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 3 > ix->chunk_rows_seen)
                 ix->tensor_demoted[ix->ns_in_use] = true;
         }
         const void *dX;
@@ -1233,7 +1251,7 @@ static int raster_impl(IX *ix, int d, const void *bands, int32_t x_dtype, int64_
     for (auto &s : ix->slots) { s.ev_used = 0; s.fb_pending = false; s.flag_pending = false; }
     ix->stats = sknnr_stats{};
     ix->n_simt_rows = ix->n_exact_rows = 0;
-    ix->chunk_rows_seen = ix->chunk_fb_seen = 0;
+    ix->chunk_rows_seen = ix->chunk_fb_seen = ix->chunk_fail_seen = 0;
     if (n_valid_out) *n_valid_out = 0;
     if (n_pix == 0) { guard.ok = true; return SKNNR_OK; }
 
@@ -1328,7 +1346,7 @@ int sknnr_raster_kneighbors(sknnr_index *ix, const void *bands, int32_t x_dtype,
                        out_dist, out_idx, out_pred, fill_dist, fill_idx, fill_pred, n_valid_out,
                        [&](Slot &s, const void *xc, int64_t nv, int64_t row0, double *o_dist, long long *o_idx,
                            double *o_pred) -> int {
-                           if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 20 > ix->chunk_rows_seen)
+                           if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 3 > ix->chunk_rows_seen)
                                ix->tensor_demoted[ix->ns_in_use] = true;
                            ix->spread_tail = false;
                            return run_chunk(ix, s, xc, x_dtype == SKNNR_F32, ix->d_in, false, nv, row0, k, flags,

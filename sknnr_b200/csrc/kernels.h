@@ -33,9 +33,10 @@ size_t search_simt_smem_bytes(int dpad, int kc, int nstage);
 int search_simt_pick_stages(int dpad, int kc);
 cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, int n_rtiles,
                                long long n_q, int kc, int *cand_idx, float *cand_thr,
-                               const int *n_rows_dev, int spread_ctas, cudaStream_t st);
+                               const int *n_rows_dev, int spread_ctas, int bypass_rows, cudaStream_t st);
 // n_rows_dev != null: compacted launch, the row count is read on the device; spread_ctas > 0 then
-// deals the rows out over up to that many CTAs in units of one warp (0: one CTA per 384 rows)
+// deals the rows out over up to that many CTAs in units of one warp (0: one CTA per 384 rows); a compacted
+// launch with fewer than bypass_rows rows does nothing (refine then hands the rows on, RefineArgs.bypass_rows)
 
 // ---- search_tc.cu (tcgen05 / TMEM engine) ------------------------------------------------
 // Two candidate-stream layouts: ns = 2 (two lists of up to 7 per query, k (+1) <= 7) and ns = 1 (one
@@ -48,8 +49,10 @@ extern int g_tc_debug;  // timing experiments: bit 0 = skip the hit path (wrong 
 // seed_stride: one reference tile in seed_stride is pre-scanned to seed the thresholds (0 = the
 // default, 4; small reference sets use a denser stride, see search_tc_seed_stride)
 cudaError_t launch_search_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int ns, int config, int seed_stride, int *cand_idx,
+                             long long n_q, int ns, int config, int seed_stride, int wide_joint, int *cand_idx,
                              float *cand_thr, const float *init_thr, const int *n_rows_dev, cudaStream_t st);
+// wide_joint (two streams only): the joint threshold sits at rank 12 of the query's candidates instead of 10
+// (fewer uncertified rows, more candidates to carry)
 // init_thr != null: second pass - no seeding, row q starts from threshold init_thr[q]; n_rows_dev != null:
 // compacted launch, the row count is read on the device
 
@@ -75,6 +78,8 @@ struct RefineArgs {
                             // second pass of the same engine has to list every reference (retry_threshold)
     const int *n_rows_dev;  // compacted launch: only the first *n_rows_dev rows exist
     const int *row_map;     // compacted launch: row of the original chunk (goes into fb_list)
+    int bypass_rows;        // compacted launch with fewer rows than this: the search was skipped, every row
+                            // goes to fb_list unexamined
 };
 cudaError_t launch_refine(const RefineArgs &a, const FinishParams &fp, cudaStream_t st);
 

@@ -120,6 +120,10 @@ refine_kernel(RefineArgs a, FinishParams fp) {
     const int warp = __shfl_sync(SK_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * REFINE_WARPS + warp;
     if (q >= a.n_q || (a.n_rows_dev && q >= *a.n_rows_dev)) return;
+    if (a.n_rows_dev && *a.n_rows_dev < a.bypass_rows) {   // the search was skipped: hand the row on
+        if (lane == 0) a.fb_list[atomicAdd(a.fb_count, 1)] = a.row_map ? a.row_map[q] : (int)q;
+        return;
+    }
     const double *zq = a.z64 + q * a.d;
 
     // Exact squared distances of the candidates: each half warp takes one candidate per pass (its
@@ -211,6 +215,10 @@ refine2_kernel(RefineArgs a, FinishParams fp) {
     if (q0 >= n_rows) return;                       // both segments idle: the whole warp leaves
     const bool live = q0 + seg < n_rows;            // odd tail: the second segment rides along
     const long long q = live ? q0 + seg : q0;
+    if (a.n_rows_dev && n_rows < a.bypass_rows) {   // the search was skipped: hand the rows on
+        if (live && hl == 0) a.fb_list[atomicAdd(a.fb_count, 1)] = a.row_map ? a.row_map[q] : (int)q;
+        return;
+    }
     const double *zq = a.z64 + q * a.d;
     double zr[DJ];
 #pragma unroll

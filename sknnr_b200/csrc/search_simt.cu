@@ -33,7 +33,8 @@ template <int KC>
 __global__ void __launch_bounds__(SEARCH_THREADS, 1)
 search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rimg, int dpad,
                    int n_rtiles, int nstage, long long n_q, int *__restrict__ cand_idx,
-                   float *__restrict__ cand_thr, const int *__restrict__ n_rows_dev, int spread_ctas) {
+                   float *__restrict__ cand_thr, const int *__restrict__ n_rows_dev, int spread_ctas,
+                   int bypass_rows) {
     long long qtile = blockIdx.x;
     int wpc = NCOMPUTE_WARPS, woff = 0;   // warps of this CTA that have rows, first warp slot of the tile it serves
     if (n_rows_dev) {
@@ -43,6 +44,7 @@ search_simt_kernel(const float *__restrict__ qimg, const float *__restrict__ rim
         // up to spread_ctas CTAs: CTA b serves wpc consecutive warp slots of a query tile, wpc the smallest
         // divisor of 12 that covers the rows, and its other warps retire at once.
         const long long n_dev = *n_rows_dev;
+        if (n_dev < bypass_rows) return;   // too few rows to be worth a scan: they go to the exhaustive kernel
         n_q = min(n_q, n_dev);
         const long long n_w = (n_q + 31) / 32;
         const long long per = spread_ctas > 0 ? (n_w + spread_ctas - 1) / spread_ctas : NCOMPUTE_WARPS;
@@ -251,7 +253,7 @@ int search_simt_pick_stages(int dpad, int kc) {
 template <int KC>
 static cudaError_t launch_kc(const float *qimg, const float *rimg, int dpad, int n_rtiles,
                              long long n_q, int *cand_idx, float *cand_thr, const int *n_rows_dev,
-                             int spread_ctas, cudaStream_t st) {
+                             int spread_ctas, int bypass_rows, cudaStream_t st) {
     const int nstage = search_simt_pick_stages(dpad, KC);
     if (nstage == 0) return cudaErrorInvalidValue;
     const size_t smem = search_simt_smem_bytes(dpad, KC, nstage);
@@ -261,18 +263,18 @@ static cudaError_t launch_kc(const float *qimg, const float *rimg, int dpad, int
     const long long n_qtiles = (n_q + QTILE - 1) / QTILE;
     const long long grid = n_rows_dev && spread_ctas > n_qtiles ? spread_ctas : n_qtiles;
     search_simt_kernel<KC><<<(unsigned)grid, SEARCH_THREADS, smem, st>>>(
-        qimg, rimg, dpad, n_rtiles, nstage, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas);
+        qimg, rimg, dpad, n_rtiles, nstage, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, bypass_rows);
     return cudaGetLastError();
 }
 
 cudaError_t launch_search_simt(const float *qimg, const float *rimg, int dpad, int n_rtiles,
                                long long n_q, int kc, int *cand_idx, float *cand_thr,
-                               const int *n_rows_dev, int spread_ctas, cudaStream_t st) {
+                               const int *n_rows_dev, int spread_ctas, int bypass_rows, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
     switch (kc) {
-        case 8: return launch_kc<8>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, st);
-        case 16: return launch_kc<16>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, st);
-        case 32: return launch_kc<32>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, st);
+        case 8: return launch_kc<8>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, bypass_rows, st);
+        case 16: return launch_kc<16>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, bypass_rows, st);
+        case 32: return launch_kc<32>(qimg, rimg, dpad, n_rtiles, n_q, cand_idx, cand_thr, n_rows_dev, spread_ctas, bypass_rows, st);
         default: return cudaErrorInvalidValue;
     }
 }

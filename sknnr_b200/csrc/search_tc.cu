@@ -86,7 +86,11 @@ __device__ unsigned long long g_tc_counters[8];
 // rank (in the union of both streams' lists) of the score the joint threshold is set to: the k-th
 // neighbour must clear it by the certificate's error margin, so it sits a few ranks above k
 #ifndef SK_TC_JOINT
-#define SK_TC_JOINT 12
+#define SK_TC_JOINT 10
+#endif
+// ... and the rank an index falls back to when too many of its rows fail rank SK_TC_JOINT (api.cu, tc_wide_joint)
+#ifndef SK_TC_JOINT_WIDE
+#define SK_TC_JOINT_WIDE 12
 #endif
 // jobs between two resolutions of the pending queues (0 = 8 with queues of four octets, 2 with queues of two)
 #ifndef SK_TC_DRAIN_EVERY
@@ -656,41 +660,38 @@ static cudaError_t launch_tc_dbg(const __half *qimg, const __half *rimg, int kc_
 
 template <int KC, int MT, int NS, int CAP>
 static cudaError_t launch_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles, int nstage,
-                             int cape, int seed_stride, long long n_q, int *cand_idx, float *cand_thr,
+                             int cape, int seed_stride, int wide_joint, long long n_q, int *cand_idx, float *cand_thr,
                              const float *init_thr, const int *n_rows_dev, cudaStream_t st) {
     // rank of the joint threshold: the certificate's margin grows with the contraction depth
     // (eps * (|q|^2 + max|r|^2)), so deep spaces keep the streams' own KC-th best (rank 2 KC = off)
-    constexpr int JLO = NS == 2 ? SK_TC_JOINT : 1, JHI = NS == 2 ? 2 * KC : 1;
+    constexpr int JLO = NS == 2 ? SK_TC_JOINT : 1, JMID = NS == 2 ? SK_TC_JOINT_WIDE : 1, JHI = NS == 2 ? 2 * KC : 1;
     const bool deep = kc_tot > 6;   // more than 48 FP16 elements, i.e. d' > 45 (search_tc_smem_bytes knows the same rule)
+#define SK_TC_GO(CAPE_, J_, DBG_)                                                                                  \
+    return launch_tc_dbg<KC, MT, NS, CAP, CAPE_, J_, DBG_>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q, \
+                                                           cand_idx, cand_thr, init_thr, n_rows_dev, st)
     // the timing-experiment hooks ("tc_debug") live in a separate instantiation: none of their
     // tests is compiled into the product kernel
-    if (g_tc_debug && cape == 4 && !deep)
-        return launch_tc_dbg<KC, MT, NS, CAP, 4, JLO, true>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                            cand_idx, cand_thr, init_thr, n_rows_dev, st);
-    if (cape == 4 && !deep)
-        return launch_tc_dbg<KC, MT, NS, CAP, 4, JLO, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                             cand_idx, cand_thr, init_thr, n_rows_dev, st);
-    if (cape == 4)
-        return launch_tc_dbg<KC, MT, NS, CAP, 4, JHI, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                             cand_idx, cand_thr, init_thr, n_rows_dev, st);
-    if (cape == 2)
-        return launch_tc_dbg<KC, MT, NS, CAP, 2, JHI, false>(qimg, rimg, kc_tot, n_rtiles, nstage, seed_stride, n_q,
-                                                             cand_idx, cand_thr, init_thr, n_rows_dev, st);
+    if (g_tc_debug && cape == 4 && !deep) SK_TC_GO(4, JLO, true);
+    if (cape == 4 && !deep && NS == 2 && wide_joint) SK_TC_GO(4, JMID, false);
+    if (cape == 4 && !deep) SK_TC_GO(4, JLO, false);
+    if (cape == 4) SK_TC_GO(4, JHI, false);
+    if (cape == 2) SK_TC_GO(2, JHI, false);
+#undef SK_TC_GO
     return cudaErrorInvalidValue;
 }
 
 // cand_idx [n_q][16] (ns lists of 16 / ns entries), cand_thr [n_q][ns]; `config` from search_tc_pick_config
 cudaError_t launch_search_tc(const __half *qimg, const __half *rimg, int kc_tot, int n_rtiles,
-                             long long n_q, int ns, int config, int seed_stride, int *cand_idx,
+                             long long n_q, int ns, int config, int seed_stride, int wide_joint, int *cand_idx,
                              float *cand_thr, const float *init_thr, const int *n_rows_dev, cudaStream_t st) {
     if (n_q <= 0) return cudaSuccess;
     const int nstage = config & 0xff, cape = (config >> 8) & 0xff;
     if (ns == 2)
-        return launch_tc<8, TC_MT, 2, 16>(qimg, rimg, kc_tot, n_rtiles, nstage, cape, seed_stride, n_q, cand_idx,
-                                          cand_thr, init_thr, n_rows_dev, st);
+        return launch_tc<8, TC_MT, 2, 16>(qimg, rimg, kc_tot, n_rtiles, nstage, cape, seed_stride, wide_joint, n_q,
+                                          cand_idx, cand_thr, init_thr, n_rows_dev, st);
     if (ns == 1)
-        return launch_tc<16, TC_MT, 1, 32>(qimg, rimg, kc_tot, n_rtiles, nstage, cape, seed_stride, n_q, cand_idx,
-                                           cand_thr, init_thr, n_rows_dev, st);
+        return launch_tc<16, TC_MT, 1, 32>(qimg, rimg, kc_tot, n_rtiles, nstage, cape, seed_stride, 0, n_q,
+                                           cand_idx, cand_thr, init_thr, n_rows_dev, st);
     return cudaErrorInvalidValue;
 }
 

@@ -942,13 +942,33 @@ def test_tensor_second_pass_equals_fp32_stage_and_takes_most_of_its_rows(k, n_re
         L.set_option("tc_retry", 1)
     assert ix.stats()["engine"] == L.ENGINE_TENSOR
     assert np.array_equal(i0, i1) and np.array_equal(d0, d1) and np.array_equal(p0, p1)
-    # (which rows the first pass certifies depends a little on when its two streams see each other's
-    # published scores, so its count moves by a row or two between runs)
+    # (without a second pass behind it the first pass sets its joint threshold at rank 12 instead of
+    # 10, so the two calls' first-pass counts are not comparable; what reaches the FP32 engine is)
     assert c0["after_tensor"] == c0["to_fp32"], (c0, c1)
-    assert abs(c1["after_tensor"] - c0["after_tensor"]) <= max(3, 0.02 * c0["after_tensor"]), (c0, c1)
     assert c1["to_fp32"] <= c1["after_tensor"]
+    assert c1["to_fp32"] <= c0["to_fp32"], (c0, c1)
     if k + int(exclude_self) > 7:
         # one stream of 16 in the first pass already: a second pass would meet the same list, so there is none
         assert c1["to_fp32"] == c1["after_tensor"], (c0, c1)
     elif c1["after_tensor"] >= 50:
         assert c1["to_fp32"] < 0.2 * c1["after_tensor"], (c0, c1)
+
+
+def test_joint_threshold_rank_adapts_to_crowded_neighbourhoods():
+    """Few features and many plots put more references inside the FP16 error margin of the k-th
+    neighbour than rank 10 of the two-stream layout's joint threshold allows for: after one call
+    that saw > 4 % first-pass failures the index moves to rank 12.  Results do not depend on it."""
+    from sknnr_b200._engine import KNNIndex
+
+    rng = np.random.default_rng(5)
+    R = rng.standard_normal((50_000, 8))
+    Q = rng.standard_normal((60_000, 8))
+    ix = KNNIndex(R, None, None, None, rng.standard_normal((50_000, 2)))
+    d0, i0, _ = ix.query(Q, 7, transformed=True)
+    c0 = ix.cascade_counts()
+    d1, i1, _ = ix.query(Q, 7, transformed=True)
+    c1 = ix.cascade_counts()
+    assert ix.stats()["engine"] == L.ENGINE_TENSOR
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    assert c0["after_tensor"] > 0.04 * len(Q), c0
+    assert c1["after_tensor"] < 0.6 * c0["after_tensor"], (c0, c1)
