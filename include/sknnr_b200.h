@@ -102,6 +102,12 @@ int sknnr_device_count(int *count);
  *   "tc_seed_stride" 0..64: the tensor engine pre-scans one reference tile in n to seed its
  *                 thresholds (default 4; 0 = the default too: the engine never starts cold, and
  *                 reference sets below 192 / 64 tiles are pre-scanned at stride <= 2 / 1)
+ *   "tail_priority" 0/1 the cascade's tail streams (second pass, FP32 and exhaustive stages of the uncertified
+ *                 rows) get the highest stream priority; read when an index is created (default 1)
+ *   "host_nt"     0/1 staging copies of pageable caller buffers use streaming (non-temporal) stores (default 1)
+ *   "host_pipeline" 0/1 host-buffer calls run as a three-stage pipeline: one in-order H2D stream, one compute
+ *                 stream, one D2H stream over up to four slots of buffers (default 1); 0: every chunk in
+ *                 flight has a stream of its own for copies and kernels (round 1's layout)
  *   "simt_min_rows" 0..2^20: when fewer rows than this are still uncertified after the tensor engine,
  *                 they skip the FP32 engine (one warp would scan the whole reference set for them)
  *                 and go to the exhaustive float64 kernel (default 256)

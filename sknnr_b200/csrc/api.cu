@@ -16,6 +16,10 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <chrono>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <vector>
 
 using namespace sk;
@@ -47,6 +51,9 @@ struct Options {
     int64_t kc = 16; // minimum candidate-list length of the float search (0 = smallest that fits k+1)
     int64_t tc_streams = 0;     // tensor engine: candidate streams per query (0 = automatic, else 1 or 2)
     int64_t host_slots = 8;     // chunks of a host-buffer call in flight (1..8)
+    int64_t tail_priority = 1;  // the slots' tail streams are created with the highest stream priority (read at index creation)
+    int64_t host_nt = 1;        // staging copies of pageable buffers use streaming stores
+    int64_t host_pipeline = 1;  // host-buffer calls: one compute stream fed by an in-order H2D stream, drained by a D2H stream
     int64_t simt_min_rows = 256; // cascade: fewer uncertified rows than this skip the FP32 engine (exhaustive kernel instead)
     int64_t tc_retry = 1;       // tensor engine: second pass over the uncertified rows before the FP32 stage
     int64_t tail_spread = 1;    // second stage: deal the uncertified rows out over all SMs (0: one CTA per 384 rows)
@@ -92,7 +99,7 @@ public:
             int n = (int)g_opt.host_threads;
             if (n <= 0) {
                 const unsigned hw = std::thread::hardware_concurrency();
-                n = (int)std::min(16u, std::max(2u, hw / 2));
+                n = (int)std::min(16u, std::max(2u, hw * 3 / 4));
             }
             return new HostPool(n - 1);   // the calling thread takes a share as well
         }();
@@ -122,6 +129,28 @@ public:
     }
 };
 
+// A staging copy is written once and read next by the DMA engine (or by the caller much later):
+// streaming stores keep it out of the cache and spare the read-for-ownership of every destination
+// line, a third of the copy's memory traffic (8 threads on the build host: 21 -> 27 GB/s).
+void stream_copy(unsigned char *d, const unsigned char *s, size_t n) {
+#if defined(__SSE2__)
+    if (g_opt.host_nt && n >= (256u << 10)) {
+        while (n && ((uintptr_t)d & 15)) { *d++ = *s++; --n; }
+        for (size_t i = n / 64; i; --i, s += 64, d += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)s), b = _mm_loadu_si128((const __m128i *)(s + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i *)(s + 32)), e = _mm_loadu_si128((const __m128i *)(s + 48));
+            _mm_stream_si128((__m128i *)d, a);
+            _mm_stream_si128((__m128i *)(d + 16), b);
+            _mm_stream_si128((__m128i *)(d + 32), c);
+            _mm_stream_si128((__m128i *)(d + 48), e);
+        }
+        _mm_sfence();
+        n %= 64;
+    }
+#endif
+    memcpy(d, s, n);
+}
+
 // rows x row_bytes from src (row stride src_ld bytes) to dst (row stride dst_ld bytes), split over the pool
 void parallel_copy_rows(void *dst, size_t dst_ld, const void *src, size_t src_ld, size_t row_bytes, int64_t rows) {
     if (rows <= 0 || row_bytes == 0) return;
@@ -135,7 +164,7 @@ void parallel_copy_rows(void *dst, size_t dst_ld, const void *src, size_t src_ld
         unsigned char *d = (unsigned char *)dst + (size_t)r0 * dst_ld;
         const unsigned char *sp = (const unsigned char *)src + (size_t)r0 * src_ld;
         if (dst_ld == row_bytes && src_ld == row_bytes) {
-            memcpy(d, sp, (size_t)(r1 - r0) * row_bytes);
+            stream_copy(d, sp, (size_t)(r1 - r0) * row_bytes);
         } else {
             for (int64_t r = r0; r < r1; ++r, d += dst_ld, sp += src_ld) memcpy(d, sp, row_bytes);
         }
@@ -265,6 +294,8 @@ struct Slot {
     // device-pointer calls are not synchronised: the slot's scratch stays in use until ev_last
     cudaEvent_t ev_last = nullptr;
     bool last_pending = false;
+    // host-buffer calls (pipelined): the chunk's input has arrived / its first stage is through
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     // page-locked staging of pageable caller buffers (one chunk in, one chunk out) and the copy-out
     // that is still owed to the caller once the slot's stream has drained
     PinBuf<unsigned char> h_x, h_dist, h_idx, h_pred;
@@ -288,6 +319,9 @@ struct Slot {
         owed.clear();
         if (ev_last) cudaEventDestroy(ev_last);
         ev_last = nullptr; last_pending = false; flag_pending = false;
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
+        ev_in = ev_out = nullptr;
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (tail_stream) cudaStreamDestroy(tail_stream);
         if (ev_stage1) cudaEventDestroy(ev_stage1);
@@ -327,6 +361,12 @@ struct IndexBase {
     long long chunk_fb_seen = 0;
     long long chunk_fail_seen = 0;  // plain count of first-pass failures (same window)
     bool tc_wide_joint = false;     // tensor engine, two streams: joint threshold at rank 12 instead of 10
+    // Host-buffer calls run as a three-stage pipeline over a few slots of buffers: every chunk's input
+    // goes through ONE in-order H2D stream, its kernels through ONE compute stream (the slots' tail
+    // streams take the uncertified rows, as in a device-pointer call), its results through ONE D2H
+    // stream.  (One stream per chunk, round 1's layout, left it to the driver how eight streams share
+    // its hardware queues: traced on this pool, chunk c only started once chunk c - 2 was through.)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, host_compute = nullptr;
 
     int init_common(int dev, const double *y, int64_t nref, int nout) {
         int count = 0;
@@ -346,16 +386,25 @@ struct IndexBase {
             CK(cudaMalloc(&d_y, (size_t)nref * nout * sizeof(double)));
             CK(cudaMemcpy(d_y, y, (size_t)nref * nout * sizeof(double), cudaMemcpyHostToDevice));
         }
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithFlags(&host_compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h2d_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
         for (auto &s : slots) {
             CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             s.own_stream = true;
-            CK(cudaStreamCreateWithFlags(&s.tail_stream, cudaStreamNonBlocking));
+            // (the tail's few CTAs go ahead of the thousands the next chunk's first stage has queued:
+            // the chunk's results are complete, and its slot free, a whole first stage earlier)
+            CK(cudaStreamCreateWithPriority(&s.tail_stream, cudaStreamNonBlocking, g_opt.tail_priority ? prio_hi : prio_lo));
             CK(cudaEventCreateWithFlags(&s.ev_stage1, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
             CK(cudaHostAlloc((void **)&s.h_fb, 4 * sizeof(int), cudaHostAllocDefault));
             s.h_fb[0] = s.h_fb[1] = s.h_fb[2] = s.h_fb[3] = 0;
             CK(s.nonfinite.reserve(1));
             CK(cudaEventCreateWithFlags(&s.ev_last, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
             CK(cudaHostAlloc((void **)&s.h_cnt, sizeof(int), cudaHostAllocDefault));
             CK(cudaEventCreateWithFlags(&s.ev_cnt, cudaEventDisableTiming));
         }
@@ -364,6 +413,10 @@ struct IndexBase {
     void release_common() {
         cudaSetDevice(device);
         for (auto &s : slots) s.release();
+        for (cudaStream_t *st : {&host_compute, &h2d_stream, &d2h_stream}) {
+            if (*st) cudaStreamDestroy(*st);
+            *st = nullptr;
+        }
         exact_scr.release(); exact_big.release();
         if (ev_exact) cudaEventDestroy(ev_exact);
         ev_exact = nullptr;
@@ -452,6 +505,7 @@ struct IndexBase {
     }
     // error path: nothing of this call may still be reading or writing caller memory when it returns
     void quiesce() {
+        for (cudaStream_t st : {h2d_stream, host_compute}) if (st) cudaStreamSynchronize(st);
         for (auto &s : slots) {
             cudaStreamSynchronize(s.stream);
             if (s.tail_stream) cudaStreamSynchronize(s.tail_stream);
@@ -460,6 +514,7 @@ struct IndexBase {
             s.owed.clear();
             s.ev_used = 0;
         }
+        if (d2h_stream) cudaStreamSynchronize(d2h_stream);
         cudaGetLastError();
     }
 };
@@ -593,6 +648,12 @@ int sknnr_set_option(const char *name, int64_t value) {
     } else if (!strcmp(name, "stage_rows")) {
         if (value < 1024) return fail(SKNNR_EINVAL, "stage_rows must be >= 1024");
         g_opt.stage_rows = (value + 1023) / 1024 * 1024;
+    } else if (!strcmp(name, "tail_priority")) {
+        g_opt.tail_priority = value ? 1 : 0;
+    } else if (!strcmp(name, "host_nt")) {
+        g_opt.host_nt = value ? 1 : 0;
+    } else if (!strcmp(name, "host_pipeline")) {
+        g_opt.host_pipeline = value ? 1 : 0;
     } else if (!strcmp(name, "simt_min_rows")) {
         if (value < 0 || value > (1 << 20)) return fail(SKNNR_EINVAL, "simt_min_rows must be 0..2^20");
         g_opt.simt_min_rows = value;
@@ -1110,12 +1171,30 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     // tails; measured +1.8 %), while host buffers prefer the shorter pipeline ramp of the smaller one
     int64_t chunk = dev_ptrs ? 2 * g_opt.chunk_rows : (staged ? std::min(g_opt.stage_rows, g_opt.chunk_rows) : g_opt.chunk_rows);
     chunk = std::min<int64_t>(chunk, (n_q + 255) / 256 * 256);
-    const int n_slots = dev_ptrs ? 2 : (staged ? std::min<int>(4, (int)g_opt.host_slots) : (int)g_opt.host_slots);
+    const bool piped = !dev_ptrs && g_opt.host_pipeline != 0;
+    const int n_slots = dev_ptrs ? 2 : (staged || piped ? std::min<int>(4, (int)g_opt.host_slots) : (int)g_opt.host_slots);
     // Host buffers: the first chunk's H2D copy and the last chunk's D2H copy cannot overlap any
     // kernel, so the stream of chunks ramps up (1/4, 1/2, 1, ...) and down (..., 1/2, 1/4).
     const bool ramp = !dev_ptrs && n_q >= 4 * chunk && chunk % 1024 == 0;
     int ci = 0;
     int64_t rows = 0;
+    // SKNNR_B200_TRACE=1: per-chunk timeline of a host-buffer call on stderr (events on the chunk's stream:
+    // enqueued / input arrived / results complete / results delivered, ms since the call began)
+    static const bool trace_on = getenv("SKNNR_B200_TRACE") != nullptr;
+    struct ChunkTrace { int64_t rows; cudaEvent_t e[4]; double host_ms; };
+    std::vector<ChunkTrace> trace;
+    cudaEvent_t trace_t0 = nullptr;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    const bool tracing = trace_on && !dev_ptrs;
+    if (tracing) {
+        CK(cudaEventCreate(&trace_t0));
+        CK(cudaEventRecord(trace_t0, ix->slots[0].stream));
+    }
+    auto trace_mark = [&](int which, cudaStream_t st) -> cudaError_t {
+        if (!tracing) return cudaSuccess;
+        cudaError_t e = cudaEventCreate(&trace.back().e[which]);
+        return e != cudaSuccess ? e : cudaEventRecord(trace.back().e[which], st);
+    };
     for (int64_t r0 = 0; r0 < n_q; r0 += rows, ++ci) {
         rows = std::min(chunk, n_q - r0);
         if (ramp) {
@@ -1123,20 +1202,17 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             if (ci == 0) rows = q4;
             else if (ci == 1) rows = 2 * q4;
             else if (left > chunk + 3 * q4) rows = chunk;
-            else if (left > 3 * q4) rows = left - 3 * q4;   // leaves 1/2 + 1/4 for the last two
+            else if (left > 3 * q4) {                        // leaves 1/2 + 1/4 for the last two
+                rows = left - 3 * q4;
+                if (rows < q4) rows += 2 * q4;               // (a sliver rides with the half chunk instead)
+            }
             else if (left > q4) rows = left - q4;
             else rows = left;
         }
         // the slots alternate: the tail of chunk c (on its slot's tail stream) overlaps the first
         // stage of chunk c + 1 (other slot's buffers)
         Slot &s = ix->slots[ci % n_slots];
-        StreamLoan loan(s, user_stream, dev_ptrs);
-        if (dev_ptrs) {
-            if (s.tail_pending) {   // the slot's buffers are free once its previous tail is done
-                CK(cudaStreamWaitEvent(user_stream, s.ev_tail, 0));
-                s.tail_pending = false;
-            }
-        } else {
+        if (!dev_ptrs) {
             CK(ix->finish_slot(s));   // previous chunk on this slot is done, its results delivered
             // adaptive engine choice: if the FP16 filter cannot certify > 5 % of the rows
             // (ill-conditioned features: huge norms relative to neighbour distances) the FP32
@@ -1144,8 +1220,20 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             if (ix->chunk_rows_seen >= 4096 && ix->chunk_fb_seen * 3 > ix->chunk_rows_seen)
                 ix->tensor_demoted[ix->ns_in_use] = true;
         }
+        // (the chunk's kernels run on the caller's stream / the pipeline's compute stream, lent to the slot)
+        StreamLoan loan(s, piped ? ix->host_compute : user_stream, dev_ptrs || piped);
+        if (dev_ptrs && s.tail_pending) {   // the slot's buffers are free once its previous tail is done
+            CK(cudaStreamWaitEvent(user_stream, s.ev_tail, 0));
+            s.tail_pending = false;
+        }
+        const cudaStream_t cin = piped ? ix->h2d_stream : s.stream, cout = piped ? ix->d2h_stream : s.stream;
         const void *dX;
         int64_t dld = ldx;
+        if (tracing) {
+            trace.push_back({rows, {nullptr, nullptr, nullptr, nullptr},
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count()});
+            CK(trace_mark(0, cin));
+        }
         if (x_on_device) {
             dX = (const unsigned char *)X + (size_t)r0 * ldx * esz;
         } else {
@@ -1154,12 +1242,16 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
             if (stage_in) {
                 CK(s.h_x.reserve((size_t)rows * cols * esz));
                 parallel_copy_rows(s.h_x.p, (size_t)cols * esz, src, (size_t)ldx * esz, (size_t)cols * esz, rows);
-                CK(cudaMemcpyAsync(s.x.p, s.h_x.p, (size_t)rows * cols * esz, cudaMemcpyDefault, s.stream));
+                CK(cudaMemcpyAsync(s.x.p, s.h_x.p, (size_t)rows * cols * esz, cudaMemcpyDefault, cin));
             } else if (ldx == cols) {
-                CK(cudaMemcpyAsync(s.x.p, src, (size_t)rows * cols * esz, cudaMemcpyDefault, s.stream));
+                CK(cudaMemcpyAsync(s.x.p, src, (size_t)rows * cols * esz, cudaMemcpyDefault, cin));
             } else {
                 CK(cudaMemcpy2DAsync(s.x.p, (size_t)cols * esz, src, (size_t)ldx * esz, (size_t)cols * esz,
-                                     (size_t)rows, cudaMemcpyDefault, s.stream));
+                                     (size_t)rows, cudaMemcpyDefault, cin));
+            }
+            if (piped) {
+                CK(cudaEventRecord(s.ev_in, cin));
+                CK(cudaStreamWaitEvent(s.stream, s.ev_in, 0));
             }
             ix->stats.h2d_bytes += rows * cols * (int64_t)esz;
             dX = s.x.p;
@@ -1179,11 +1271,17 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
         // the last chunk's second stage has nothing to hide under: it is dealt out over all SMs; the
         // others keep to a few SMs, which costs the following chunk's tensor kernel less
         ix->spread_tail = r0 + rows >= n_q;
+        CK(trace_mark(1, cin));
         rc = run_chunk(ix, s, dX, x_dtype == SKNNR_F32, dld, transformed, rows, row_offset + r0, k,
                        flags, decimals, weights, o_dist, o_idx, o_pred, check_finite);
         if (rc != SKNNR_OK) return rc;
         if (!dev_ptrs) {
-            if (s.tail_pending) CK(cudaStreamWaitEvent(s.stream, s.ev_tail, 0));  // results complete
+            if (piped) {   // the D2H stream picks the results up behind the first stage and the slot's tail
+                CK(cudaEventRecord(s.ev_out, s.stream));
+                CK(cudaStreamWaitEvent(cout, s.ev_out, 0));
+            }
+            if (s.tail_pending) CK(cudaStreamWaitEvent(cout, s.ev_tail, 0));  // results complete
+            CK(trace_mark(2, cout));
             // D2H straight into page-locked caller memory, else into the slot's staging buffer (the
             // pool copies it out when the slot is next visited)
             auto deliver = [&](void *dst, const void *src, size_t bytes, bool stage, PinBuf<unsigned char> &hb) -> cudaError_t {
@@ -1195,11 +1293,16 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
                     s.owed.push_back({dst, hb.p, bytes});
                 }
                 ix->stats.d2h_bytes += (int64_t)bytes;
-                return cudaMemcpyAsync(to, src, bytes, cudaMemcpyDefault, s.stream);
+                return cudaMemcpyAsync(to, src, bytes, cudaMemcpyDefault, cout);
             };
             if (out_dist) CK(deliver(out_dist + r0 * k, o_dist, (size_t)rows * k * 8, stage_dist, s.h_dist));
             if (out_idx) CK(deliver(out_idx + r0 * k, o_idx, (size_t)rows * k * 8, stage_idx, s.h_idx));
             if (o_pred) CK(deliver(out_pred + r0 * ix->n_out, o_pred, (size_t)rows * ix->n_out * 8, stage_pred, s.h_pred));
+            CK(trace_mark(3, cout));
+            if (piped) {   // what finish_slot waits for before the slot's buffers are reused
+                CK(cudaEventRecord(s.ev_last, cout));
+                s.last_pending = true;
+            }
         } else {
             CK(cudaEventRecord(s.ev_last, user_stream));
             s.last_pending = true;
@@ -1207,6 +1310,22 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     }
     if (!dev_ptrs) {
         for (auto &s : ix->slots) CK(ix->finish_slot(s));
+        if (tracing) {
+            fprintf(stderr, "sknnr trace: %zu chunks, chunk %lld rows, %d slots; ms since call start: enqueued(host) started in_arrived results_done delivered\n",
+                    trace.size(), (long long)chunk, n_slots);
+            for (size_t i = 0; i < trace.size(); ++i) {
+                float t[4] = {0, 0, 0, 0};
+                for (int w = 0; w < 4; ++w) {
+                    if (trace[i].e[w]) {
+                        cudaEventElapsedTime(&t[w], trace_t0, trace[i].e[w]);
+                        cudaEventDestroy(trace[i].e[w]);
+                    }
+                }
+                fprintf(stderr, "  chunk %2zu rows %8lld  %7.2f  %7.2f %7.2f %7.2f %7.2f\n", i, (long long)trace[i].rows,
+                        trace[i].host_ms, t[0], t[1], t[2], t[3]);
+            }
+            cudaEventDestroy(trace_t0);
+        }
     } else {
         // results are complete on the caller's stream once both tails have joined it
         for (auto &s : ix->slots)

@@ -92,6 +92,11 @@ __device__ unsigned long long g_tc_counters[8];
 #ifndef SK_TC_JOINT_WIDE
 #define SK_TC_JOINT_WIDE 12
 #endif
+// hit path of a chunk: 0 = every lane runs the predicated parking code of all four octets, 1 = a
+// vote per octet first (octets nobody hits are skipped), 2 = a vote per pair of octets
+#ifndef SK_TC_OCTVOTE
+#define SK_TC_OCTVOTE 1
+#endif
 // jobs between two resolutions of the pending queues (0 = 8 with queues of four octets, 2 with queues of two)
 #ifndef SK_TC_DRAIN_EVERY
 #define SK_TC_DRAIN_EVERY 0
@@ -234,8 +239,22 @@ __device__ __forceinline__ void tc_chunk(const uint32_t (&r)[32], int idb, uint3
     } else {
         if (!__any_sync(SK_FULL, hit)) return;   // vote straight into a predicate
     }
+#if SK_TC_OCTVOTE == 1
+    // which octets hold a hit somewhere in the warp (votes against the threshold on entry: it only
+    // falls inside, so a vote can only be a false alarm); octets without one are skipped, branch uniform
+    unsigned ov[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) ov[o] = __ballot_sync(SK_FULL, g[o] < thr);
+#elif SK_TC_OCTVOTE == 2
+    unsigned ov[4];
+    ov[0] = ov[1] = __ballot_sync(SK_FULL, fminf(g[0], g[1]) < thr);
+    ov[2] = ov[3] = __ballot_sync(SK_FULL, fminf(g[2], g[3]) < thr);
+#endif
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
+#if SK_TC_OCTVOTE
+        if (ov[o] == 0u) continue;
+#endif
         const bool p = g[o] < thr;
         const bool room = pqo < PQ_END;
         SK_CHECK(pqo < PQ_END + ES);
