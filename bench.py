@@ -699,7 +699,7 @@ def bench_c3(a, rank, world, local_rank, dev, stream, lib, L, KNNIndex, barrier,
     return line
 
 
-TC_TRAFFIC_PER_ROW = 152.9e6 / float(1 << 20)     # profiles/r02_search_tc_q.md: 105.6 MB read + 47.3 MB written
+TC_TRAFFIC_PER_ROW = 150.8e6 / float(1 << 20)     # profiles/r02_search_tc_final2.md: 106.0 MB read + 44.8 MB written
 
 
 def bench_c5(a, rank, world, local_rank, dev, stream, lib, L, barrier, timed, peaks, gemm, dist):
