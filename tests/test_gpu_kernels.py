@@ -972,3 +972,52 @@ def test_joint_threshold_rank_adapts_to_crowded_neighbourhoods():
     assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
     assert c0["after_tensor"] > 0.04 * len(Q), c0
     assert c1["after_tensor"] < 0.6 * c0["after_tensor"], (c0, c1)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_pipeline_equals_one_stream_per_chunk(pinned):
+    """Host-buffer calls run as a three-stage pipeline (in-order H2D stream, compute stream, D2H
+    stream; csrc/api.cu).  Many ramped chunks, more chunks than slots, a ragged last chunk, tensor
+    and FP32 engines, a NaN row under the device-side finite check: all bit-equal with the layout
+    that gives every chunk a stream of its own, and a second call on the same index reuses the
+    slots cleanly."""
+    from sknnr_b200._engine import KNNIndex, pinned_empty
+
+    rng = np.random.default_rng(77)
+    for n_ref, d in ((3000, 32), (600, 5)):          # tensor engine / FP32 engine
+        R = rng.standard_normal((n_ref, d))
+        y = rng.standard_normal((n_ref, 3))
+        n_q = 70_001
+        X = rng.standard_normal((n_q, d))
+        if pinned:
+            Xp = pinned_empty((n_q, d))
+            Xp[:] = X
+            X = Xp
+        ix = KNNIndex(R, None, None, None, y)
+        L.set_option("chunk_rows", 4096)
+        L.set_option("stage_rows", 2048)
+        try:
+            res = {}
+            for mode in (0, 1, 1):
+                L.set_option("host_pipeline", mode)
+                out = None
+                if pinned:
+                    out = (pinned_empty((n_q, 6)), pinned_empty((n_q, 6), np.int64), pinned_empty((n_q, 3)))
+                got = ix.query(X, 6, transformed=True, weights="distance", with_pred=True, out=out)
+                if mode in res:
+                    for a, b in zip(res[mode], got):
+                        assert np.array_equal(a, b)
+                res[mode] = [np.array(g) for g in got]
+            for a, b in zip(res[0], res[1]):
+                assert np.array_equal(a, b)
+            Xb = np.array(X)
+            Xb[n_q - 3, 1] = np.nan
+            with pytest.raises(L.NonFiniteInput):
+                ix.query(Xb, 6, transformed=True, check_finite=True)
+            again = ix.query(X, 6, transformed=True, weights="distance", with_pred=True)
+            for a, b in zip(res[1], again):
+                assert np.array_equal(a, b)
+        finally:
+            L.set_option("host_pipeline", 1)
+            L.set_option("chunk_rows", 1 << 20)
+            L.set_option("stage_rows", 1 << 19)
