@@ -7,9 +7,10 @@ Headline workload (BASELINE.json configs[2], "C3"): EuclideanKNNRegressor, 10M q
 50k reference plots x 32 features, k=7, predict(weights="distance") over 8 targets; synthetic
 N(0,1) data with the seeds of BASELINE.md section 3.  One "step" = one pass of the hot path
 over the whole 10M-row query batch of a rank.  N > 1: every rank holds the full reference set
-and its own 10M-row shard (weak scaling); the finishing kernels of every rank store their rows
-straight into rank 0's result arrays over NVLink (CUDA IPC mapping), so the gather is fused
-into the compute and lies inside the timed region.
+and its own 10M-row shard (weak scaling); every rank's rows land in rank 0's result arrays
+(CUDA IPC mapping) over NVLink inside the timed region: as per-chunk copy-engine peer copies
+under the next chunks' kernels (default), or stored by the finishing kernels themselves
+(--gather fused; the mode not chosen is timed right behind the headline as `gather_alt`).
 
 `value`   : device-resident inputs/outputs (queries/s, whole job).
 `e2e`     : the same through the host-buffer C-ABI call, pinned host inputs/outputs, H2D/D2H
@@ -78,12 +79,17 @@ def parse_args():
     ap.add_argument("--host-slots", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="library option for an experiment (sknnr_set_option), repeatable")
+    ap.add_argument("--no-gather-ab", action="store_true", help="N > 1: do not time the other gather mode as well")
     ap.add_argument("--gather", default="auto", choices=["auto", "fused", "copy"],
                     help="N > 1: how a rank's rows reach rank 0's arrays - fused = the finishing kernels store "
                          "over NVLink; copy = per-chunk copy-engine peer copies on the chunk's stream")
     a = ap.parse_args()
     if a.gather == "auto":
-        a.gather = "fused"
+        # measured on 8 GPUs (gpurun_out/bench_8gpu_ab.log): copy 83.4 ms per step against 88.6 fused and
+        # 82.4 on one GPU - the ranks run in step, so seven ranks' finishing kernels store into rank 0 at
+        # once (7 x ~195 GB/s against 900 GB/s of NVLink ingress) while the copy engines spread the same
+        # bytes under the next chunks' search kernels
+        a.gather = "copy"
     if a.only:
         a.no_c4 = a.no_c4 or a.only != "c4"
         a.no_c5 = a.no_c5 or a.only != "c5"
@@ -102,9 +108,11 @@ def config_of(a):
     return {"workload": workload_name(a), "n_ref": a.n_ref, "dim": a.dim, "k": a.k,
             "queries_per_gpu": a.n_queries,
             "l2": f"inputs {a.n_queries * a.dim * 8 / 1e9:.2f} GB per step exceed the 126 MB L2 (no flush needed)",
-            "multi_gpu": "queries sharded, reference set replicated, every rank's finishing kernels store into "
-                         "rank 0's result arrays over NVLink (CUDA IPC) inside the timed region; NCCL carries "
-                         "the barriers and the out-of-band verification gather"}
+            "multi_gpu": "queries sharded, reference set replicated, every rank's results land in rank 0's result "
+                         "arrays over NVLink (CUDA IPC mapping) inside the timed region - per-chunk copy-engine "
+                         "peer copies under the next chunks' kernels (--gather copy, the default) or stores of "
+                         "the finishing kernels themselves (--gather fused, timed beside it as gather_alt); "
+                         "NCCL carries the barriers and the out-of-band verification gather"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -563,6 +571,44 @@ def bench_c3(a, rank, world, local_rank, dev, stream, lib, L, KNNIndex, barrier,
     ms_total = timed(step_timed, a.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = world * n_q * a.steps / (ms_total * 1e-3)
+    barrier()
+    headline_launches = int(index.stats()["kernel_launches"])   # of one headline step (this rank)
+
+    # out-of-band verification of the fused gather: every rank repeats its block into local memory and
+    # NCCL gathers those; rank 0 compares them with what the ranks stored into its arrays over NVLink
+    def verify_gather():
+        loc = [torch.empty((n_q, k), dtype=torch.float64, device=dev), torch.empty((n_q, k), dtype=torch.int64, device=dev),
+               torch.empty((n_q, n_out), dtype=torch.float64, device=dev)]
+        index.query_device(X_dev.data_ptr(), False, n_q, d, k, dist_ptr=loc[0].data_ptr(), idx_ptr=loc[1].data_ptr(),
+                           pred_ptr=loc[2].data_ptr(), weights="distance", row_offset=rank * n_q,
+                           stream=stream.cuda_stream)
+        barrier()
+        ok = True
+        for i, t in enumerate(loc):
+            parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+            dist.gather(t, parts, dst=0)
+            if rank == 0:
+                for r in range(world):
+                    got = shared.to_host(i, r, 4096, np.float64 if i != 1 else np.int64, t.shape[1])
+                    tail = parts[r][:4096].cpu().numpy()
+                    ok = ok and bool(np.array_equal(got, tail))
+            del parts
+        del loc
+        assert rank != 0 or ok, "rows that arrived over NVLink differ from the NCCL-gathered blocks"
+        return ok
+
+    gather_ok = verify_gather() if world > 1 else None
+    # the other way of getting the results to rank 0, timed the same way right behind the headline
+    # (fused: the finishing kernels store over NVLink; copy: every chunk's results leave as copy-engine
+    # peer copies under the next chunks' kernels)
+    gather_alt = None
+    if world > 1 and not a.no_gather_ab:
+        alt = step_device if step_timed is step_copy else step_copy
+        alt()
+        ms_alt = timed(alt, a.steps)
+        gather_alt = {"mode": "fused" if a.gather == "copy" else "copy",
+                      "value": world * n_q * a.steps / (ms_alt * 1e-3), "ms_per_step": ms_alt / a.steps,
+                      "verified": verify_gather()}
 
     # dominant-kernel timing: one more device-resident step; the library brackets every search
     # kernel launch with CUDA events on the launching stream (option "timing") and the stats
@@ -573,29 +619,6 @@ def bench_c3(a, rank, world, local_rank, dev, stream, lib, L, KNNIndex, barrier,
     dev_stats = index.stats()
     cascade = index.cascade_counts()
     search_ms = dev_stats["search_ms"]
-
-    # out-of-band verification of the fused gather: every rank repeats its block into local memory and
-    # NCCL gathers those; rank 0 compares them with what the ranks stored into its arrays over NVLink
-    gather_ok = None
-    if world > 1:
-        loc = [torch.empty((n_q, k), dtype=torch.float64, device=dev), torch.empty((n_q, k), dtype=torch.int64, device=dev),
-               torch.empty((n_q, n_out), dtype=torch.float64, device=dev)]
-        index.query_device(X_dev.data_ptr(), False, n_q, d, k, dist_ptr=loc[0].data_ptr(), idx_ptr=loc[1].data_ptr(),
-                           pred_ptr=loc[2].data_ptr(), weights="distance", row_offset=rank * n_q,
-                           stream=stream.cuda_stream)
-        barrier()
-        gather_ok = True
-        for i, t in enumerate(loc):
-            parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-            dist.gather(t, parts, dst=0)
-            if rank == 0:
-                for r in range(world):
-                    got = shared.to_host(i, r, 4096, np.float64 if i != 1 else np.int64, t.shape[1])
-                    tail = parts[r][:4096].cpu().numpy()
-                    gather_ok = gather_ok and bool(np.array_equal(got, tail))
-            del parts
-        del loc
-        assert rank != 0 or gather_ok, "rows stored over NVLink differ from the NCCL-gathered blocks"
 
     # e2e through the host-buffer call (pinned host in/out, copies inside the timed region)
     e2e = e2e_est = None
@@ -690,10 +713,11 @@ def bench_c3(a, rank, world, local_rank, dev, stream, lib, L, KNNIndex, barrier,
                       traffic_per_row=(TC_TRAFFIC_PER_ROW if d == 32 else None), rows_per_launch=n_q / n_chunks,
                       note=TC_NOTE),
         "hbm": hbm, "cpu_baseline": cpu, "e2e": e2e, "e2e_estimator": e2e_est,
-        "gpu_launches": int(dev_stats["kernel_launches"] * a.steps),
+        "gpu_launches": headline_launches * a.steps,
         "fallback_rows_per_step": int(dev_stats["n_fallback"]), "cascade_rows_per_step": cascade,
-        "fused_gather_verified": gather_ok,
-        "gather": (a.gather if world > 1 else None),
+        "gather_verified": gather_ok,
+        "fused_gather_verified": (gather_ok if a.gather == "fused" else (gather_alt or {}).get("verified")),
+        "gather": (a.gather if world > 1 else None), "gather_alt": gather_alt,
         "clocks": clocks,
     }
     return line
