@@ -118,7 +118,7 @@ int sknnr_device_count(int *count);
  *   "tail_spread" 0/1 the second (FP32) stage of the cascade deals its few rows out over all SMs,
  *                 one warp of 32 rows at a time (default 1; 0 = one CTA per 384 rows)
  *   "host_threads" workers that stage pageable caller buffers through page-locked slot buffers
- *                 (default 0 = min(16, cores / 2); read when the first pageable call starts them)
+ *                 (default 0 = min(16, 3/4 of the cores); read when the first pageable call starts them)
  *   "stage_rows"  rows per chunk of a call with pageable buffers (default 1<<19)
  *   "tc_debug"    timing experiments only (bit 0 skips the hit path, bit 2 skips the tile
  *                 loads: results are wrong)                                             */
