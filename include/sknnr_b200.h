@@ -124,6 +124,12 @@ int sknnr_device_count(int *count);
  *                 loads: results are wrong)                                             */
 int sknnr_set_option(const char *name, int64_t value);
 
+/* The chunk schedule a host-buffer call of n_q rows uses with chunks of chunk_rows (host code only, no
+ * device needed): rows_out[0 .. min(cap, *n_chunks)) = rows per chunk.  From four chunks' worth of rows
+ * up the schedule ramps up (1/4, 1/2, 1, ...) and down (..., 1/2, 1/4): the first chunk's copy in and
+ * the last chunk's copy out overlap no kernel. */
+int sknnr_host_chunk_plan(int64_t n_q, int64_t chunk_rows, int64_t *rows_out, int32_t cap, int32_t *n_chunks);
+
 /* ---- Euclidean-space index: Raw / Euclidean / Mahalanobis / MSN / GNN ------------------
  * Fitted state of one estimator.  The four float transformers are one affine map
  *     Z = ((X - center) / scale) @ proj

@@ -29,7 +29,7 @@ EXPORTS = [
     "sknnr_host_free", "sknnr_measure_fp32_peak", "sknnr_forest_create", "sknnr_forest_destroy",
     "sknnr_forest_apply", "sknnr_hamming_kneighbors_forest", "sknnr_raster_kneighbors",
     "sknnr_hamming_raster_kneighbors_forest", "sknnr_device_alloc", "sknnr_device_free",
-    "sknnr_ipc_export", "sknnr_ipc_open", "sknnr_ipc_close", "sknnr_device_copy",
+    "sknnr_ipc_export", "sknnr_ipc_open", "sknnr_ipc_close", "sknnr_device_copy", "sknnr_host_chunk_plan",
 ]
 
 
@@ -133,6 +133,16 @@ def device_count() -> int:
 
 def set_option(name: str, value: int) -> None:
     check(load().sknnr_set_option(name.encode(), int(value)))
+
+
+def host_chunk_plan(n_q: int, chunk_rows: int = 1 << 20) -> list[int]:
+    """Rows per chunk of a host-buffer call (host code only: works without a device)."""
+    n = C.c_int32(0)
+    lib = load()
+    check(lib.sknnr_host_chunk_plan(C.c_int64(n_q), C.c_int64(chunk_rows), None, 0, C.byref(n)))
+    rows = (C.c_int64 * max(n.value, 1))()
+    check(lib.sknnr_host_chunk_plan(C.c_int64(n_q), C.c_int64(chunk_rows), rows, n.value, C.byref(n)))
+    return [int(rows[i]) for i in range(n.value)]
 
 
 def measure_fp32_peak(device: int = 0) -> float:

@@ -542,6 +542,24 @@ struct CallGuard {
     }
 };
 
+// Rows of chunk `ci` of a call with `left` rows still to go.  Host buffers: the first chunk's H2D copy
+// and the last chunk's D2H copy cannot overlap any kernel, so the stream of chunks ramps up (1/4, 1/2,
+// 1, ...) and down (..., 1/2, 1/4 of `chunk`); the remainder rides in the chunk before the ramp down.
+int64_t next_chunk_rows(int ci, int64_t left, int64_t chunk, bool ramp) {
+    if (!ramp) return std::min(chunk, left);
+    const int64_t q4 = chunk / 4;
+    if (ci == 0) return q4;
+    if (ci == 1) return 2 * q4;
+    if (left > chunk + 3 * q4) return chunk;
+    if (left > 3 * q4) {                                  // leaves 1/2 + 1/4 for the last two
+        const int64_t rows = left - 3 * q4;
+        return rows < q4 ? rows + 2 * q4 : rows;          // (a sliver rides with the half chunk instead)
+    }
+    if (left > q4) return left - q4;
+    return left;
+}
+bool ramp_applies(bool dev_ptrs, int64_t n_q, int64_t chunk) { return !dev_ptrs && n_q >= 4 * chunk && chunk % 1024 == 0; }
+
 int check_query_args(int64_t n_ref, int n_out, int64_t n_q, int k, uint32_t flags, int weights,
                      const void *X, const double *out_pred, int &kk) {
     const bool excl = flags & SKNNR_EXCLUDE_SELF;
@@ -617,6 +635,19 @@ int sknnr_device_count(int *count) {
     int c = 0;
     if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0;
     *count = c;
+    return SKNNR_OK;
+}
+
+int sknnr_host_chunk_plan(int64_t n_q, int64_t chunk_rows, int64_t *rows_out, int32_t cap, int32_t *n_chunks) {
+    if (n_q < 0 || chunk_rows < 256 || !n_chunks || (cap > 0 && !rows_out)) return fail(SKNNR_EINVAL, "bad chunk plan arguments");
+    const int64_t chunk = std::min<int64_t>((chunk_rows + 255) / 256 * 256, (n_q + 255) / 256 * 256);
+    const bool ramp = ramp_applies(false, n_q, chunk);
+    int ci = 0;
+    for (int64_t r0 = 0, rows = 0; r0 < n_q; r0 += rows, ++ci) {
+        rows = next_chunk_rows(ci, n_q - r0, chunk, ramp);
+        if (ci < cap) rows_out[ci] = rows;
+    }
+    *n_chunks = ci;
     return SKNNR_OK;
 }
 
@@ -1175,7 +1206,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
     const int n_slots = dev_ptrs ? 2 : (staged || piped ? std::min<int>(4, (int)g_opt.host_slots) : (int)g_opt.host_slots);
     // Host buffers: the first chunk's H2D copy and the last chunk's D2H copy cannot overlap any
     // kernel, so the stream of chunks ramps up (1/4, 1/2, 1, ...) and down (..., 1/2, 1/4).
-    const bool ramp = !dev_ptrs && n_q >= 4 * chunk && chunk % 1024 == 0;
+    const bool ramp = ramp_applies(dev_ptrs, n_q, chunk);
     int ci = 0;
     int64_t rows = 0;
     // SKNNR_B200_TRACE=1: per-chunk timeline of a host-buffer call on stderr (events on the chunk's stream:
@@ -1196,19 +1227,7 @@ int sknnr_kneighbors(sknnr_index *ix, const void *X, int32_t x_dtype, int64_t n_
         return e != cudaSuccess ? e : cudaEventRecord(trace.back().e[which], st);
     };
     for (int64_t r0 = 0; r0 < n_q; r0 += rows, ++ci) {
-        rows = std::min(chunk, n_q - r0);
-        if (ramp) {
-            const int64_t left = n_q - r0, q4 = chunk / 4;
-            if (ci == 0) rows = q4;
-            else if (ci == 1) rows = 2 * q4;
-            else if (left > chunk + 3 * q4) rows = chunk;
-            else if (left > 3 * q4) {                        // leaves 1/2 + 1/4 for the last two
-                rows = left - 3 * q4;
-                if (rows < q4) rows += 2 * q4;               // (a sliver rides with the half chunk instead)
-            }
-            else if (left > q4) rows = left - q4;
-            else rows = left;
-        }
+        rows = next_chunk_rows(ci, n_q - r0, chunk, ramp);
         // the slots alternate: the tail of chunk c (on its slot's tail stream) overlaps the first
         // stage of chunk c + 1 (other slot's buffers)
         Slot &s = ix->slots[ci % n_slots];

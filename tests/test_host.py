@@ -221,3 +221,27 @@ def test_device_cache_is_outside_the_estimator_and_dies_with_it():
     del t
     gc.collect()
     assert len(_cache._CACHE) == n - 1
+
+
+def test_host_chunk_schedule_ramps_and_covers_every_row():
+    """The chunk schedule of a host-buffer call (csrc/api.cu, next_chunk_rows): every row exactly once,
+    no chunk above the chunk size, a 1/4 - 1/2 ramp at both ends from four chunks' worth of rows up, and
+    no sliver chunk in the middle of a large call."""
+    from sknnr_b200 import _lib as L
+
+    for chunk in (1024, 4096, 1 << 19, 1 << 20):
+        for n_q in (0, 1, 255, 256, 1000, chunk - 1, chunk, chunk + 1, 4 * chunk - 1, 4 * chunk, 4 * chunk + 1,
+                    5 * chunk + 37, 10_000_000, 9 * chunk + 3 * chunk // 4 + 5, 70_001, 12_345_678):
+            plan = L.host_chunk_plan(n_q, chunk)
+            assert sum(plan) == n_q, (n_q, chunk, plan)
+            assert all(0 < r <= chunk for r in plan), (n_q, chunk, plan)
+            if n_q >= 4 * chunk:
+                assert plan[0] == chunk // 4 and plan[1] == chunk // 2, (n_q, chunk, plan[:3])
+                assert plan[-1] <= chunk // 4 and plan[-2] <= chunk // 2 + chunk // 4, (n_q, chunk, plan[-3:])
+                assert min(plan[:-1]) >= chunk // 4, (n_q, chunk, plan)
+                assert all(r == chunk for r in plan[2:-3]), (n_q, chunk, plan)
+            elif n_q > 0:
+                assert plan == [min(chunk, n_q - i) for i in range(0, n_q, chunk)], (n_q, chunk, plan)
+    assert L.host_chunk_plan(10_000_000, 1 << 20) == [262144, 524288] + [1 << 20] * 8 + [562816, 262144]
+    with pytest.raises(ValueError):
+        L.host_chunk_plan(-1, 1 << 20)
