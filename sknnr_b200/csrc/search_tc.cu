@@ -1,19 +1,20 @@
-// Tensor-core engine of the fused distance + top-KC candidate search: tcgen05.mma (kind::tf32)
-// with accumulators in TMEM, operands staged by 1-D TMA bulk copies, selection fused into the
-// TMEM epilogue so the score matrix never leaves the SM.
+// Tensor-core engine of the fused distance + top-KC candidate search: tcgen05.mma (kind::f16, FP16
+// operands, FP32 accumulators in TMEM), operands staged by 1-D TMA bulk copies, selection fused into
+// the TMEM epilogue so the score matrix never leaves the SM.
 //
 // Same role as search_simt.cu (it replaces the dgemm + heap-test hot loop of scikit-learn's
 // EuclideanArgKmin64, $SP/sklearn/metrics/_pairwise_distances_reduction/_argkmin.pyx.tp:401-510)
-// but the contraction runs on the 5th-generation tensor cores.  TF32 scores carry ~1e-3
-// relative error, so this kernel is only ever a FILTER: it returns (at most) the KC best
-// references by approximate score plus a threshold that every reference outside the list is
-// known to reach; refine.cu re-evaluates the survivors in float64 and proves (error bound
-// eps_s = 2^-10) that nothing outside the list can belong to the k nearest; rows it cannot
-// certify are re-searched by the FP32 SIMT engine and, failing that, by the exhaustive float64
-// kernel.
+// but the contraction runs on the 5th-generation tensor cores.  FP16 operands carry 2^-11 relative
+// error each (the 11-bit significand of TF32 at twice its MMA rate), so this kernel is only ever a
+// FILTER: it returns (at most) the KC - 1 best references per stream by approximate score plus a
+// threshold that every reference outside the lists is known to reach; refine.cu re-evaluates the
+// survivors in float64 and proves (error bound eps_s ~ 2^-10) that nothing outside the lists can
+// belong to the k nearest; rows it cannot certify come back to this kernel once (second pass: one
+// stream of 15, every row from the threshold refine proved sufficient, `init_thr`), then go to the
+// FP32 SIMT engine and, failing that, to the exhaustive float64 kernel.
 //
 // One CTA = 256 queries = two M=128 MMA tiles that share every 128-plot reference tile (N=128).  A
-// "job" is one (reference tile, M tile) pair = K/8 tcgen05.mma into one of four 128-column TMEM
+// "job" is one (reference tile, M tile) pair = K/16 tcgen05.mma into one of four 128-column TMEM
 // accumulator slots; jobs run in (tile, M tile) order and job j uses slot j % 4, i.e. every M tile
 // owns two slots and its MMAs run at most one job ahead of its scanners.  19 warps (ns = 2):
 //   TMA producer (1 thread)   bulk copies (cp.async.bulk + mbarrier) of the query image once and of
@@ -24,32 +25,34 @@
 //   16 scanner warps = (column stream p, M tile h, TMEM lane quarter): thread <-> (query, stream).
 //                    Per job a warp waits "slot ready", reads its stream's 64 accumulator columns
 //                    with one tcgen05.ld.x64, hands the slot back BEFORE reducing anything, then per
-//                    32-column chunk: min3 tree -> one vote "did any lane beat its threshold".  If
-//                    so the hit lanes descend the tree in-lane (group of 9 -> triple -> values) and
-//                    append (score, index) to their own candidate column in shared memory with
-//                    branch-free stores; the count of a column lives in the offset of its next free
-//                    slot (power-of-two slot stride).  When a column is nearly full the whole warp
-//                    compacts: every thread sorts its own column in registers (bitonic network),
-//                    keeps the KC smallest and lowers its threshold to the KC-th.  A lane that runs
-//                    out of slots inside one chunk is redone through a cooperative path (publish
-//                    the 32 scores to the warp's scratch line, one score per lane).
+//                    32-column chunk: min3 tree over four octets -> one vote "did any lane beat its
+//                    threshold".  If so, a ballot per octet picks the octets somebody hit, and every
+//                    lane PARKS those of its octets whose minimum beats its threshold (8 raw scores +
+//                    the first index) in its own pending queue in shared memory with predicated
+//                    stores: straight-line code, no cross-lane traffic.  All scanner warps of the CTA
+//                    RESOLVE their queues in the same jobs (every eighth, sooner when a queue is
+//                    nearly full): tc_drain appends the values below the lane's threshold to the
+//                    lane's candidate column, tc_compact (register bitonic network) keeps the entries
+//                    below the KC-th best, lowers the threshold to it and - two streams - to the
+//                    joint rank of both streams' published scores.  A score that cannot be stored
+//                    lowers the threshold to itself instead (always valid, costs a certificate).
 //   All role / slot / barrier values derive from a shuffled (provably warp-uniform) warp index and
 //   live in uniform registers: the scanners have 96 vector registers, 64 of them hold a job.
-//   (ns = 1: one stream of 16 candidates, 8 scanner warps of four chunks, for k (+1) <= 14.)
+//   (ns = 1: one stream of 16 candidates, 8 scanner warps of four chunks, for k (+1) <= 15.)
 //
 // Threshold seeding.  A streaming top-KC pays KC*ln(n_ref/KC) threshold hits per query, almost
 // all of them while the threshold is still loose.  The kernel therefore first runs every
 // `seed_stride`-th reference tile in a min-only mode that keeps 32 group minima per (query, stream)
 // in the still unused candidate column; the KC-th smallest group minimum is an upper bound of the
 // stream's KC-th best score (KC distinct references reach it), so the main pass starts with a
-// threshold close to its final value: ~20 hits per stream instead of ~65.
+// threshold close to its final value: ~18 parked octets per stream instead of ~65 hits.
 //
-// The |r|^2 term is folded into the contraction: each operand gets one extra K block holding
-// (1,1,1,0,..) on the query side and a 3-way TF32 split of |r|^2 on the reference side, so the
-// accumulator is directly s = |r|^2 - 2 q.r.
+// The |r|^2 term is folded into the contraction: each operand gets three extra K elements holding
+// (1,1,1) on the query side and a 3-way FP16 split of sigma^2 |r - mu|^2 on the reference side, so
+// the accumulator is directly s = |r|^2 - 2 q.r.
 //
-// Operand layout (no swizzle, K-major "interleaved" canonical layout): 16-byte K chunks of 4
-// TF32 values, [chunk][row][4]; core matrix = 8 rows x 16 B contiguous, SBO = 128 B between row
+// Operand layout (no swizzle, K-major "interleaved" canonical layout): 16-byte K chunks of 8 FP16
+// values, [chunk][row][8]; core matrix = 8 rows x 16 B contiguous, SBO = 128 B between row
 // groups, LBO = rows * 16 B between K chunks.  The images are pre-arranged in HBM in exactly
 // this order, so a plain bulk copy stages them.
 #include <cstdio>

@@ -8,7 +8,7 @@ namespace sk {
 
 constexpr int TC_SLOTS = 4;                     // TMEM accumulator slots of TC_N columns
 constexpr int TC_GROUPS = 32;                   // seeding: group minima per query
-constexpr uint32_t TC_ROWB = 16;                // bytes of one row of one K chunk (4 TF32)
+constexpr uint32_t TC_ROWB = 16;                // bytes of one row of one K chunk (8 FP16)
 static_assert(TC_N == 128, "epilogue assumes four 32-column chunks per tile");
 static_assert(TC_SLOTS * TC_N == 512, "the accumulator slots fill TMEM");
 
