@@ -85,7 +85,7 @@ def parse_args():
                          "over NVLink; copy = per-chunk copy-engine peer copies on the chunk's stream")
     a = ap.parse_args()
     if a.gather == "auto":
-        # measured on 8 GPUs (gpurun_out/bench_8gpu_ab.log): copy 83.4 ms per step against 88.6 fused and
+        # measured on 8 GPUs (profiles/r02_multi_gpu_gather.md): copy 83.4 ms per step against 88.6 fused and
         # 82.4 on one GPU - the ranks run in step, so seven ranks' finishing kernels store into rank 0 at
         # once (7 x ~195 GB/s against 900 GB/s of NVLink ingress) while the copy engines spread the same
         # bytes under the next chunks' search kernels
