@@ -256,3 +256,44 @@ def test_oracle_matches_installed_reference_on_fresh_random_data(est_name, weigh
     # (a prediction may differ only where the k-th place is an exact tie between duplicated plots)
     assert (~ok).sum() <= 12, int((~ok).sum())
     assert ok[:20].all()                                  # zero-distance rows: indicator weights in both
+
+
+@pytest.mark.parametrize("est_name", ["RFNNRegressor", "GBNNRegressor"])
+def test_hamming_oracle_matches_installed_reference_on_fresh_forests(est_name):
+    """RFNN (equal tree weights) and GBNN (train-improvement weights) of the unmodified reference,
+    fitted NOW on seeded random data: the oracle, given the reference's own node-ID matrices and
+    `hamming_weights_`, must return bit-equal distances (integer compares and one float64 sum in SciPy's
+    order) and tie-aware equal neighbours, for target rows and for the X=None self-query."""
+    sknnr = _installed_reference()
+    if sknnr is None:
+        pytest.skip("oracle/_ref is not installed (run __graft_entry__.build() where /root/reference exists)")
+    rng = np.random.default_rng(7)
+    n_ref, d, k = 250, 5, 5
+    R = rng.standard_normal((n_ref, d))
+    y = np.column_stack([R[:, 0] + 0.3 * rng.standard_normal(n_ref), R[:, 1] * R[:, 2], rng.standard_normal(n_ref)])
+    Q = rng.standard_normal((120, d))
+    kw = dict(n_estimators=12, random_state=3) if est_name == "RFNNRegressor" else dict(n_estimators=8, random_state=3)
+    est = getattr(sknnr, est_name)(n_neighbors=k, **kw).fit(R, y)
+    tr = est.transformer_
+    w = np.asarray(est.hamming_weights_, dtype=np.float64)
+    ids_ref = np.asarray(tr.transform(R)).astype(np.int64)
+    ids_q = np.asarray(tr.transform(Q)).astype(np.int64)
+    assert ids_ref.shape[1] == len(w) and abs(w.sum() - 1.0) < 1e-9
+    if est_name == "GBNNRegressor":
+        assert len(np.unique(w)) > 3   # genuinely unequal weights
+    st = orc.FittedState(kind="hamming", fit_Z=ids_ref, y=y, hamming_w=w)
+    for X, ids in ((Q, ids_q), (None, None)):
+        rd, ri = est.kneighbors(X)
+        od, oi = orc.kneighbors(st, ids, k=k)
+        assert np.array_equal(od, rd)
+        orc.assert_tie_aware_equal(od, oi, rd, ri, rtol=0, atol=0, gap_rtol=0)
+    # few trees = few distinct distances = many exact ties at the k-th place, which the two sides may
+    # break differently (tie-aware check above); the averaging step is compared on the reference's own
+    # neighbours, the whole prediction on the rows where both picked the same ones
+    rd, ri = est.kneighbors(Q)
+    od, oi = orc.kneighbors(st, ids_q, k=k)
+    rp = est.predict(Q)
+    np.testing.assert_allclose(orc.weighted_average(y, ri), rp, rtol=1e-12)
+    same = (oi == ri).all(axis=1)
+    assert same.sum() >= 20
+    np.testing.assert_allclose(orc.predict(st, ids_q, k=k)[same], rp[same], rtol=1e-12)
